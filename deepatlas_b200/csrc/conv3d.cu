@@ -1,0 +1,664 @@
+// conv3d: the 3D convolutions of the segmentation / registration encoder-decoders.
+//
+// Covers nn.Conv3d k3 (stride 1/2, pad 1) and k1 as built by unets.convBlock
+// (lib/network_factory/unets.py:24-39,98,250), modules.convBlock (lib/network_factory/modules.py:48)
+// and the flow head (lib/network_factory/voxel_morph.py:57); nn.ConvTranspose3d k3 s1 p1
+// (unets.py:89-96 via UNet.decoder :124-137) runs through the same kernels with a flipped /
+// transposed weight repack.  The skip concatenations (unets.py:275,157-171; voxel_morph.py:65-82) are never
+// materialised: every kernel takes two channel-planar sources.
+//
+// Layout: planar NCDHW fp32 (the reference's own), W contiguous -> every warp access is a
+// coalesced row segment.  Weights are repacked per call to [cin][tap][cout_pad] so that one
+// thread's output-channel vector is a broadcast LDS.128.
+//
+// Kernels in this file (exact fp32 FFMA; tensor-core variants live in conv3d_mma.cu):
+//   repack_weights_kernel      (Cout,Cin,k^3) | (Cin,Cout,k^3)  ->  [a][tap][b_pad]
+//   conv3d_direct_kernel<KS,CO>     any stride/pad, two sources, bias + optional leaky/ReLU epilogue
+//   conv3d_tiled_kernel<CK,CO>      k3 s1 p1 hot path: smem halo tile, 4 voxels x CO channels per thread
+//   conv3d_dgrad_s2_kernel<CO>      gather form of the stride-2 transposed conv
+//   conv3d_wgrad_kernel<KS,CI,CO>   lane = voxel along W, register accumulators, butterfly reduce
+//   reduce_partials_kernel          fixed-order second stage (deterministic)
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// weight repack:  dst[a][tap'][b_pad]  from src laid out (d0, d1, T).
+//   a_is_dim0: a indexes d0 (else d1);  b indexes the other one, offset by b_off;  flip: tap' = T-1-tap
+// ------------------------------------------------------------------------------------------------
+__global__ void repack_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int d0, int d1, int T,
+                                      int a_is_dim0, int flip, int A, int a_off, int B, int b_off, int Bpad) {
+  const int64_t total = (int64_t)A * T * Bpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i % Bpad);
+    const int t = (int)((i / Bpad) % T);
+    const int a = (int)(i / ((int64_t)Bpad * T));
+    float v = 0.f;
+    if (b < B) {
+      const int ts = flip ? (T - 1 - t) : t;
+      const int i0 = a_is_dim0 ? (a + a_off) : (b + b_off);
+      const int i1 = a_is_dim0 ? (b + b_off) : (a + a_off);
+      v = src[((int64_t)i0 * d1 + i1) * T + ts];
+    }
+    dst[i] = v;
+  }
+}
+
+struct ConvGeom {
+  int N;
+  int C1, C2;          // channels of the two planar sources (C2 may be 0)
+  int Di, Hi, Wi;      // input extent
+  int Do, Ho, Wo;      // output extent
+  int Cout, Cop;       // real / padded output channels (packed weight pitch)
+  int stride, pad;
+  int act;             // 0 none, 1 leaky/relu with slope
+  float slope;
+};
+
+// ------------------------------------------------------------------------------------------------
+// generic direct convolution
+// ------------------------------------------------------------------------------------------------
+constexpr int DIRECT_THREADS = 128;
+constexpr int DIRECT_CC = 8;  // input channels staged per weight chunk
+
+template <int KS, int CO>
+__global__ void __launch_bounds__(DIRECT_THREADS) conv3d_direct_kernel(const float* __restrict__ x1,
+                                                                       const float* __restrict__ x2,
+                                                                       const float* __restrict__ wp,
+                                                                       const float* __restrict__ bias,
+                                                                       float* __restrict__ out, ConvGeom g) {
+  constexpr int T = KS * KS * KS;
+  __shared__ __align__(16) float sw[DIRECT_CC * T * CO];
+  const int n = blockIdx.z, cog = blockIdx.y;
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo, Vi = (int64_t)g.Di * g.Hi * g.Wi;
+  const int64_t v = (int64_t)blockIdx.x * DIRECT_THREADS + threadIdx.x;
+  const bool live = v < Vo;
+  const int xo = (int)(v % g.Wo), yo = (int)((v / g.Wo) % g.Ho), zo = (int)(v / ((int64_t)g.Wo * g.Ho));
+  const int zi0 = zo * g.stride - g.pad, yi0 = yo * g.stride - g.pad, xi0 = xo * g.stride - g.pad;
+  uint32_t mask = 0;
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int kz = t / (KS * KS), ky = (t / KS) % KS, kx = t % KS;
+      const int zi = zi0 + kz, yi = yi0 + ky, xi = xi0 + kx;
+      if (zi >= 0 && zi < g.Di && yi >= 0 && yi < g.Hi && xi >= 0 && xi < g.Wi) mask |= 1u << t;
+    }
+  }
+  const int64_t base = ((int64_t)zi0 * g.Hi + yi0) * g.Wi + xi0;
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  const int Cin = g.C1 + g.C2;
+  for (int c0 = 0; c0 < Cin; c0 += DIRECT_CC) {
+    const int cc = min(DIRECT_CC, Cin - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cc * T * CO; i += DIRECT_THREADS) {
+      const int co = i % CO, rest = i / CO;  // rest = ci_local*T + tap
+      sw[i] = wp[((int64_t)c0 * T + rest) * g.Cop + cog * CO + co];
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int cl = 0; cl < cc; ++cl) {
+      const int ci = c0 + cl;
+      const float* src = (ci < g.C1) ? x1 + ((int64_t)n * g.C1 + ci) * Vi : x2 + ((int64_t)n * g.C2 + (ci - g.C1)) * Vi;
+      src += base;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int kz = t / (KS * KS), ky = (t / KS) % KS, kx = t % KS;
+        const float xv = (mask >> t) & 1u ? __ldg(src + ((int64_t)kz * g.Hi + ky) * g.Wi + kx) : 0.f;
+        const float4* w4 = reinterpret_cast<const float4*>(sw + (cl * T + t) * CO);
+#pragma unroll
+        for (int q = 0; q < CO / 4; ++q) {
+          const float4 w = w4[q];
+          acc[4 * q + 0] = fmaf(xv, w.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv, w.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, w.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, w.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  if (!live) return;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const int co = cog * CO + c;
+    if (co >= g.Cout) break;
+    float r = acc[c] + (bias ? bias[co] : 0.f);
+    if (g.act) r = r > 0.f ? r : r * g.slope;
+    out[((int64_t)n * g.Cout + co) * Vo + v] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiled k3 s1 p1 convolution: output tile 4(z) x 8(y) x 32(x), 256 threads, each thread 4 voxels
+// along x times CO output channels; input halo tile [CK][6][10][36] in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int TZ = 4, TY = 8, TX = 32, VX = 4;
+constexpr int HZ = TZ + 2, HY = TY + 2, HXP = 36;  // halo extents; x pitch padded to a multiple of 4 (>= TX+2)
+constexpr int TILED_THREADS = TZ * TY * (TX / VX);  // 256
+
+template <int CK, int CO>
+__global__ void __launch_bounds__(TILED_THREADS, 2) conv3d_tiled_kernel(const float* __restrict__ x1,
+                                                                        const float* __restrict__ x2,
+                                                                        const float* __restrict__ wp,
+                                                                        const float* __restrict__ bias,
+                                                                        float* __restrict__ out, ConvGeom g,
+                                                                        int tiles_x, int tiles_y) {
+  extern __shared__ __align__(16) float smem[];
+  float* sx = smem;                          // [CK][HZ][HY][HXP]
+  float* sw = smem + CK * HZ * HY * HXP;     // [CK][27][CO]
+  const int n = blockIdx.z, cog = blockIdx.y;
+  int tb = blockIdx.x;
+  const int bx = tb % tiles_x; tb /= tiles_x;
+  const int by = tb % tiles_y;
+  const int bz = tb / tiles_y;
+  const int X0 = bx * TX, Y0 = by * TY, Z0 = bz * TZ;
+  const int tx = threadIdx.x % (TX / VX), ty = (threadIdx.x / (TX / VX)) % TY, tz = threadIdx.x / ((TX / VX) * TY);
+  const int64_t Vi = (int64_t)g.Di * g.Hi * g.Wi;
+
+  float acc[VX][CO];
+#pragma unroll
+  for (int i = 0; i < VX; ++i)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[i][c] = 0.f;
+
+  const int Cin = g.C1 + g.C2;
+  for (int c0 = 0; c0 < Cin; c0 += CK) {
+    const int cc = min(CK, Cin - c0);
+    __syncthreads();
+    // halo fill: rows of TX+2 (=34) floats; global x from X0-1
+    for (int i = threadIdx.x; i < CK * HZ * HY * HXP; i += TILED_THREADS) {
+      const int hx = i % HXP;
+      int r = i / HXP;
+      const int hy = r % HY; r /= HY;
+      const int hz = r % HZ;
+      const int cl = r / HZ;
+      float v = 0.f;
+      const int gx = X0 - 1 + hx, gy = Y0 - 1 + hy, gz = Z0 - 1 + hz;
+      if (cl < cc && hx < TX + 2 && gx >= 0 && gx < g.Wi && gy >= 0 && gy < g.Hi && gz >= 0 && gz < g.Di) {
+        const int ci = c0 + cl;
+        const float* src = (ci < g.C1) ? x1 + ((int64_t)n * g.C1 + ci) * Vi : x2 + ((int64_t)n * g.C2 + (ci - g.C1)) * Vi;
+        v = __ldg(src + ((int64_t)gz * g.Hi + gy) * g.Wi + gx);
+      }
+      sx[i] = v;
+    }
+    for (int i = threadIdx.x; i < CK * 27 * CO; i += TILED_THREADS) {
+      const int co = i % CO, rest = i / CO;
+      sw[i] = (rest < cc * 27) ? wp[((int64_t)c0 * 27 + rest) * g.Cop + cog * CO + co] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int cl = 0; cl < CK; ++cl) {
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float* row = sx + ((cl * HZ + tz + kz) * HY + ty + ky) * HXP + tx * VX;
+          const float4 a = *reinterpret_cast<const float4*>(row);
+          const float2 b = *reinterpret_cast<const float2*>(row + 4);
+          const float in[6] = {a.x, a.y, a.z, a.w, b.x, b.y};
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4* w4 = reinterpret_cast<const float4*>(sw + (cl * 27 + (kz * 3 + ky) * 3 + kx) * CO);
+#pragma unroll
+            for (int q = 0; q < CO / 4; ++q) {
+              const float4 w = w4[q];
+#pragma unroll
+              for (int i = 0; i < VX; ++i) {
+                acc[i][4 * q + 0] = fmaf(in[i + kx], w.x, acc[i][4 * q + 0]);
+                acc[i][4 * q + 1] = fmaf(in[i + kx], w.y, acc[i][4 * q + 1]);
+                acc[i][4 * q + 2] = fmaf(in[i + kx], w.z, acc[i][4 * q + 2]);
+                acc[i][4 * q + 3] = fmaf(in[i + kx], w.w, acc[i][4 * q + 3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  const int z = Z0 + tz, y = Y0 + ty, x = X0 + tx * VX;
+  if (z >= g.Do || y >= g.Ho || x >= g.Wo) return;
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo;
+  const bool vec = (x + VX <= g.Wo) && ((g.Wo & 3) == 0);
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const int co = cog * CO + c;
+    if (co >= g.Cout) break;
+    const float bv = bias ? bias[co] : 0.f;
+    float r[VX];
+#pragma unroll
+    for (int i = 0; i < VX; ++i) {
+      r[i] = acc[i][c] + bv;
+      if (g.act) r[i] = r[i] > 0.f ? r[i] : r[i] * g.slope;
+    }
+    float* o = out + ((int64_t)n * g.Cout + co) * Vo + ((int64_t)z * g.Ho + y) * g.Wo + x;
+    if (vec) {
+      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VX; ++i)
+        if (x + i < g.Wo) o[i] = r[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stride-2 (k3, pad 1) data gradient, gather form:
+//   dX[ci][q] = sum_{co} sum_{k : (q+1-k) even, o=(q+1-k)/2 in range} dY[co][o] * W[co][ci][k]
+// wp packed as [co][tap][ci_pad] (no flip).
+// ------------------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(DIRECT_THREADS) conv3d_dgrad_s2_kernel(const float* __restrict__ dy,
+                                                                         const float* __restrict__ wp,
+                                                                         float* __restrict__ dx, int N, int Cdy,
+                                                                         int Cdx, int Cdxp, int Do, int Ho, int Wo,
+                                                                         int Di, int Hi, int Wi) {
+  __shared__ __align__(16) float sw[DIRECT_CC * 27 * CO];
+  const int n = blockIdx.z, cig = blockIdx.y;
+  const int64_t Vi = (int64_t)Di * Hi * Wi, Vo = (int64_t)Do * Ho * Wo;
+  const int64_t v = (int64_t)blockIdx.x * DIRECT_THREADS + threadIdx.x;
+  const bool live = v < Vi;
+  const int xq = (int)(v % Wi), yq = (int)((v / Wi) % Hi), zq = (int)(v / ((int64_t)Wi * Hi));
+  // per-axis: tap k valid iff (q+1-k) even and 0 <= (q+1-k)/2 < O
+  uint32_t mask = 0;
+  int oz[3], oy[3], ox[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int az = zq + 1 - k, ay = yq + 1 - k, ax = xq + 1 - k;
+    oz[k] = (az >= 0 && !(az & 1) && (az >> 1) < Do) ? (az >> 1) : -1;
+    oy[k] = (ay >= 0 && !(ay & 1) && (ay >> 1) < Ho) ? (ay >> 1) : -1;
+    ox[k] = (ax >= 0 && !(ax & 1) && (ax >> 1) < Wo) ? (ax >> 1) : -1;
+  }
+  if (live) {
+#pragma unroll
+    for (int t = 0; t < 27; ++t)
+      if (oz[t / 9] >= 0 && oy[(t / 3) % 3] >= 0 && ox[t % 3] >= 0) mask |= 1u << t;
+  }
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int c0 = 0; c0 < Cdy; c0 += DIRECT_CC) {
+    const int cc = min(DIRECT_CC, Cdy - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cc * 27 * CO; i += DIRECT_THREADS) {
+      const int co = i % CO, rest = i / CO;
+      sw[i] = wp[((int64_t)c0 * 27 + rest) * Cdxp + cig * CO + co];
+    }
+    __syncthreads();
+    if (!live || mask == 0) continue;
+    for (int cl = 0; cl < cc; ++cl) {
+      const float* src = dy + ((int64_t)n * Cdy + c0 + cl) * Vo;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) {
+        if (!((mask >> t) & 1u)) continue;
+        const float gv = __ldg(src + ((int64_t)oz[t / 9] * Ho + oy[(t / 3) % 3]) * Wo + ox[t % 3]);
+        const float4* w4 = reinterpret_cast<const float4*>(sw + (cl * 27 + t) * CO);
+#pragma unroll
+        for (int q = 0; q < CO / 4; ++q) {
+          const float4 w = w4[q];
+          acc[4 * q + 0] = fmaf(gv, w.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(gv, w.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(gv, w.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(gv, w.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  if (!live) return;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const int ci = cig * CO + c;
+    if (ci >= Cdx) break;
+    dx[((int64_t)n * Cdx + ci) * Vi + v] = acc[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient.  lane = output voxel along W; a warp owns one task = (kz,ky, 4 input channels,
+// 8 output channels) with the three kx taps in registers (96 accumulators) and walks the rows of its
+// region; the accumulators are folded across lanes with a halving butterfly (1 shuffle per value).
+// partials: [region][Cout][Cin_total][T]  (PyTorch weight order, so the second stage writes grad_weight)
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 256;
+constexpr int WG_CI = 4, WG_CO = 8;
+
+template <int NV>
+__device__ __forceinline__ void butterfly_reduce(float (&v)[NV], int lane) {
+  // NV = 32*G values per lane; on exit v[g] (g<G) of lane l holds the warp total of element g*32+l
+  static_assert(NV % 32 == 0, "NV must be a multiple of 32");
+  constexpr int G = NV / 32;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    // fold the 32 values v[g*32 .. g*32+31] in place down to v[g*32]
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float keep = up ? v[g * 32 + i + s] : v[g * 32 + i];
+        const float send = up ? v[g * 32 + i] : v[g * 32 + i + s];
+        v[g * 32 + i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 1; g < G; ++g) v[g] = v[g * 32];
+}
+
+template <int KS>
+__global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  float* __restrict__ partials, int N, int C,
+                                                                  int ci_off, int Cin_total, int Cout, int co_off,
+                                                                  int64_t region_stride, int Di, int Hi,
+                                                                  int Wi, int Do, int Ho, int Wo, int stride, int pad,
+                                                                  int64_t rows_per_region, int64_t total_rows) {
+  constexpr int KX = KS;                 // taps along x held in registers
+  constexpr int T = KS * KS * KS;
+  constexpr int NACC = KX * WG_CI * WG_CO;  // 96 (k3) or 32 (k1)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nCiB = (C + WG_CI - 1) / WG_CI, nCoB = (Cout + WG_CO - 1) / WG_CO;
+  const int ntasks = KS * KS * nCiB * nCoB;
+  const int task = blockIdx.y * (WG_THREADS / 32) + warp;
+  if (task >= ntasks) return;
+  const int cob = task % nCoB;
+  const int cib = (task / nCoB) % nCiB;
+  const int kzy = task / (nCoB * nCiB);
+  const int kz = kzy / KS, ky = kzy % KS;
+  const int xb = (Wo + 31) / 32;
+  const int64_t Vi = (int64_t)Di * Hi * Wi, Vo = (int64_t)Do * Ho * Wo;
+
+  float acc[NACC < 32 ? 32 : NACC];
+#pragma unroll
+  for (int i = 0; i < (NACC < 32 ? 32 : NACC); ++i) acc[i] = 0.f;
+
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_region;
+  const int64_t r1 = min(total_rows, r0 + rows_per_region);
+  for (int64_t rb = r0; rb < r1; ++rb) {
+    const int bxi = (int)(rb % xb);
+    int64_t t = rb / xb;
+    const int yo = (int)(t % Ho); t /= Ho;
+    const int zo = (int)(t % Do);
+    const int n = (int)(t / Do);
+    const int zi = zo * stride + kz - pad, yi = yo * stride + ky - pad;
+    if (zi < 0 || zi >= Di || yi < 0 || yi >= Hi) continue;  // warp-uniform
+    const int xo = bxi * 32 + lane;
+    const bool live = xo < Wo;
+    float dv[WG_CO];
+#pragma unroll
+    for (int c = 0; c < WG_CO; ++c) {
+      const int co = cob * WG_CO + c;
+      dv[c] = (live && co < Cout) ? __ldg(dy + ((int64_t)n * Cout + co) * Vo + ((int64_t)zo * Ho + yo) * Wo + xo) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < WG_CI; ++c) {
+      const int ci = cib * WG_CI + c;
+      const float* xr = x + ((int64_t)n * C + (ci < C ? ci : 0)) * Vi + ((int64_t)zi * Hi + yi) * Wi;
+#pragma unroll
+      for (int kx = 0; kx < KX; ++kx) {
+        const int xi = xo * stride + kx - pad;
+        const float xv = (live && ci < C && xi >= 0 && xi < Wi) ? __ldg(xr + xi) : 0.f;
+#pragma unroll
+        for (int o = 0; o < WG_CO; ++o) acc[(kx * WG_CI + c) * WG_CO + o] = fmaf(xv, dv[o], acc[(kx * WG_CI + c) * WG_CO + o]);
+      }
+    }
+  }
+  butterfly_reduce<(NACC < 32 ? 32 : NACC)>(acc, lane);
+  constexpr int G = (NACC < 32 ? 32 : NACC) / 32;
+  float* pr = partials + (int64_t)blockIdx.x * region_stride;
+#pragma unroll
+  for (int gi = 0; gi < G; ++gi) {
+    const int e = gi * 32 + lane;
+    if (e >= NACC) continue;
+    const int o = e % WG_CO, c = (e / WG_CO) % WG_CI, kx = e / (WG_CO * WG_CI);
+    const int co = cob * WG_CO + o, ci = cib * WG_CI + c;
+    if (co < Cout && ci < C) pr[((int64_t)(co_off + co) * Cin_total + ci_off + ci) * T + (kz * KS + ky) * KS + kx] = acc[gi];
+  }
+}
+
+// out[i] = sum_r partials[r][i]  (fixed order)
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
+                                       float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float acc = 0.f;
+  for (int r = 0; r < nregions; ++r) acc += partials[(int64_t)r * count + i];
+  out[i] = acc;
+}
+
+// per-channel sum over N and space (bias gradient):  out[c] = sum_{n,v} x[n][c][v]
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, int N, int C, int64_t V,
+                                                          float* __restrict__ out) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  double acc = 0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = x + ((int64_t)n * C + c) * V;
+    float a = 0.f;
+    int k = 0;
+    for (int64_t i = threadIdx.x; i < V; i += 256) {
+      a += p[i];
+      if (++k == 64) { acc += (double)a; a = 0.f; k = 0; }
+    }
+    acc += (double)a;
+  }
+  const double b = block_sum<double, 8>(acc, red);
+  if (threadIdx.x == 0) out[c] = (float)b;
+}
+
+inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+inline int64_t pad_to(int64_t v, int m) { return (v + m - 1) / m * m; }
+int g_force_direct = -1;
+inline bool force_direct() {
+  if (g_force_direct < 0) {
+    const char* e = getenv("DA_CONV_IMPL");
+    g_force_direct = (e && strcmp(e, "direct") == 0) ? 1 : 0;
+  }
+  return g_force_direct == 1;
+}
+
+template <int CK, int CO>
+int launch_tiled(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g,
+                 cudaStream_t stream) {
+  const int tiles_x = (g.Wo + TX - 1) / TX, tiles_y = (g.Ho + TY - 1) / TY, tiles_z = (g.Do + TZ - 1) / TZ;
+  const size_t smem = sizeof(float) * (CK * HZ * HY * HXP + CK * 27 * CO);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3d_tiled_kernel<CK, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  dim3 grid(tiles_x * tiles_y * tiles_z, g.Cop / CO, g.N);
+  conv3d_tiled_kernel<CK, CO><<<grid, TILED_THREADS, smem, stream>>>(x1, x2, wp, bias, out, g, tiles_x, tiles_y);
+  return da_check_launch("conv3d_tiled");
+}
+
+template <int KS>
+int launch_direct(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g,
+                  cudaStream_t stream) {
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo;
+  const int CO = (g.Cop % 16 == 0) ? 16 : (g.Cop % 8 == 0 ? 8 : 4);
+  dim3 grid((unsigned)da_cdiv(Vo, DIRECT_THREADS), g.Cop / CO, g.N);
+  if (CO == 16) conv3d_direct_kernel<KS, 16><<<grid, DIRECT_THREADS, 0, stream>>>(x1, x2, wp, bias, out, g);
+  else if (CO == 8) conv3d_direct_kernel<KS, 8><<<grid, DIRECT_THREADS, 0, stream>>>(x1, x2, wp, bias, out, g);
+  else conv3d_direct_kernel<KS, 4><<<grid, DIRECT_THREADS, 0, stream>>>(x1, x2, wp, bias, out, g);
+  return da_check_launch("conv3d_direct");
+}
+
+int run_conv(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g, int KS,
+             cudaStream_t stream) {
+  if (KS == 1) return launch_direct<1>(x1, x2, wp, bias, out, g, stream);
+  const int Cin = g.C1 + g.C2;
+  const bool tiled_ok = !force_direct() && g.stride == 1 && g.pad == 1 && g.Wo >= 16 && (int64_t)g.Do * g.Ho * g.Wo >= 32768;
+  if (tiled_ok) {
+    if (g.Cop % 16 == 0) {
+      if (Cin >= 8) return launch_tiled<8, 16>(x1, x2, wp, bias, out, g, stream);
+      if (Cin >= 3) return launch_tiled<4, 16>(x1, x2, wp, bias, out, g, stream);
+      if (Cin == 2) return launch_tiled<2, 16>(x1, x2, wp, bias, out, g, stream);
+      return launch_tiled<1, 16>(x1, x2, wp, bias, out, g, stream);
+    }
+    if (g.Cop % 8 == 0) {
+      if (Cin >= 8) return launch_tiled<8, 8>(x1, x2, wp, bias, out, g, stream);
+      if (Cin >= 3) return launch_tiled<4, 8>(x1, x2, wp, bias, out, g, stream);
+      if (Cin == 2) return launch_tiled<2, 8>(x1, x2, wp, bias, out, g, stream);
+      return launch_tiled<1, 8>(x1, x2, wp, bias, out, g, stream);
+    }
+    if (Cin >= 8) return launch_tiled<8, 4>(x1, x2, wp, bias, out, g, stream);
+    return launch_tiled<4, 4>(x1, x2, wp, bias, out, g, stream);
+  }
+  return launch_direct<3>(x1, x2, wp, bias, out, g, stream);
+}
+
+inline int repack(const float* src, float* dst, int d0, int d1, int T, int a_is_dim0, int flip, int A, int a_off, int B,
+                  int b_off, int Bpad, cudaStream_t stream) {
+  const int64_t total = (int64_t)A * T * Bpad;
+  int blocks = (int)da_cdiv(total, 256);
+  if (blocks > 4096) blocks = 4096;
+  repack_weights_kernel<<<blocks, 256, 0, stream>>>(src, dst, d0, d1, T, a_is_dim0, flip, A, a_off, B, b_off, Bpad);
+  return da_check_launch("repack_weights");
+}
+
+inline int cpad(int c) { return (int)pad_to(c, c >= 16 ? 16 : (c > 4 ? 8 : 4)); }
+
+constexpr int WG_MAX_REGIONS = 128;
+inline int wg_region_cap(int64_t count) {
+  int64_t r = ((int64_t)32 << 20) / (count > 0 ? count : 1);
+  if (r > WG_MAX_REGIONS) r = WG_MAX_REGIONS;
+  if (r < 4) r = 4;
+  return (int)r;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------------
+
+// Kernel selection for k3 s1 p1 convolutions: 0 = automatic (tiled where it applies), 1 = always the generic
+// direct kernel (used by the parity tests to cross-check the two implementations).  Also settable through the
+// environment variable DA_CONV_IMPL=direct before the first call.
+DA_API int da_set_conv_impl(int impl) {
+  DA_REQUIRE(impl == 0 || impl == 1, "da_set_conv_impl: impl must be 0 (auto) or 1 (direct)");
+  g_force_direct = impl;
+  return DA_OK;
+}
+
+// workspace for da_conv3d_fwd / da_conv3d_dgrad: one packed weight copy
+DA_API int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks) {
+  const int m = Cin > Cout ? Cin : Cout;
+  return (int64_t)sizeof(float) * (int64_t)m * ks * ks * ks * cpad(m) + 256;
+}
+DA_API int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
+  const int64_t count = (int64_t)Cin * Cout * ks * ks * ks;
+  return (int64_t)sizeof(float) * wg_region_cap(count) * count + 256;
+}
+
+// Forward.  x1 [N,C1,Di,Hi,Wi], x2 [N,C2,...] or null (C2=0): the conv sees cat(x1,x2) along channels.
+// weight: transposed==0 -> nn.Conv3d layout (Cout, C1+C2, k,k,k); transposed==1 -> nn.ConvTranspose3d layout
+// (C1+C2, Cout, k,k,k), only k3 s1 p1 (equivalent to a conv with the flipped kernel).
+// bias nullable.  act: 0 none, 1 leaky-relu(slope) fused (slope 0 = ReLU).  out [N,Cout,Do,Ho,Wo].
+DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed,
+                         const float* bias, float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride,
+                         int pad, int act, float slope, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(x1 && weight && out && workspace, "da_conv3d_fwd: null pointer");
+  DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_fwd: unsupported kernel size %d (1 or 3)", ks);
+  DA_REQUIRE(stride == 1 || stride == 2, "da_conv3d_fwd: unsupported stride %d", stride);
+  DA_REQUIRE(!transposed || (ks == 3 && stride == 1 && pad == 1), "da_conv3d_fwd: transposed only for k3 s1 p1");
+  DA_REQUIRE((C2 == 0) == (x2 == nullptr), "da_conv3d_fwd: x2/C2 mismatch");
+  const int Cin = C1 + C2, T = ks * ks * ks;
+  if (workspace_bytes < da_conv3d_pack_bytes(Cin, Cout, ks)) { da_set_error("da_conv3d_fwd: workspace too small"); return DA_ERR_WORKSPACE; }
+  ConvGeom g{N, C1, C2, Di, Hi, Wi, conv_out(Di, ks, stride, pad), conv_out(Hi, ks, stride, pad), conv_out(Wi, ks, stride, pad),
+             Cout, cpad(Cout), stride, pad, act, slope};
+  float* wp = (float*)workspace;
+  int rc = transposed ? repack(weight, wp, Cin, Cout, T, 1, 1, Cin, 0, Cout, 0, g.Cop, stream)
+                      : repack(weight, wp, Cout, Cin, T, 0, 0, Cin, 0, Cout, 0, g.Cop, stream);
+  if (rc) return rc;
+  return run_conv(x1, x2, wp, bias, out, g, ks, stream);
+}
+
+// Data gradient for one source: dx [N,Cdx,Di,Hi,Wi] = gradient w.r.t. channels [ci_off, ci_off+Cdx) of the conv input.
+// dy [N,Cout,Do,Ho,Wo].  Same weight/transposed convention as forward (Cin_total = all input channels of the layer).
+DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed, float* dx, int N, int Cin_total,
+                           int ci_off, int Cdx, int Cout, int Di, int Hi, int Wi, int ks, int stride, int pad,
+                           void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(dy && weight && dx && workspace, "da_conv3d_dgrad: null pointer");
+  DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_dgrad: unsupported kernel size %d", ks);
+  DA_REQUIRE(stride == 1 || (stride == 2 && ks == 3 && pad == 1 && !transposed), "da_conv3d_dgrad: unsupported stride/kernel");
+  const int T = ks * ks * ks;
+  if (workspace_bytes < da_conv3d_pack_bytes(Cin_total, Cout, ks)) { da_set_error("da_conv3d_dgrad: workspace too small"); return DA_ERR_WORKSPACE; }
+  const int Do = conv_out(Di, ks, stride, pad), Ho = conv_out(Hi, ks, stride, pad), Wo = conv_out(Wi, ks, stride, pad);
+  float* wp = (float*)workspace;
+  const int Cp = cpad(Cdx);
+  if (stride == 1) {
+    // dgrad = conv of dy (Cout channels) with [co][flip tap][ci]; for a transposed layer: no flip, dims swapped
+    int rc = transposed ? repack(weight, wp, Cin_total, Cout, T, 0, 0, Cout, 0, Cdx, ci_off, Cp, stream)
+                        : repack(weight, wp, Cout, Cin_total, T, 1, 1, Cout, 0, Cdx, ci_off, Cp, stream);
+    if (rc) return rc;
+    ConvGeom g{N, Cout, 0, Do, Ho, Wo, Di, Hi, Wi, Cdx, Cp, 1, ks == 3 ? 1 : 0, 0, 0.f};
+    DA_REQUIRE(ks == 1 || pad == 1, "da_conv3d_dgrad: k3 needs pad 1");
+    return run_conv(dy, nullptr, wp, nullptr, dx, g, ks, stream);
+  }
+  int rc = repack(weight, wp, Cout, Cin_total, T, 1, 0, Cout, 0, Cdx, ci_off, Cp, stream);
+  if (rc) return rc;
+  const int CO = (Cp % 16 == 0) ? 16 : (Cp % 8 == 0 ? 8 : 4);
+  dim3 grid((unsigned)da_cdiv((int64_t)Di * Hi * Wi, DIRECT_THREADS), Cp / CO, N);
+  if (CO == 16) conv3d_dgrad_s2_kernel<16><<<grid, DIRECT_THREADS, 0, stream>>>(dy, wp, dx, N, Cout, Cdx, Cp, Do, Ho, Wo, Di, Hi, Wi);
+  else if (CO == 8) conv3d_dgrad_s2_kernel<8><<<grid, DIRECT_THREADS, 0, stream>>>(dy, wp, dx, N, Cout, Cdx, Cp, Do, Ho, Wo, Di, Hi, Wi);
+  else conv3d_dgrad_s2_kernel<4><<<grid, DIRECT_THREADS, 0, stream>>>(dy, wp, dx, N, Cout, Cdx, Cp, Do, Ho, Wo, Di, Hi, Wi);
+  return da_check_launch("conv3d_dgrad_s2");
+}
+
+// Weight gradient (+ optional bias gradient).  grad_weight has the layer's own layout
+// ((Cout,Cin,k^3), or (Cin,Cout,k^3) when transposed).  x2 may be null.
+DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
+                           float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
+                           int stride, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(x1 && dy && grad_weight && workspace, "da_conv3d_wgrad: null pointer");
+  DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_wgrad: unsupported kernel size %d", ks);
+  DA_REQUIRE(!transposed || (ks == 3 && stride == 1 && pad == 1), "da_conv3d_wgrad: transposed only for k3 s1 p1");
+  const int Cin = C1 + C2, T = ks * ks * ks;
+  if (workspace_bytes < da_conv3d_wgrad_workspace_bytes(Cin, Cout, ks)) { da_set_error("da_conv3d_wgrad: workspace too small"); return DA_ERR_WORKSPACE; }
+  const int Do = conv_out(Di, ks, stride, pad), Ho = conv_out(Hi, ks, stride, pad), Wo = conv_out(Wi, ks, stride, pad);
+  float* partials = (float*)workspace;
+  const int64_t count = (int64_t)Cin * Cout * T;
+  const int64_t total_rows = (int64_t)N * Do * Ho * ((Wo + 31) / 32);
+  const int cap = wg_region_cap(count);
+  int nregions = (int)(total_rows < cap ? total_rows : cap);
+  if (nregions < 1) nregions = 1;
+  const int64_t rpr = da_cdiv(total_rows, nregions);
+  nregions = (int)da_cdiv(total_rows, rpr);
+  // kernel computes  P[co_off+o][ci_off+i][k] = sum_p xin[i][p*s+k-pad] * gout[o][p]
+  auto launch = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off) -> int {
+    const int ntasks = ks * ks * ((C + WG_CI - 1) / WG_CI) * ((Cout_ + WG_CO - 1) / WG_CO);
+    dim3 grid(nregions, (ntasks + WG_THREADS / 32 - 1) / (WG_THREADS / 32));
+    if (ks == 3)
+      conv3d_wgrad_kernel<3><<<grid, WG_THREADS, 0, stream>>>(xin, gout, partials, N, C, ci_off, Cin_total_, Cout_, co_off, count, Di, Hi, Wi, Do, Ho, Wo, stride, pad, rpr, total_rows);
+    else
+      conv3d_wgrad_kernel<1><<<grid, WG_THREADS, 0, stream>>>(xin, gout, partials, N, C, ci_off, Cin_total_, Cout_, co_off, count, Di, Hi, Wi, Do, Ho, Wo, stride, pad, rpr, total_rows);
+    return da_check_launch("conv3d_wgrad");
+  };
+  int rc;
+  if (!transposed) {
+    rc = launch(x1, C1, 0, Cin, dy, Cout, 0);
+    if (!rc && C2) rc = launch(x2, C2, C1, Cin, dy, Cout, 0);
+  } else {
+    // transposed (k3 s1 p1): dWt[ci][co][k] = sum_q x[ci][q] * dy[co][q+k-1]: the same kernel with the operands
+    // swapped ("input" = dy with Cout channels, "outgrad" = x_k); source 2 rows start at ci = C1.
+    rc = launch(dy, Cout, 0, Cout, x1, C1, 0);
+    if (!rc && C2) rc = launch(dy, Cout, 0, Cout, x2, C2, C1);
+  }
+  if (rc) return rc;
+  reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
+  rc = da_check_launch("conv3d_wgrad/reduce");
+  if (rc) return rc;
+  if (grad_bias) {
+    channel_sum_kernel<<<Cout, 256, 0, stream>>>(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias);
+    rc = da_check_launch("conv3d_wgrad/bias");
+  }
+  return rc;
+}
+
+// out[c] = sum over batch and space of x[n][c][:]
+DA_API int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, cudaStream_t stream) {
+  DA_REQUIRE(x && out, "da_channel_sum: null pointer");
+  channel_sum_kernel<<<C, 256, 0, stream>>>(x, N, C, V, out);
+  return da_check_launch("da_channel_sum");
+}

@@ -1,0 +1,284 @@
+// deconv_k2s2: nn.ConvTranspose3d(kernel 2, stride 2) of unets.deconvBlock
+// (lib/network_factory/unets.py:42-58, used at :240-241 and UNet.dc9/dc6/dc3 :88,91,94).
+//
+//   out[co][2z+a][2y+b][2x+c] = bias[co] + sum_ci x[ci][z][y][x] * W[ci][co][a][b][c]
+// i.e. eight independent 1x1 convolutions interleaved in space.  The output is 8x the input, so the op is
+// write-bound (AI 14-28 FLOP/B).  One thread owns two adjacent input voxels along W
+// (= four adjacent output voxels -> float4 stores) and four output channels; the weight layout
+// (Cin,Cout,2,2,2) is already [ci][co][pos], so no repack is needed.
+#include "common.cuh"
+
+namespace {
+
+constexpr int DC_THREADS = 128;
+constexpr int DC_CC = 32;  // channels staged per smem chunk
+
+// grid (ceil(D*H*ceil(W/2)/128), ceil(Cout/4), N)
+__global__ void __launch_bounds__(DC_THREADS) deconv_k2s2_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, float* __restrict__ out,
+                                                                     int Cin, int Cout, int D, int H, int W) {
+  __shared__ __align__(16) float sw[DC_CC * 32];  // [ci_local][co 4][pos 8]
+  const int n = blockIdx.z, co0 = blockIdx.y * 4;
+  const int W2 = (W + 1) / 2;
+  const int64_t pairs = (int64_t)D * H * W2, V = (int64_t)D * H * W;
+  const int64_t p = (int64_t)blockIdx.x * DC_THREADS + threadIdx.x;
+  const bool live = p < pairs;
+  const int xt = (int)(p % W2), y = (int)((p / W2) % H), z = (int)(p / ((int64_t)W2 * H));
+  const int x0 = 2 * xt;
+  const bool two = x0 + 1 < W;
+  const int64_t vin = ((int64_t)z * H + y) * W + x0;
+  float acc[2][4][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[i][c][k] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += DC_CC) {
+    const int cc = min(DC_CC, Cin - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cc * 32; i += DC_THREADS) {
+      const int cl = i / 32, r = i % 32, co = co0 + r / 8;
+      sw[i] = co < Cout ? w[((int64_t)(c0 + cl) * Cout + co) * 8 + (r % 8)] : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int cl = 0; cl < cc; ++cl) {
+      const float* px = x + ((int64_t)n * Cin + c0 + cl) * V + vin;
+      const float xa = __ldg(px), xb = two ? __ldg(px + 1) : 0.f;
+      const float4* w4 = reinterpret_cast<const float4*>(sw + cl * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 wv = w4[q];
+        const int c = q >> 1, k = (q & 1) * 4;
+        acc[0][c][k + 0] = fmaf(xa, wv.x, acc[0][c][k + 0]); acc[1][c][k + 0] = fmaf(xb, wv.x, acc[1][c][k + 0]);
+        acc[0][c][k + 1] = fmaf(xa, wv.y, acc[0][c][k + 1]); acc[1][c][k + 1] = fmaf(xb, wv.y, acc[1][c][k + 1]);
+        acc[0][c][k + 2] = fmaf(xa, wv.z, acc[0][c][k + 2]); acc[1][c][k + 2] = fmaf(xb, wv.z, acc[1][c][k + 2]);
+        acc[0][c][k + 3] = fmaf(xa, wv.w, acc[0][c][k + 3]); acc[1][c][k + 3] = fmaf(xb, wv.w, acc[1][c][k + 3]);
+      }
+    }
+  }
+  if (!live) return;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t Vo = 8 * V;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int co = co0 + c;
+    if (co >= Cout) break;
+    const float bv = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int ab = 0; ab < 4; ++ab) {
+      const int a = ab >> 1, b = ab & 1;
+      float* o = out + ((int64_t)n * Cout + co) * Vo + ((int64_t)(2 * z + a) * Ho + (2 * y + b)) * Wo + 2 * x0;
+      const float r0 = acc[0][c][ab * 2] + bv, r1 = acc[0][c][ab * 2 + 1] + bv;
+      const float r2 = acc[1][c][ab * 2] + bv, r3 = acc[1][c][ab * 2 + 1] + bv;
+      if (two && (W & 1) == 0) {
+        *reinterpret_cast<float4*>(o) = make_float4(r0, r1, r2, r3);
+      } else {
+        o[0] = r0; o[1] = r1;
+        if (two) { o[2] = r2; o[3] = r3; }
+      }
+    }
+  }
+}
+
+// dX[ci][v] = sum_co sum_pos dY[co][2v+pos] * W[ci][co][pos];  grid (pairs/128, ceil(Cin/4), N)
+__global__ void __launch_bounds__(DC_THREADS) deconv_k2s2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                                       float* __restrict__ dx, int Cin, int Cout, int D, int H,
+                                                                       int W) {
+  __shared__ __align__(16) float sw[DC_CC * 32];  // [co_local][ci 4][pos 8]
+  const int n = blockIdx.z, ci0 = blockIdx.y * 4;
+  const int W2 = (W + 1) / 2;
+  const int64_t pairs = (int64_t)D * H * W2, V = (int64_t)D * H * W;
+  const int64_t p = (int64_t)blockIdx.x * DC_THREADS + threadIdx.x;
+  const bool live = p < pairs;
+  const int xt = (int)(p % W2), y = (int)((p / W2) % H), z = (int)(p / ((int64_t)W2 * H));
+  const int x0 = 2 * xt;
+  const bool two = x0 + 1 < W;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t Vo = 8 * V;
+  float acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (int c0 = 0; c0 < Cout; c0 += DC_CC) {
+    const int cc = min(DC_CC, Cout - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cc * 32; i += DC_THREADS) {
+      const int cl = i / 32, r = i % 32, ci = ci0 + r / 8;
+      sw[i] = ci < Cin ? w[((int64_t)ci * Cout + c0 + cl) * 8 + (r % 8)] : 0.f;
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int cl = 0; cl < cc; ++cl) {
+      const float* pg = dy + ((int64_t)n * Cout + c0 + cl) * Vo;
+      float g[2][8];
+#pragma unroll
+      for (int ab = 0; ab < 4; ++ab) {
+        const float* q = pg + ((int64_t)(2 * z + (ab >> 1)) * Ho + (2 * y + (ab & 1))) * Wo + 2 * x0;
+        if (two && (W & 1) == 0) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+          g[0][ab * 2] = v.x; g[0][ab * 2 + 1] = v.y; g[1][ab * 2] = v.z; g[1][ab * 2 + 1] = v.w;
+        } else {
+          g[0][ab * 2] = q[0]; g[0][ab * 2 + 1] = q[1];
+          g[1][ab * 2] = two ? q[2] : 0.f; g[1][ab * 2 + 1] = two ? q[3] : 0.f;
+        }
+      }
+      const float* ws = sw + cl * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[0][c] = fmaf(g[0][k], ws[c * 8 + k], acc[0][c]);
+          acc[1][c] = fmaf(g[1][k], ws[c * 8 + k], acc[1][c]);
+        }
+    }
+  }
+  if (!live) return;
+  const int64_t vin = ((int64_t)z * H + y) * W + x0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int ci = ci0 + c;
+    if (ci >= Cin) break;
+    float* o = dx + ((int64_t)n * Cin + ci) * V + vin;
+    o[0] = acc[0][c];
+    if (two) o[1] = acc[1][c];
+  }
+}
+
+// dW[ci][co][pos] = sum_{n,v} x[ci][v] * dY[co][2v+pos].  lane = input voxel along W; warp task = (4 ci, 2 co).
+constexpr int DW_THREADS = 256;
+__global__ void __launch_bounds__(DW_THREADS) deconv_k2s2_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                       float* __restrict__ partials, int N, int Cin, int Cout,
+                                                                       int D, int H, int W, int64_t rows_per_region,
+                                                                       int64_t total_rows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nCiB = (Cin + 3) / 4, nCoB = (Cout + 1) / 2;
+  const int task = blockIdx.y * (DW_THREADS / 32) + warp;
+  if (task >= nCiB * nCoB) return;
+  const int cob = task % nCoB, cib = task / nCoB;
+  const int xb = (W + 31) / 32;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const int64_t V = (int64_t)D * H * W, Vo = 8 * V;
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_region, r1 = min(total_rows, r0 + rows_per_region);
+  for (int64_t rb = r0; rb < r1; ++rb) {
+    const int bxi = (int)(rb % xb);
+    int64_t t = rb / xb;
+    const int y = (int)(t % H); t /= H;
+    const int z = (int)(t % D);
+    const int n = (int)(t / D);
+    const int xi = bxi * 32 + lane;
+    const bool live = xi < W;
+    float xv[4], g[2][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int ci = cib * 4 + c;
+      xv[c] = (live && ci < Cin) ? __ldg(x + ((int64_t)n * Cin + ci) * V + ((int64_t)z * H + y) * W + xi) : 0.f;
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const int co = cob * 2 + o;
+#pragma unroll
+      for (int ab = 0; ab < 4; ++ab) {
+        float2 v = make_float2(0.f, 0.f);
+        if (live && co < Cout)
+          v = __ldg(reinterpret_cast<const float2*>(dy + ((int64_t)n * Cout + co) * Vo +
+                                                    ((int64_t)(2 * z + (ab >> 1)) * Ho + (2 * y + (ab & 1))) * Wo + 2 * xi));
+        g[o][ab * 2] = v.x; g[o][ab * 2 + 1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[(c * 2 + o) * 8 + k] = fmaf(xv[c], g[o][k], acc[(c * 2 + o) * 8 + k]);
+  }
+  // halving butterfly: 2 groups of 32
+#pragma unroll
+  for (int gI = 0; gI < 2; ++gI) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float keep = up ? acc[gI * 32 + i + s] : acc[gI * 32 + i];
+        const float send = up ? acc[gI * 32 + i] : acc[gI * 32 + i + s];
+        acc[gI * 32 + i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+  }
+  float* pr = partials + (int64_t)blockIdx.x * Cin * Cout * 8;
+#pragma unroll
+  for (int gI = 0; gI < 2; ++gI) {
+    const int e = gI * 32 + lane;
+    const int k = e % 8, o = (e / 8) % 2, c = e / 16;
+    const int ci = cib * 4 + c, co = cob * 2 + o;
+    if (ci < Cin && co < Cout) pr[((int64_t)ci * Cout + co) * 8 + k] = acc[gI * 32];
+  }
+}
+
+__global__ void dc_reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float acc = 0.f;
+  for (int r = 0; r < nregions; ++r) acc += partials[(int64_t)r * count + i];
+  out[i] = acc;
+}
+
+constexpr int DC_MAX_REGIONS = 64;
+inline int dc_region_cap(int64_t count) {
+  int64_t r = ((int64_t)16 << 20) / (count > 0 ? count : 1);
+  if (r > DC_MAX_REGIONS) r = DC_MAX_REGIONS;
+  if (r < 4) r = 4;
+  return (int)r;
+}
+
+}  // namespace
+
+extern "C" int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, cudaStream_t stream);
+
+DA_API int64_t da_deconv_k2s2_wgrad_workspace_bytes(int Cin, int Cout) {
+  const int64_t count = (int64_t)Cin * Cout * 8;
+  return (int64_t)sizeof(float) * dc_region_cap(count) * count + 256;
+}
+
+// x [N,Cin,D,H,W]; weight (Cin,Cout,2,2,2); out [N,Cout,2D,2H,2W]
+DA_API int da_deconv_k2s2_fwd(const float* x, const float* weight, const float* bias, float* out, int N, int Cin, int Cout,
+                              int D, int H, int W, cudaStream_t stream) {
+  DA_REQUIRE(x && weight && out, "da_deconv_k2s2_fwd: null pointer");
+  const int64_t pairs = (int64_t)D * H * ((W + 1) / 2);
+  dim3 grid((unsigned)da_cdiv(pairs, DC_THREADS), (Cout + 3) / 4, N);
+  deconv_k2s2_fwd_kernel<<<grid, DC_THREADS, 0, stream>>>(x, weight, bias, out, Cin, Cout, D, H, W);
+  return da_check_launch("da_deconv_k2s2_fwd");
+}
+
+DA_API int da_deconv_k2s2_dgrad(const float* dy, const float* weight, float* dx, int N, int Cin, int Cout, int D, int H, int W,
+                                cudaStream_t stream) {
+  DA_REQUIRE(dy && weight && dx, "da_deconv_k2s2_dgrad: null pointer");
+  const int64_t pairs = (int64_t)D * H * ((W + 1) / 2);
+  dim3 grid((unsigned)da_cdiv(pairs, DC_THREADS), (Cin + 3) / 4, N);
+  deconv_k2s2_dgrad_kernel<<<grid, DC_THREADS, 0, stream>>>(dy, weight, dx, Cin, Cout, D, H, W);
+  return da_check_launch("da_deconv_k2s2_dgrad");
+}
+
+DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N, int Cin, int Cout,
+                                int D, int H, int W, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(x && dy && grad_weight && workspace, "da_deconv_k2s2_wgrad: null pointer");
+  if (workspace_bytes < da_deconv_k2s2_wgrad_workspace_bytes(Cin, Cout)) { da_set_error("da_deconv_k2s2_wgrad: workspace too small"); return DA_ERR_WORKSPACE; }
+  const int64_t count = (int64_t)Cin * Cout * 8;
+  const int64_t total_rows = (int64_t)N * D * H * ((W + 31) / 32);
+  const int cap = dc_region_cap(count);
+  int nregions = (int)(total_rows < cap ? total_rows : cap);
+  const int64_t rpr = da_cdiv(total_rows, nregions);
+  nregions = (int)da_cdiv(total_rows, rpr);
+  const int ntasks = ((Cin + 3) / 4) * ((Cout + 1) / 2);
+  dim3 grid(nregions, (ntasks + DW_THREADS / 32 - 1) / (DW_THREADS / 32));
+  deconv_k2s2_wgrad_kernel<<<grid, DW_THREADS, 0, stream>>>(x, dy, (float*)workspace, N, Cin, Cout, D, H, W, rpr, total_rows);
+  int rc = da_check_launch("da_deconv_k2s2_wgrad");
+  if (rc) return rc;
+  dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
+  rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
+  if (rc || !grad_bias) return rc;
+  return da_channel_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, stream);
+}

@@ -1,0 +1,349 @@
+// Batch-norm / activation / pooling / nearest-upsampling kernels of the encoder-decoders.
+//
+//   nn.BatchNorm3d, train mode with batch 1  (lib/network_factory/unets.py:31,51,116,130)
+//   nn.LeakyReLU(0.01) / nn.ReLU             (unets.py:5-6,32 ; lib/network_factory/modules.py:58)
+//   nn.MaxPool3d(2)                          (unets.py:84-86,230)  first-maximum tie rule kept
+//   F.interpolate(size=) default 'nearest'   (lib/network_factory/voxel_morph.py:72-80)
+// All are HBM-bound streaming kernels over planar NCDHW fp32; reductions are shuffle trees with a
+// fixed-order fp64 second stage (deterministic).
+#include "common.cuh"
+
+namespace {
+
+constexpr int BN_THREADS = 256;
+constexpr int BN_SPLITS = 32;  // blocks per channel for the statistics passes
+
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) { return (act && z <= 0.f) ? z * slope : z; }
+__device__ __forceinline__ float act_grad(float z, int act, float slope) { return (act && z <= 0.f) ? slope : 1.f; }
+
+// partials [C][BN_SPLITS][2] (sum, sumsq) in fp64
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t V,
+                                                              double* __restrict__ partials) {
+  __shared__ double red[BN_THREADS / 32];
+  const int c = blockIdx.x, s = blockIdx.y;
+  const int64_t chunk = da_cdiv(V, BN_SPLITS);
+  double a1 = 0, a2 = 0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = x + ((int64_t)n * C + c) * V;
+    const int64_t lo = (int64_t)s * chunk, hi = min(V, lo + chunk);
+    float f1 = 0.f, f2 = 0.f;
+    int k = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
+      const float v = p[i];
+      f1 += v; f2 = fmaf(v, v, f2);
+      if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+    }
+    a1 += (double)f1; a2 += (double)f2;
+  }
+  const double b1 = block_sum<double, BN_THREADS / 32>(a1, red);
+  const double b2 = block_sum<double, BN_THREADS / 32>(a2, red);
+  if (threadIdx.x == 0) {
+    partials[((int64_t)c * BN_SPLITS + s) * 2 + 0] = b1;
+    partials[((int64_t)c * BN_SPLITS + s) * 2 + 1] = b2;
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ partials, int C, double M, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0, s2 = 0;
+  for (int s = 0; s < BN_SPLITS; ++s) {
+    s1 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 0];
+    s2 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 1];
+  }
+  const double mu = s1 / M;
+  double var = s2 / M - mu * mu;
+  if (var < 0) var = 0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
+  if (running_var) {
+    const double unbiased = M > 1 ? var * M / (M - 1) : var;
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  }
+}
+
+// y = act((x - mean) * invstd * gamma + beta); grid (blocks, C, N)
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                         const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int C, int64_t V, int act,
+                                                         float slope, float* __restrict__ y) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  const int64_t base = ((int64_t)n * C + c) * V;
+  const float4* x4 = reinterpret_cast<const float4*>(x + base);
+  float4* y4 = reinterpret_cast<float4*>(y + base);
+  const bool vec = ((V & 3) == 0);
+  if (vec) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < V / 4; i += (int64_t)gridDim.x * 256) {
+      float4 v = x4[i];
+      v.x = act_fwd((v.x - mu) * is * ga + be, act, slope);
+      v.y = act_fwd((v.y - mu) * is * ga + be, act, slope);
+      v.z = act_fwd((v.z - mu) * is * ga + be, act, slope);
+      v.w = act_fwd((v.w - mu) * is * ga + be, act, slope);
+      y4[i] = v;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < V; i += (int64_t)gridDim.x * 256)
+      y[base + i] = act_fwd((x[base + i] - mu) * is * ga + be, act, slope);
+  }
+}
+
+// backward statistics: s1 = sum g, s2 = sum g*xhat with g = dy * act'(z)
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  int N, int C, int64_t V, int act, float slope,
+                                                                  double* __restrict__ partials) {
+  __shared__ double red[BN_THREADS / 32];
+  const int c = blockIdx.x, s = blockIdx.y;
+  const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  const int64_t chunk = da_cdiv(V, BN_SPLITS);
+  double a1 = 0, a2 = 0;
+  for (int n = 0; n < N; ++n) {
+    const int64_t base = ((int64_t)n * C + c) * V;
+    const int64_t lo = (int64_t)s * chunk, hi = min(V, lo + chunk);
+    float f1 = 0.f, f2 = 0.f;
+    int k = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
+      const float xh = (x[base + i] - mu) * is;
+      const float g = dy[base + i] * act_grad(xh * ga + be, act, slope);
+      f1 += g; f2 = fmaf(g, xh, f2);
+      if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+    }
+    a1 += (double)f1; a2 += (double)f2;
+  }
+  const double b1 = block_sum<double, BN_THREADS / 32>(a1, red);
+  const double b2 = block_sum<double, BN_THREADS / 32>(a2, red);
+  if (threadIdx.x == 0) {
+    partials[((int64_t)c * BN_SPLITS + s) * 2 + 0] = b1;
+    partials[((int64_t)c * BN_SPLITS + s) * 2 + 1] = b2;
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ s12) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0, s2 = 0;
+  for (int s = 0; s < BN_SPLITS; ++s) {
+    s1 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 0];
+    s2 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 1];
+  }
+  if (dbeta) dbeta[c] = (float)s1;
+  if (dgamma) dgamma[c] = (float)s2;
+  s12[2 * c] = (float)s1;
+  s12[2 * c + 1] = (float)s2;
+}
+
+// dx = gamma*invstd*(g - s1/M - xhat*s2/M)   (training)  |  gamma*invstd*g   (eval)
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ s12, int C, int64_t V, float invM,
+                                                         int training, int act, float slope, float* __restrict__ dx) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+  const float m1 = training ? s12[2 * c] * invM : 0.f, m2 = training ? s12[2 * c + 1] * invM : 0.f;
+  const float k = ga * is;
+  const int64_t base = ((int64_t)n * C + c) * V;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < V; i += (int64_t)gridDim.x * 256) {
+    const float xh = (x[base + i] - mu) * is;
+    const float g = dy[base + i] * act_grad(xh * ga + be, act, slope);
+    dx[base + i] = k * (g - m1 - xh * m2);
+  }
+}
+
+// dx = dy * (y > 0 ? 1 : slope)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope,
+                                                      int64_t total, float* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256)
+    dx[i] = y[i] > 0.f ? dy[i] : dy[i] * slope;
+}
+
+// ---- max pool 2x2x2 stride 2 (floor) ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t NC,
+                                                           int D, int H, int W, int Do, int Ho, int Wo) {
+  const int64_t total = NC * Do * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int xo = (int)(i % Wo);
+    int64_t t = i / Wo;
+    const int yo = (int)(t % Ho); t /= Ho;
+    const int zo = (int)(t % Do);
+    const int64_t nc = t / Do;
+    const float* p = x + ((nc * D + 2 * zo) * H + 2 * yo) * W + 2 * xo;
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = p[((int64_t)(k >> 2) * H + ((k >> 1) & 1)) * W + (k & 1)];
+      if (v > m || v != v) m = v;  // ATen: (val > maxval) || isnan(val)
+    }
+    y[i] = m;
+  }
+}
+
+// dx is fully written when D,H,W are even; odd trailing planes are zeroed by the entry point's memset.
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           float* __restrict__ dx, int64_t NC, int D, int H, int W, int Do,
+                                                           int Ho, int Wo) {
+  const int64_t total = NC * Do * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int xo = (int)(i % Wo);
+    int64_t t = i / Wo;
+    const int yo = (int)(t % Ho); t /= Ho;
+    const int zo = (int)(t % Do);
+    const int64_t nc = t / Do;
+    const int64_t off = ((nc * D + 2 * zo) * H + 2 * yo) * W + 2 * xo;
+    const float* p = x + off;
+    float m = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float v = p[((int64_t)(k >> 2) * H + ((k >> 1) & 1)) * W + (k & 1)];
+      if (v > m || v != v) { m = v; arg = k; }
+    }
+    const float g = dy[i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dx[off + ((int64_t)(k >> 2) * H + ((k >> 1) & 1)) * W + (k & 1)] = (k == arg) ? g : 0.f;
+  }
+}
+
+// ---- nearest upsampling to an explicit size ------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
+  const int s = (int)floorf((float)dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+
+__global__ void __launch_bounds__(256) upsample_nearest_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                   int64_t NC, int D, int H, int W, int Do, int Ho, int Wo) {
+  const float sz = (float)D / (float)Do, sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const int64_t total = NC * Do * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int xo = (int)(i % Wo);
+    int64_t t = i / Wo;
+    const int yo = (int)(t % Ho); t /= Ho;
+    const int zo = (int)(t % Do);
+    const int64_t nc = t / Do;
+    y[i] = x[((nc * D + nearest_src(zo, sz, D)) * H + nearest_src(yo, sy, H)) * W + nearest_src(xo, sx, W)];
+  }
+}
+
+__device__ __forceinline__ void dst_range(int src, float scale, int in, int out, int& lo, int& hi) {
+  // all dst with nearest_src(dst) == src form a contiguous range (the map is monotone)
+  int d = (int)floorf((float)src / scale) - 2;
+  if (d < 0) d = 0;
+  while (d < out && nearest_src(d, scale, in) < src) ++d;
+  lo = d;
+  while (d < out && nearest_src(d, scale, in) == src) ++d;
+  hi = d;
+}
+
+__global__ void __launch_bounds__(256) upsample_nearest_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                                                   int64_t NC, int D, int H, int W, int Do, int Ho, int Wo) {
+  const float sz = (float)D / (float)Do, sy = (float)H / (float)Ho, sx = (float)W / (float)Wo;
+  const int64_t total = NC * D * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int xs = (int)(i % W);
+    int64_t t = i / W;
+    const int ys = (int)(t % H); t /= H;
+    const int zs = (int)(t % D);
+    const int64_t nc = t / D;
+    int z0, z1, y0, y1, x0, x1;
+    dst_range(zs, sz, D, Do, z0, z1);
+    dst_range(ys, sy, H, Ho, y0, y1);
+    dst_range(xs, sx, W, Wo, x0, x1);
+    float acc = 0.f;
+    for (int z = z0; z < z1; ++z)
+      for (int y = y0; y < y1; ++y)
+        for (int xx = x0; xx < x1; ++xx) acc += dy[((nc * Do + z) * Ho + y) * Wo + xx];
+    dx[i] = acc;
+  }
+}
+
+inline int ew_grid(int64_t total, int per_block = 256) {
+  int64_t b = da_cdiv(total, per_block);
+  const int64_t cap = (int64_t)DA_NUM_SMS * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+DA_API int64_t da_bn_workspace_bytes(int C) { return (int64_t)sizeof(double) * C * BN_SPLITS * 2 + (int64_t)sizeof(float) * 2 * C + 256; }
+
+// Training-mode statistics: mean/invstd [C] out; running stats (nullable) updated in place with `momentum`
+// (unbiased variance), as nn.BatchNorm3d does.
+DA_API int da_bn_stats(const float* x, int N, int C, int64_t V, float eps, float momentum, float* mean, float* invstd,
+                       float* running_mean, float* running_var, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t stream) {
+  DA_REQUIRE(x && mean && invstd && workspace, "da_bn_stats: null pointer");
+  if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_stats: workspace too small"); return DA_ERR_WORKSPACE; }
+  dim3 grid(C, BN_SPLITS);
+  bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, (double*)workspace);
+  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean,
+                                                        invstd, running_mean, running_var);
+  return da_check_launch("da_bn_stats");
+}
+
+// Eval-mode helper: mean = running_mean, invstd = rsqrt(running_var + eps) is formed by the caller.
+DA_API int da_bn_act_fwd(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         int N, int C, int64_t V, int act, float slope, float* y, cudaStream_t stream) {
+  DA_REQUIRE(x && mean && invstd && y, "da_bn_act_fwd: null pointer");
+  dim3 grid(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
+  bn_act_fwd_kernel<<<grid, 256, 0, stream>>>(x, mean, invstd, gamma, beta, C, V, act, slope, y);
+  return da_check_launch("da_bn_act_fwd");
+}
+
+DA_API int da_bn_act_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
+                         float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(dy && x && mean && invstd && dx && workspace, "da_bn_act_bwd: null pointer");
+  if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_act_bwd: workspace too small"); return DA_ERR_WORKSPACE; }
+  double* partials = (double*)workspace;
+  float* s12 = (float*)(partials + (int64_t)C * BN_SPLITS * 2);
+  dim3 g1(C, BN_SPLITS);
+  bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, partials);
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(partials, C, dgamma, dbeta, s12);
+  dim3 g2(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
+  bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)(1.0 / ((double)N * (double)V)),
+                                            training, act, slope, dx);
+  return da_check_launch("da_bn_act_bwd");
+}
+
+DA_API int da_act_bwd(const float* dy, const float* y, float slope, int64_t total, float* dx, cudaStream_t stream) {
+  DA_REQUIRE(dy && y && dx, "da_act_bwd: null pointer");
+  act_bwd_kernel<<<ew_grid(total), 256, 0, stream>>>(dy, y, slope, total, dx);
+  return da_check_launch("da_act_bwd");
+}
+
+DA_API int da_maxpool2_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, cudaStream_t stream) {
+  DA_REQUIRE(x && y, "da_maxpool2_fwd: null pointer");
+  DA_REQUIRE(D >= 2 && H >= 2 && W >= 2, "da_maxpool2_fwd: extent too small");
+  maxpool2_fwd_kernel<<<ew_grid(NC * (D / 2) * (H / 2) * (W / 2)), 256, 0, stream>>>(x, y, NC, D, H, W, D / 2, H / 2, W / 2);
+  return da_check_launch("da_maxpool2_fwd");
+}
+
+DA_API int da_maxpool2_bwd(const float* dy, const float* x, float* dx, int64_t NC, int D, int H, int W, cudaStream_t stream) {
+  DA_REQUIRE(dy && x && dx, "da_maxpool2_bwd: null pointer");
+  if ((D | H | W) & 1) {
+    cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)NC * D * H * W, stream);
+    if (e != cudaSuccess) { da_set_error("da_maxpool2_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  maxpool2_bwd_kernel<<<ew_grid(NC * (D / 2) * (H / 2) * (W / 2)), 256, 0, stream>>>(dy, x, dx, NC, D, H, W, D / 2, H / 2, W / 2);
+  return da_check_launch("da_maxpool2_bwd");
+}
+
+DA_API int da_upsample_nearest_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, int Do, int Ho, int Wo,
+                                   cudaStream_t stream) {
+  DA_REQUIRE(x && y, "da_upsample_nearest_fwd: null pointer");
+  upsample_nearest_fwd_kernel<<<ew_grid(NC * Do * Ho * Wo), 256, 0, stream>>>(x, y, NC, D, H, W, Do, Ho, Wo);
+  return da_check_launch("da_upsample_nearest_fwd");
+}
+
+DA_API int da_upsample_nearest_bwd(const float* dy, float* dx, int64_t NC, int D, int H, int W, int Do, int Ho, int Wo,
+                                   cudaStream_t stream) {
+  DA_REQUIRE(dy && dx, "da_upsample_nearest_bwd: null pointer");
+  upsample_nearest_bwd_kernel<<<ew_grid(NC * D * H * W), 256, 0, stream>>>(dy, dx, NC, D, H, W, Do, Ho, Wo);
+  return da_check_launch("da_upsample_nearest_bwd");
+}

@@ -1,0 +1,193 @@
+// warp3d: the deformation-field spatial transformer of the registration branch.
+//
+// Replaces, in ONE pass each way, the reference sequence (lib/network_factory/voxel_morph.py:85-91)
+//   id    = get_identity_transform(...)                (lib/utils.py:89-102, materialised 3xDxHxW)
+//   phi   = disp + id                                  (:88)
+//   out   = F.grid_sample(src, phi.permute(0,2,3,4,1), 'bilinear', 'zeros', align_corners=True)  (:90-91)
+// The identity grid is recomputed from the voxel index with the reference's own fp32 rounding
+// sequence (k/(n-1)*2-1, each step rounded), never stored unless the caller asks for phi.
+// Layout: planar NCDHW fp32 (the reference's), one thread per output voxel looping over channels so
+// the 8 corner offsets / weights are computed once; consecutive threads are consecutive along W.
+// HBM-bound: image warp fwd+bwd 13*V*4 B, C-channel (5C+9)*V*4 B.
+#include "common.cuh"
+
+namespace {
+
+struct WarpGeom {
+  int N, C, D, H, W;      // source extent
+  int Do, Ho, Wo;         // output / field extent
+};
+
+__device__ __forceinline__ float ident_coord(int k, int n) {
+  // torch.arange(0,n).float() / (n-1) * 2.0 - 1   -- every op rounded to fp32, no contraction
+  return __fadd_rn(__fmul_rn(__fdiv_rn((float)k, (float)(n - 1)), 2.0f), -1.0f);
+}
+__device__ __forceinline__ float unnormalize(float g, int size) {
+  // ATen grid_sampler_unnormalize, align_corners=True: ((g + 1) / 2) * (size - 1)
+  return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.0f), 2.0f), (float)(size - 1));
+}
+
+template <bool ADD_ID>
+__device__ __forceinline__ void load_phi(const float* __restrict__ field, int64_t Vo, int64_t v, int x,
+                                         int y, int z, const WarpGeom& g, float& px, float& py,
+                                         float& pz) {
+  px = field[v];
+  py = field[Vo + v];
+  pz = field[2 * Vo + v];
+  if (ADD_ID) {
+    px = __fadd_rn(px, ident_coord(x, g.Wo));
+    py = __fadd_rn(py, ident_coord(y, g.Ho));
+    pz = __fadd_rn(pz, ident_coord(z, g.Do));
+  }
+}
+
+struct Corners {
+  int64_t off[8];
+  float w[8];
+  bool ok[8];
+  float fx[2], fy[2], fz[2];
+};
+
+__device__ __forceinline__ void make_corners(float ix, float iy, float iz, const WarpGeom& g, Corners& c) {
+  const float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
+  const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+  // weight of the "0" corner is (x1 - ix); of the "1" corner (ix - x0)  (ATen GridSampler naming:
+  // tnw = (ix_bse-ix)(iy_bse-iy)(iz_bse-iz), ...)
+  c.fx[0] = (x0f + 1.0f) - ix; c.fx[1] = ix - x0f;
+  c.fy[0] = (y0f + 1.0f) - iy; c.fy[1] = iy - y0f;
+  c.fz[0] = (z0f + 1.0f) - iz; c.fz[1] = iz - z0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {  // order tnw,tne,tsw,tse,bnw,bne,bsw,bse = (dz,dy,dx) binary count
+    const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+    const int xi = x0 + dx, yi = y0 + dy, zi = z0 + dz;
+    c.ok[k] = (xi >= 0) & (xi < g.W) & (yi >= 0) & (yi < g.H) & (zi >= 0) & (zi < g.D);
+    c.off[k] = ((int64_t)zi * g.H + yi) * g.W + xi;
+    c.w[k] = c.fx[dx] * c.fy[dy] * c.fz[dz];
+  }
+}
+
+template <bool ADD_ID>
+__global__ void __launch_bounds__(256) warp3d_fwd_kernel(const float* __restrict__ src,
+                                                         const float* __restrict__ field,
+                                                         float* __restrict__ out,
+                                                         float* __restrict__ phi_out, WarpGeom g) {
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo, Vs = (int64_t)g.D * g.H * g.W;
+  const int64_t total = (int64_t)g.N * Vo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Vo);
+    const int64_t v = i - (int64_t)n * Vo;
+    const int x = (int)(v % g.Wo), y = (int)((v / g.Wo) % g.Ho), z = (int)(v / ((int64_t)g.Wo * g.Ho));
+    float px, py, pz;
+    load_phi<ADD_ID>(field + (int64_t)n * 3 * Vo, Vo, v, x, y, z, g, px, py, pz);
+    if (phi_out) {
+      float* p = phi_out + (int64_t)n * 3 * Vo;
+      p[v] = px; p[Vo + v] = py; p[2 * Vo + v] = pz;
+    }
+    Corners c;
+    make_corners(unnormalize(px, g.W), unnormalize(py, g.H), unnormalize(pz, g.D), g, c);
+    const float* s = src + (int64_t)n * g.C * Vs;
+    float* o = out + (int64_t)n * g.C * Vo + v;
+    for (int ch = 0; ch < g.C; ++ch, s += Vs, o += Vo) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (c.ok[k]) acc += __ldg(s + c.off[k]) * c.w[k];
+      *o = acc;
+    }
+  }
+}
+
+// grad_src must be zero-filled by the caller-facing entry point (done below with a memset).
+template <bool ADD_ID>
+__global__ void __launch_bounds__(256) warp3d_bwd_kernel(const float* __restrict__ gout,
+                                                         const float* __restrict__ src,
+                                                         const float* __restrict__ field,
+                                                         float* __restrict__ gsrc,
+                                                         float* __restrict__ gfield, WarpGeom g) {
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo, Vs = (int64_t)g.D * g.H * g.W;
+  const int64_t total = (int64_t)g.N * Vo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Vo);
+    const int64_t v = i - (int64_t)n * Vo;
+    const int x = (int)(v % g.Wo), y = (int)((v / g.Wo) % g.Ho), z = (int)(v / ((int64_t)g.Wo * g.Ho));
+    float px, py, pz;
+    load_phi<ADD_ID>(field + (int64_t)n * 3 * Vo, Vo, v, x, y, z, g, px, py, pz);
+    Corners c;
+    make_corners(unnormalize(px, g.W), unnormalize(py, g.H), unnormalize(pz, g.D), g, c);
+    const float* s = src + (int64_t)n * g.C * Vs;
+    float* gs = gsrc ? gsrc + (int64_t)n * g.C * Vs : nullptr;
+    const float* go = gout + (int64_t)n * g.C * Vo + v;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int ch = 0; ch < g.C; ++ch, s += Vs, go += Vo) {
+      const float gO = *go;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!c.ok[k]) continue;
+        const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+        if (gs) atomicAdd(gs + (int64_t)ch * Vs + c.off[k], c.w[k] * gO);
+        if (gfield) {
+          const float val = __ldg(s + c.off[k]) * gO;
+          gx += (dx ? val : -val) * c.fy[dy] * c.fz[dz];
+          gy += (dy ? val : -val) * c.fx[dx] * c.fz[dz];
+          gz += (dz ? val : -val) * c.fx[dx] * c.fy[dy];
+        }
+      }
+    }
+    if (gfield) {
+      float* gf = gfield + (int64_t)n * 3 * Vo;
+      gf[v] = gx * (0.5f * (float)(g.W - 1));
+      gf[Vo + v] = gy * (0.5f * (float)(g.H - 1));
+      gf[2 * Vo + v] = gz * (0.5f * (float)(g.D - 1));
+    }
+  }
+}
+
+inline int grid_for(int64_t total, int threads) {
+  int64_t b = da_cdiv(total, threads);
+  const int64_t cap = (int64_t)DA_NUM_SMS * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+// src [N,C,D,H,W]; field [N,3,Do,Ho,Wo] (channel 0 = x/W, 1 = y/H, 2 = z/D, normalised [-1,1]);
+// out [N,C,Do,Ho,Wo]; phi_out (nullable) [N,3,Do,Ho,Wo] receives field (+ identity).
+DA_API int da_warp3d_fwd(const float* src, const float* field, int add_identity, float* out,
+                         float* phi_out, int N, int C, int D, int H, int W, int Do, int Ho, int Wo,
+                         cudaStream_t stream) {
+  DA_REQUIRE(src && field && out, "da_warp3d_fwd: null pointer");
+  DA_REQUIRE(N > 0 && C > 0 && D > 0 && H > 0 && W > 0 && Do > 0 && Ho > 0 && Wo > 0,
+             "da_warp3d_fwd: bad extent");
+  WarpGeom g{N, C, D, H, W, Do, Ho, Wo};
+  const int64_t total = (int64_t)N * Do * Ho * Wo;
+  const int grid = grid_for(total, 256);
+  if (add_identity)
+    warp3d_fwd_kernel<true><<<grid, 256, 0, stream>>>(src, field, out, phi_out, g);
+  else
+    warp3d_fwd_kernel<false><<<grid, 256, 0, stream>>>(src, field, out, phi_out, g);
+  return da_check_launch("da_warp3d_fwd");
+}
+
+// grad_src (nullable) [N,C,D,H,W] is zeroed here then scatter-added (fp32 atomics: the only
+// non-deterministic reduction in the library, as in ATen's grid_sampler_3d_backward);
+// grad_field (nullable) [N,3,Do,Ho,Wo].
+DA_API int da_warp3d_bwd(const float* grad_out, const float* src, const float* field, int add_identity,
+                         float* grad_src, float* grad_field, int N, int C, int D, int H, int W, int Do,
+                         int Ho, int Wo, cudaStream_t stream) {
+  DA_REQUIRE(grad_out && src && field, "da_warp3d_bwd: null pointer");
+  DA_REQUIRE(grad_src || grad_field, "da_warp3d_bwd: nothing to compute");
+  WarpGeom g{N, C, D, H, W, Do, Ho, Wo};
+  if (grad_src) {
+    cudaError_t e = cudaMemsetAsync(grad_src, 0, sizeof(float) * (size_t)N * C * D * H * W, stream);
+    if (e != cudaSuccess) { da_set_error("da_warp3d_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const int64_t total = (int64_t)N * Do * Ho * Wo;
+  const int grid = grid_for(total, 256);
+  if (add_identity)
+    warp3d_bwd_kernel<true><<<grid, 256, 0, stream>>>(grad_out, src, field, grad_src, grad_field, g);
+  else
+    warp3d_bwd_kernel<false><<<grid, 256, 0, stream>>>(grad_out, src, field, grad_src, grad_field, g);
+  return da_check_launch("da_warp3d_bwd");
+}

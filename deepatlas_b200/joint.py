@@ -1,0 +1,72 @@
+"""The joint seg+reg training step, assembled from the reference's registry entries.
+
+The reference tree ships no joint loop (README.md:15-19 lists it as TODO); its ingredients are all
+present and SURVEY.md 8(d) fixes the step definition used here and by the oracle:
+
+    P_m = seg(I_m) ; P_t = seg(I_t)                      two B=1 calls (BN statistics per volume)
+    disp, I_w, phi = reg(I_m, I_t)                        lib/network_factory/voxel_morph.py:62-92
+    S_w = grid_sample(softmax(P_m), phi)                  same call as voxel_morph.py:90-91
+    L = l_sim * lncc(I_w, I_t) + l_reg * bendingEnergy(disp)
+      + l_ana * dice(S_w, onehot(S_t))                    soft-target branch lib/loss.py:435-436
+      + l_sup * (dice(P_m, S_m) + dice(P_t, S_t))         softmax=True, train_seg.py:54-55
+
+The lambdas are not in the reference (paper hyper-parameters); they are configuration here.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .losses import get_loss_function
+from .networks import get_network
+
+DEFAULT_LAMBDAS = dict(sim=1.0, reg=1000.0, ana=1.0, sup=1.0)
+
+
+class JointModel(nn.Module):
+    def __init__(self, n_classes=32, in_channel=1, seg_name="UNet_light", lambdas=None):
+        super().__init__()
+        self.n_classes = n_classes
+        self.seg = get_network(seg_name)(in_channel, n_classes, bias=True, BN=True)
+        self.reg = get_network("voxel_morph_cvpr")()
+        self.lambdas = dict(DEFAULT_LAMBDAS, **(lambdas or {}))
+        self.sim_loss = get_loss_function("lncc")()
+        self.reg_loss = get_loss_function("bendingEnergy")()
+        self.sup_dice = get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", softmax=True, eps=1e-6)
+        self.ana_dice = get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", softmax=False, eps=1e-6)
+
+    def weights_init(self):
+        self.seg.weights_init()
+        self.reg.weights_init()
+
+    def trainable_parameters(self):
+        return list(self.seg.parameters()) + list(self.reg.parameters())
+
+    def joint_loss(self, I_m, S_m, I_t, S_t):
+        """I_*: (1,1,D,H,W) fp32 images; S_*: (1,D,H,W) integer label maps (uint8 is read directly)."""
+        lam = self.lambdas
+        P_m = self.seg(I_m)
+        P_t = self.seg(I_t)
+        disp, I_w, phi = self.reg(I_m, I_t)
+        S_w = ops.warp3d(ops.softmax(P_m), phi, add_identity=False)
+        parts = {
+            "sim": self.sim_loss(I_w, I_t),
+            "reg": self.reg_loss(disp),
+            "ana": self.ana_dice(S_w, S_t),   # labels stand for onehot(S_t): same sums, no 629 MB one-hot
+            "sup": self.sup_dice(P_m, S_m) + self.sup_dice(P_t, S_t),
+        }
+        loss = lam["sim"] * parts["sim"] + lam["reg"] * parts["reg"] + lam["ana"] * parts["ana"] + lam["sup"] * parts["sup"]
+        return loss, parts
+
+
+def make_synthetic_pair(size, n_classes, seed=230, device="cpu"):
+    """SURVEY.md 8(d) synthetic inputs: images U[0,1) fp32 (1,1,D,H,W); labels randint(0,C) uint8 (1,D,H,W);
+    moving and target are independent draws.  Generated on the CPU generator so every device sees the same data."""
+    g = torch.Generator().manual_seed(seed)
+    D, H, W = size
+    I_m = torch.rand((1, 1, D, H, W), generator=g)
+    I_t = torch.rand((1, 1, D, H, W), generator=g)
+    S_m = torch.randint(0, n_classes, (1, D, H, W), generator=g, dtype=torch.uint8)
+    S_t = torch.randint(0, n_classes, (1, D, H, W), generator=g, dtype=torch.uint8)
+    return tuple(t.to(device) for t in (I_m, S_m, I_t, S_t))

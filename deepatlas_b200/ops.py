@@ -1,0 +1,467 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (one per library op the reference calls).
+
+PyTorch is plumbing here: it owns device memory (outputs, saved tensors, workspaces come from the
+caching allocator), the CUDA stream, and the autograd graph.  All arithmetic happens in
+``libdeepatlas_b200.so``.  Inputs must be CUDA fp32 tensors -- there is no CPU or eager fallback, a
+CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"deepatlas_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"deepatlas_b200: '{name}' must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# warp3d  (lib/network_factory/voxel_morph.py:85-91)
+# ------------------------------------------------------------------------------------------------------
+class Warp3dFunction(torch.autograd.Function):
+    """out, phi = warp3d(src, field, add_identity): phi = field (+ identity grid), out = trilinear
+    sample of src at phi (zeros padding, align_corners=True)."""
+
+    @staticmethod
+    def forward(ctx, src, field, add_identity: bool, want_phi: bool):
+        src, field = _f32(src, "src"), _f32(field, "field")
+        N, C, D, H, W = src.shape
+        if field.dim() != 5 or field.shape[0] != N or field.shape[1] != 3:
+            raise ValueError(f"warp3d: field must be (N,3,Do,Ho,Wo), got {tuple(field.shape)}")
+        Do, Ho, Wo = field.shape[2:]
+        out = torch.empty((N, C, Do, Ho, Wo), dtype=torch.float32, device=src.device)
+        phi = torch.empty_like(field) if want_phi else None
+        _lib.call("da_warp3d_fwd", _p(src), _p(field), int(add_identity), _p(out), _p(phi), N, C, D, H, W,
+                  Do, Ho, Wo, _stream())
+        ctx.save_for_backward(src, field)
+        ctx.add_identity = bool(add_identity)
+        if want_phi:
+            return out, phi
+        ctx.mark_non_differentiable()
+        return out, None
+
+    @staticmethod
+    def backward(ctx, g_out, g_phi):
+        src, field = ctx.saved_tensors
+        N, C, D, H, W = src.shape
+        Do, Ho, Wo = field.shape[2:]
+        need_src, need_field = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_src = g_field = None
+        if g_out is not None and (need_src or need_field):
+            g_out = _f32(g_out, "grad_out")
+            g_src = torch.empty_like(src) if need_src else None
+            g_field = torch.empty_like(field) if need_field else None
+            _lib.call("da_warp3d_bwd", _p(g_out), _p(src), _p(field), int(ctx.add_identity), _p(g_src),
+                      _p(g_field), N, C, D, H, W, Do, Ho, Wo, _stream())
+        if need_field and g_phi is not None:
+            g_field = g_phi if g_field is None else g_field + g_phi
+        return g_src, g_field, None, None
+
+
+def warp3d(src, field, add_identity=False, want_phi=False):
+    out, phi = Warp3dFunction.apply(src, field, add_identity, want_phi)
+    return (out, phi) if want_phi else out
+
+
+# ------------------------------------------------------------------------------------------------------
+# softmax + Dice sums  (lib/loss.py:427-472, lib/transforms.py:675-689)
+# ------------------------------------------------------------------------------------------------------
+_KIND = {torch.uint8: 0, torch.int64: 1, torch.int32: 3}
+
+
+class DiceSumsFunction(torch.autograd.Function):
+    """sums[N,3,C] = (sum p, sum t, sum p*t) with p = softmax(source) if apply_softmax else source and
+    t = one-hot(labels) (never materialised) or a soft target."""
+
+    @staticmethod
+    def forward(ctx, source, target, apply_softmax: bool):
+        source = _f32(source, "source")
+        N, C = source.shape[:2]
+        V = source[0, 0].numel()
+        if not target.is_cuda:
+            raise RuntimeError("deepatlas_b200: 'target' must be a CUDA tensor")
+        if target.is_floating_point():
+            target = _f32(target, "target")
+            if target.numel() != source.numel():
+                raise ValueError("dice: soft target must have the shape of source")
+            kind = 2
+        else:
+            if target.dtype not in _KIND:
+                target = target.long()
+            target = target.contiguous()
+            if target.numel() != N * V:
+                raise ValueError("dice: label target must have N*D*H*W elements")
+            kind = _KIND[target.dtype]
+        sums = torch.empty((N, 3, C), dtype=torch.float32, device=source.device)
+        nb = _lib.size("da_dice_workspace_bytes", N, C, V)
+        ws = _ws(nb, source.device)
+        _lib.call("da_dice_sums_fwd", _p(source), _p(target), kind, int(apply_softmax), N, C, V, _p(sums),
+                  _p(ws), nb, _stream())
+        ctx.save_for_backward(source, target)
+        ctx.kind, ctx.apply_softmax = kind, bool(apply_softmax)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        source, target = ctx.saved_tensors
+        N, C = source.shape[:2]
+        V = source[0, 0].numel()
+        g = _f32(g, "grad_sums")
+        gS, gT, gI = g[:, 0].contiguous(), g[:, 1].contiguous(), g[:, 2].contiguous()
+        need_t = ctx.kind == 2 and ctx.needs_input_grad[1]
+        g_src = torch.empty_like(source) if ctx.needs_input_grad[0] else None
+        g_tgt = torch.empty_like(target) if need_t else None
+        if g_src is not None or g_tgt is not None:
+            _lib.call("da_dice_sums_bwd", _p(source), _p(target), ctx.kind, int(ctx.apply_softmax), N, C, V,
+                      _p(gS), _p(gT), _p(gI), _p(g_src), _p(g_tgt), _stream())
+        return g_src, g_tgt, None
+
+
+def dice_sums(source, target, apply_softmax=False):
+    return DiceSumsFunction.apply(source, target, apply_softmax)
+
+
+class SoftmaxFunction(torch.autograd.Function):
+    """Channel softmax (F.softmax(dim=1)) for the anatomy branch, where the probabilities get warped."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x, "x")
+        N, C = x.shape[:2]
+        y = torch.empty_like(x)
+        _lib.call("da_softmax_fwd", _p(x), _p(y), N, C, x[0, 0].numel(), _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _f32(dy, "grad_out")
+        N, C = y.shape[:2]
+        dx = torch.empty_like(y)
+        _lib.call("da_softmax_bwd", _p(y), _p(dy), _p(dx), N, C, y[0, 0].numel(), _stream())
+        return dx
+
+
+def softmax(x):
+    return SoftmaxFunction.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------------
+# local NCC  (lib/loss.py:597-617)
+# ------------------------------------------------------------------------------------------------------
+class LnccFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, I, J, win: int, eps: float):
+        I, J = _f32(I, "I"), _f32(J, "J")
+        if I.shape != J.shape or I.dim() != 5 or I.shape[1] != 1:
+            raise ValueError(f"lncc: I and J must both be (N,1,D,H,W), got {tuple(I.shape)} / {tuple(J.shape)}")
+        N, _, D, H, W = I.shape
+        need = (1 if ctx.needs_input_grad[0] else 0) | (2 if ctx.needs_input_grad[1] else 0)
+        loss = torch.empty((), dtype=torch.float32, device=I.device)
+        coef = _ws(_lib.size("da_lncc_coef_bytes", N, D, H, W, win, need), I.device) if need else None
+        nb = _lib.size("da_lncc_fwd_workspace_bytes", N, D, H, W, win)
+        ws = _ws(nb, I.device)
+        _lib.call("da_lncc_fwd", _p(I), _p(J), N, D, H, W, win, float(eps), need, _p(loss), _p(coef), _p(ws),
+                  nb, _stream())
+        ctx.save_for_backward(I, J, coef if coef is not None else torch.empty(0, device=I.device))
+        ctx.win, ctx.need = win, need
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        I, J, coef = ctx.saved_tensors
+        N, _, D, H, W = I.shape
+        g = _f32(g, "grad_out").reshape(1)
+        nb = _lib.size("da_lncc_bwd_workspace_bytes", N, D, H, W, ctx.win)
+        ws = _ws(nb, I.device)
+        gI = gJ = None
+        slot = 0
+        if ctx.need & 1:
+            gI = torch.empty_like(I)
+            _lib.call("da_lncc_bwd", _p(I), _p(J), _p(g), _p(coef), slot, 0, N, D, H, W, ctx.win, _p(gI),
+                      _p(ws), nb, _stream())
+            slot += 1
+        if ctx.need & 2:
+            gJ = torch.empty_like(J)
+            _lib.call("da_lncc_bwd", _p(I), _p(J), _p(g), _p(coef), slot, 1, N, D, H, W, ctx.win, _p(gJ),
+                      _p(ws), nb, _stream())
+        return gI, gJ, None, None
+
+
+def lncc(I, J, win=9, eps=1e-6):
+    return LnccFunction.apply(I, J, win, eps)
+
+
+# ------------------------------------------------------------------------------------------------------
+# bending energy sums  (lib/loss.py:702-718)
+# ------------------------------------------------------------------------------------------------------
+class BendingSumsFunction(torch.autograd.Function):
+    """sums[N,3,6]: per channel the interior sum of squared (ddD, ddH, ddW, dDdH, dHdW, dDdW)."""
+
+    @staticmethod
+    def forward(ctx, u):
+        u = _f32(u, "input")
+        if u.dim() != 5 or u.shape[1] != 3:
+            raise ValueError(f"bending: input must be (N,3,D,H,W), got {tuple(u.shape)}")
+        N, _, D, H, W = u.shape
+        sums = torch.empty((N, 3, 6), dtype=torch.float32, device=u.device)
+        nb = _lib.size("da_bending_fwd_workspace_bytes", N)
+        ws = _ws(nb, u.device)
+        _lib.call("da_bending_fwd", _p(u), N, D, H, W, _p(sums), _p(ws), nb, _stream())
+        ctx.save_for_backward(u)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        N, _, D, H, W = u.shape
+        g = _f32(g, "grad_sums")
+        nb = _lib.size("da_bending_bwd_workspace_bytes", N, D, H, W)
+        ws = _ws(nb, u.device)
+        gu = torch.empty_like(u)
+        _lib.call("da_bending_bwd", _p(u), _p(g), N, D, H, W, _p(gu), _p(ws), nb, _stream())
+        return gu
+
+
+def bending_sums(u):
+    return BendingSumsFunction.apply(u)
+
+
+# ------------------------------------------------------------------------------------------------------
+# conv3d  (lib/network_factory/unets.py:30,36,98,250; modules.py:48; voxel_morph.py:57)
+# ------------------------------------------------------------------------------------------------------
+def _conv_out(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+class Conv3dFunction(torch.autograd.Function):
+    """out = act(conv3d(cat(x1, x2), weight) + bias); weight in nn.Conv3d layout, or nn.ConvTranspose3d
+    layout when ``transposed`` (k3 s1 p1 only).  act: None or the leaky slope (0.0 = ReLU)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, transposed: bool, stride: int, pad: int, slope):
+        x1, weight = _f32(x1, "x1"), _f32(weight, "weight")
+        x2 = _f32(x2, "x2") if x2 is not None else None
+        bias = _f32(bias, "bias") if bias is not None else None
+        N, C1, Di, Hi, Wi = x1.shape
+        C2 = x2.shape[1] if x2 is not None else 0
+        if x2 is not None and (x2.shape[0] != N or tuple(x2.shape[2:]) != (Di, Hi, Wi)):
+            raise ValueError("conv3d: x1 and x2 must share batch and spatial extents")
+        ks = weight.shape[2]
+        Cout, Cin = (weight.shape[1], weight.shape[0]) if transposed else (weight.shape[0], weight.shape[1])
+        if Cin != C1 + C2:
+            raise ValueError(f"conv3d: weight expects {Cin} input channels, got {C1}+{C2}")
+        Do, Ho, Wo = (_conv_out(n, ks, stride, pad) for n in (Di, Hi, Wi))
+        out = torch.empty((N, Cout, Do, Ho, Wo), dtype=torch.float32, device=x1.device)
+        nb = _lib.size("da_conv3d_pack_bytes", Cin, Cout, ks)
+        ws = _ws(nb, x1.device)
+        _lib.call("da_conv3d_fwd", _p(x1), C1, _p(x2), C2, _p(weight), int(transposed), _p(bias), _p(out), N, Di,
+                  Hi, Wi, Cout, ks, stride, pad, 0 if slope is None else 1, 0.0 if slope is None else float(slope),
+                  _p(ws), nb, _stream())
+        ctx.save_for_backward(x1, x2, weight, out if slope is not None else None)
+        ctx.cfg = (bool(transposed), ks, stride, pad, slope, bias is not None, Cout)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, x2, weight, out = ctx.saved_tensors
+        transposed, ks, stride, pad, slope, has_bias, Cout = ctx.cfg
+        dy = _f32(dy, "grad_out")
+        N, C1, Di, Hi, Wi = x1.shape
+        C2 = x2.shape[1] if x2 is not None else 0
+        Cin = C1 + C2
+        st = _stream()
+        if slope is not None:
+            g = torch.empty_like(dy)
+            _lib.call("da_act_bwd", _p(dy), _p(out), float(slope), dy.numel(), _p(g), st)
+            dy = g
+        dx1 = dx2 = dw = db = None
+        nb = _lib.size("da_conv3d_pack_bytes", Cin, Cout, ks)
+        ws = _ws(nb, dy.device)
+        if ctx.needs_input_grad[0]:
+            dx1 = torch.empty_like(x1)
+            _lib.call("da_conv3d_dgrad", _p(dy), _p(weight), int(transposed), _p(dx1), N, Cin, 0, C1, Cout, Di, Hi,
+                      Wi, ks, stride, pad, _p(ws), nb, st)
+        if x2 is not None and ctx.needs_input_grad[1]:
+            dx2 = torch.empty_like(x2)
+            _lib.call("da_conv3d_dgrad", _p(dy), _p(weight), int(transposed), _p(dx2), N, Cin, C1, C2, Cout, Di, Hi,
+                      Wi, ks, stride, pad, _p(ws), nb, st)
+        if ctx.needs_input_grad[2] or (has_bias and ctx.needs_input_grad[3]):
+            dw = torch.empty_like(weight)
+            db = torch.empty((Cout,), dtype=torch.float32, device=dy.device) if has_bias else None
+            nbw = _lib.size("da_conv3d_wgrad_workspace_bytes", Cin, Cout, ks)
+            wsw = _ws(nbw, dy.device)
+            _lib.call("da_conv3d_wgrad", _p(x1), C1, _p(x2), C2, _p(dy), int(transposed), _p(dw), _p(db), N, Di, Hi,
+                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, st)
+        return dx1, dx2, dw, db, None, None, None, None
+
+
+def conv3d(x1, weight, bias=None, x2=None, transposed=False, stride=1, pad=1, slope=None):
+    return Conv3dFunction.apply(x1, x2, weight, bias, transposed, stride, pad, slope)
+
+
+# ------------------------------------------------------------------------------------------------------
+# batch norm (+ activation)  (lib/network_factory/unets.py:31-32,51)
+# ------------------------------------------------------------------------------------------------------
+class BnActFunction(torch.autograd.Function):
+    """y = act(batch_norm(x)); training mode uses batch statistics and updates the running buffers in
+    place (momentum, unbiased variance) exactly as nn.BatchNorm3d; eval mode uses the running buffers."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training: bool, momentum: float, eps: float,
+                slope):
+        x = _f32(x, "x")
+        N, C = x.shape[:2]
+        V = x[0, 0].numel()
+        dev = x.device
+        st = _stream()
+        nb = _lib.size("da_bn_workspace_bytes", C)
+        if training:
+            mean = torch.empty((C,), dtype=torch.float32, device=dev)
+            invstd = torch.empty((C,), dtype=torch.float32, device=dev)
+            ws = _ws(nb, dev)
+            _lib.call("da_bn_stats", _p(x), N, C, V, float(eps), float(momentum), _p(mean), _p(invstd),
+                      _p(running_mean), _p(running_var), _p(ws), nb, st)
+        else:
+            mean = running_mean.detach().float().contiguous()
+            invstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
+        y = torch.empty_like(x)
+        _lib.call("da_bn_act_fwd", _p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), N, C, V,
+                  0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(y), st)
+        ctx.save_for_backward(x, mean, invstd, gamma, beta)
+        ctx.cfg = (bool(training), slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd, gamma, beta = ctx.saved_tensors
+        training, slope = ctx.cfg
+        dy = _f32(dy, "grad_out")
+        N, C = x.shape[:2]
+        V = x[0, 0].numel()
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(mean)
+        db = torch.empty_like(mean)
+        nb = _lib.size("da_bn_workspace_bytes", C)
+        ws = _ws(nb, x.device)
+        _lib.call("da_bn_act_bwd", _p(dy), _p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), N, C, V, int(training),
+                  0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(dx), _p(dg), _p(db),
+                  _p(ws), nb, _stream())
+        return dx, (dg if gamma is not None else None), (db if beta is not None else None), None, None, None, None, None, None
+
+
+def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, slope=None):
+    return BnActFunction.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, slope)
+
+
+# ------------------------------------------------------------------------------------------------------
+# max-pool 2, nearest upsample, deconv k2 s2
+# ------------------------------------------------------------------------------------------------------
+class MaxPool2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x, "x")
+        N, C, D, H, W = x.shape
+        y = torch.empty((N, C, D // 2, H // 2, W // 2), dtype=torch.float32, device=x.device)
+        _lib.call("da_maxpool2_fwd", _p(x), _p(y), N * C, D, H, W, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, C, D, H, W = x.shape
+        dy = _f32(dy, "grad_out")
+        dx = torch.empty_like(x)
+        _lib.call("da_maxpool2_bwd", _p(dy), _p(x), _p(dx), N * C, D, H, W, _stream())
+        return dx
+
+
+def maxpool2(x):
+    return MaxPool2Function.apply(x)
+
+
+class UpsampleNearestFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size: Tuple[int, int, int]):
+        x = _f32(x, "x")
+        N, C, D, H, W = x.shape
+        Do, Ho, Wo = (int(s) for s in size)
+        y = torch.empty((N, C, Do, Ho, Wo), dtype=torch.float32, device=x.device)
+        _lib.call("da_upsample_nearest_fwd", _p(x), _p(y), N * C, D, H, W, Do, Ho, Wo, _stream())
+        ctx.shape = (N, C, D, H, W, Do, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, D, H, W, Do, Ho, Wo = ctx.shape
+        dy = _f32(dy, "grad_out")
+        dx = torch.empty((N, C, D, H, W), dtype=torch.float32, device=dy.device)
+        _lib.call("da_upsample_nearest_bwd", _p(dy), _p(dx), N * C, D, H, W, Do, Ho, Wo, _stream())
+        return dx, None
+
+
+def upsample_nearest(x, size: Sequence[int]):
+    if tuple(x.shape[2:]) == tuple(size):
+        return x
+    return UpsampleNearestFunction.apply(x, tuple(size))
+
+
+class DeconvK2S2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight = _f32(x, "x"), _f32(weight, "weight")
+        bias = _f32(bias, "bias") if bias is not None else None
+        N, Cin, D, H, W = x.shape
+        if weight.shape[0] != Cin or tuple(weight.shape[2:]) != (2, 2, 2):
+            raise ValueError(f"deconv_k2s2: weight must be ({Cin},Cout,2,2,2), got {tuple(weight.shape)}")
+        Cout = weight.shape[1]
+        out = torch.empty((N, Cout, 2 * D, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        _lib.call("da_deconv_k2s2_fwd", _p(x), _p(weight), _p(bias), _p(out), N, Cin, Cout, D, H, W, _stream())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _f32(dy, "grad_out")
+        N, Cin, D, H, W = x.shape
+        Cout = weight.shape[1]
+        st = _stream()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.call("da_deconv_k2s2_dgrad", _p(dy), _p(weight), _p(dx), N, Cin, Cout, D, H, W, st)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(weight)
+            db = torch.empty((Cout,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            nb = _lib.size("da_deconv_k2s2_wgrad_workspace_bytes", Cin, Cout)
+            ws = _ws(nb, dy.device)
+            _lib.call("da_deconv_k2s2_wgrad", _p(x), _p(dy), _p(dw), _p(db), N, Cin, Cout, D, H, W, _p(ws), nb, st)
+        return dx, dw, db
+
+
+def deconv_k2s2(x, weight, bias=None):
+    return DeconvK2S2Function.apply(x, weight, bias)

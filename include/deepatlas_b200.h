@@ -1,0 +1,142 @@
+/* deepatlas_b200.h -- C ABI of libdeepatlas_b200.so (sm_100a).
+ *
+ * The reference (uncbiag/DeepAtlas) has no FFI of its own: its hot path sits behind two Python dict
+ * registries, `network_dic` (lib/network_factory/__init__.py:9-16) and `loss_dict` (lib/loss.py:739-750).
+ * The entry points below are what a binding for that path attaches to: one forward / backward pair per
+ * library op the reference's modules call, taking raw DEVICE pointers, extents, scalar
+ * hyper-parameters, a caller-owned workspace and a CUDA stream.  No torch types cross this boundary.
+ *
+ * Conventions
+ *   - all tensors are dense planar NCDHW fp32 (the reference's layout) unless stated otherwise;
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative library code
+ *     (-1 bad argument, -2 unsupported configuration, -3 workspace too small); the message is
+ *     available from da_last_error() (thread-local);
+ *   - the library never allocates or frees device memory; `*_bytes` queries size the workspaces;
+ *   - calls are asynchronous on `stream` and re-entrant (the autograd engine calls backward from its
+ *     own thread).
+ */
+#ifndef DEEPATLAS_B200_H
+#define DEEPATLAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* da_stream_t; /* == cudaStream_t */
+
+int da_version(void);
+const char* da_last_error(void);
+int da_memset_zero(void* dst, int64_t bytes, da_stream_t stream);
+
+/* ---- warp3d: identity grid + displacement + trilinear grid_sample in one pass ------------------------
+ * replaces lib/utils.py:89-102 (get_identity_transform), lib/network_factory/voxel_morph.py:88 (disp + id)
+ * and voxel_morph.py:90-91 (F.grid_sample bilinear / zeros / align_corners=True) and their autograd.
+ * src [N,C,D,H,W]; field [N,3,Do,Ho,Wo] (channel 0 = x/W, 1 = y/H, 2 = z/D, normalised [-1,1]);
+ * out [N,C,Do,Ho,Wo]; phi_out (nullable) receives field (+ identity). */
+int da_warp3d_fwd(const float* src, const float* field, int add_identity, float* out, float* phi_out,
+                  int N, int C, int D, int H, int W, int Do, int Ho, int Wo, da_stream_t stream);
+int da_warp3d_bwd(const float* grad_out, const float* src, const float* field, int add_identity,
+                  float* grad_src, float* grad_field, int N, int C, int D, int H, int W, int Do, int Ho,
+                  int Wo, da_stream_t stream);
+
+/* ---- softmax + Dice sums -----------------------------------------------------------------------------
+ * replaces F.softmax (lib/loss.py:427), mask_to_one_hot (lib/transforms.py:675-689) and the three
+ * spatial sums of DiceLossMultiClass.forward (lib/loss.py:449-450,472).
+ * source [N,C,V]; target_kind 0 = uint8 labels [N,V], 1 = int64 labels, 3 = int32 labels,
+ * 2 = soft target fp32 [N,C,V].  sums [N,3,C] = (S = sum p, T = sum t, I = sum p*t). */
+int64_t da_dice_workspace_bytes(int N, int C, int64_t V);
+int da_dice_sums_fwd(const float* source, const void* target, int target_kind, int apply_softmax, int N,
+                     int C, int64_t V, float* sums, void* workspace, int64_t workspace_bytes,
+                     da_stream_t stream);
+int da_dice_sums_bwd(const float* source, const void* target, int target_kind, int apply_softmax, int N,
+                     int C, int64_t V, const float* gS, const float* gT, const float* gI,
+                     float* grad_source, float* grad_target, da_stream_t stream);
+
+/* channel softmax (F.softmax(dim=1)) materialised for the anatomy branch, where probabilities are warped */
+int da_softmax_fwd(const float* x, float* y, int N, int C, int64_t V, da_stream_t stream);
+int da_softmax_bwd(const float* y, const float* dy, float* dx, int N, int C, int64_t V, da_stream_t stream);
+
+/* ---- local NCC (VoxelMorphLNCC.forward, lib/loss.py:597-617) --------------------------------------------
+ * I,J [N,1,D,H,W]; loss_out: one device float = 1 - mean(cc).  need_grad bit0 = I, bit1 = J; `coef`
+ * (da_lncc_coef_bytes) is saved by forward for backward. */
+int64_t da_lncc_coef_bytes(int N, int D, int H, int W, int win, int need_grad);
+int64_t da_lncc_fwd_workspace_bytes(int N, int D, int H, int W, int win);
+int64_t da_lncc_bwd_workspace_bytes(int N, int D, int H, int W, int win);
+int da_lncc_fwd(const float* I, const float* J, int N, int D, int H, int W, int win, double eps,
+                int need_grad, float* loss_out, void* coef, void* workspace, int64_t workspace_bytes,
+                da_stream_t stream);
+int da_lncc_bwd(const float* I, const float* J, const float* grad_out, const void* coef, int coef_slot,
+                int which, int N, int D, int H, int W, int win, float* grad, void* workspace,
+                int64_t workspace_bytes, da_stream_t stream);
+
+/* ---- bending energy (BendingEnergyLoss.forward, lib/loss.py:687-730) -----------------------------------
+ * u [N,3,D,H,W]; sums [N,3,6]: per channel, sum over the interior of the squared second differences in
+ * the order ddD, ddH, ddW, dDdH, dHdW, dDdW. */
+int64_t da_bending_fwd_workspace_bytes(int N);
+int64_t da_bending_bwd_workspace_bytes(int N, int D, int H, int W);
+int da_bending_fwd(const float* u, int N, int D, int H, int W, float* sums, void* workspace,
+                   int64_t workspace_bytes, da_stream_t stream);
+int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, int H, int W, float* grad_u,
+                   void* workspace, int64_t workspace_bytes, da_stream_t stream);
+
+/* ---- 3D convolution --------------------------------------------------------------------------------------
+ * nn.Conv3d k3 (stride 1/2, pad 1) and k1: lib/network_factory/unets.py:30,36,98,115,120,250,
+ * lib/network_factory/modules.py:48, lib/network_factory/voxel_morph.py:57; nn.ConvTranspose3d k3 s1 p1
+ * (`transposed` = 1, weight (Cin,Cout,3,3,3)): unets.py:128,134 as used by UNet.dc8/dc7/dc5/dc4/dc2/dc1.
+ * The conv input is cat(x1, x2) along channels (torch.cat at unets.py:275,157-171, voxel_morph.py:65-82);
+ * x2 may be NULL with C2 = 0.  act: 0 none, 1 fused leaky-ReLU(slope) (slope 0 = ReLU). */
+int da_set_conv_impl(int impl); /* 0 = auto (tiled where applicable), 1 = generic direct kernel */
+int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks);
+int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks);
+int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed,
+                  const float* bias, float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride,
+                  int pad, int act, float slope, void* workspace, int64_t workspace_bytes,
+                  da_stream_t stream);
+int da_conv3d_dgrad(const float* dy, const float* weight, int transposed, float* dx, int N, int Cin_total,
+                    int ci_off, int Cdx, int Cout, int Di, int Hi, int Wi, int ks, int stride, int pad,
+                    void* workspace, int64_t workspace_bytes, da_stream_t stream);
+int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
+                    float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
+                    int stride, int pad, void* workspace, int64_t workspace_bytes, da_stream_t stream);
+int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, da_stream_t stream);
+
+/* ---- batch norm (train mode) + activation; max-pool; nearest upsampling ---------------------------------
+ * nn.BatchNorm3d (unets.py:31,51,116,130), nn.LeakyReLU / nn.ReLU (unets.py:32, modules.py:58),
+ * nn.MaxPool3d(2) (unets.py:84-86,230), F.interpolate(size=) nearest (voxel_morph.py:72-80). */
+int64_t da_bn_workspace_bytes(int C);
+int da_bn_stats(const float* x, int N, int C, int64_t V, float eps, float momentum, float* mean,
+                float* invstd, float* running_mean, float* running_var, void* workspace,
+                int64_t workspace_bytes, da_stream_t stream);
+int da_bn_act_fwd(const float* x, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, int N, int C, int64_t V, int act, float slope, float* y,
+                  da_stream_t stream);
+int da_bn_act_bwd(const float* dy, const float* x, const float* mean, const float* invstd,
+                  const float* gamma, const float* beta, int N, int C, int64_t V, int training, int act,
+                  float slope, float* dx, float* dgamma, float* dbeta, void* workspace,
+                  int64_t workspace_bytes, da_stream_t stream);
+int da_act_bwd(const float* dy, const float* y, float slope, int64_t total, float* dx, da_stream_t stream);
+int da_maxpool2_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, da_stream_t stream);
+int da_maxpool2_bwd(const float* dy, const float* x, float* dx, int64_t NC, int D, int H, int W,
+                    da_stream_t stream);
+int da_upsample_nearest_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, int Do, int Ho,
+                            int Wo, da_stream_t stream);
+int da_upsample_nearest_bwd(const float* dy, float* dx, int64_t NC, int D, int H, int W, int Do, int Ho,
+                            int Wo, da_stream_t stream);
+
+/* ---- ConvTranspose3d kernel 2 stride 2 (unets.deconvBlock, unets.py:42-58,240-241; UNet.dc9/dc6/dc3) ---
+ * x [N,Cin,D,H,W]; weight (Cin,Cout,2,2,2); out [N,Cout,2D,2H,2W]. */
+int64_t da_deconv_k2s2_wgrad_workspace_bytes(int Cin, int Cout);
+int da_deconv_k2s2_fwd(const float* x, const float* weight, const float* bias, float* out, int N, int Cin,
+                       int Cout, int D, int H, int W, da_stream_t stream);
+int da_deconv_k2s2_dgrad(const float* dy, const float* weight, float* dx, int N, int Cin, int Cout, int D,
+                         int H, int W, da_stream_t stream);
+int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N,
+                         int Cin, int Cout, int D, int H, int W, void* workspace, int64_t workspace_bytes,
+                         da_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPATLAS_B200_H */

@@ -1,0 +1,125 @@
+"""GPU parity tests for whole networks and the joint seg+reg step (CUDA path vs the CPU oracle)."""
+import pytest
+import torch
+
+from parity_util import cpu_state, oracle_joint_loss, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4        # forward outputs (north star)
+GTOL = 1e-3       # parameter gradients through 15-30 layers with batch-1 BatchNorm (fp32 round-off amplification;
+                  # the reference's own fp32-vs-fp64 gradient noise at these depths is of the same order)
+
+
+def _param_grads(model):
+    return {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("n_classes,size,bn", [(4, (32, 32, 32), True), (32, (16, 24, 16), True), (3, (16, 16, 24), False)])
+def test_unet_light(cuda, n_classes, size, bn):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    torch.manual_seed(230)
+    net = da.get_network("UNet_light")(1, n_classes, bias=True, BN=bn).to(cuda)
+    net.weights_init()
+    g = torch.Generator().manual_seed(230)
+    x = torch.rand((1, 1) + size, generator=g)
+    lab = torch.randint(0, n_classes, (1,) + size, generator=g, dtype=torch.uint8)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in cpu_state(net).items()}
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in cpu_state(net).items()}
+    stats = {}
+    y_ref = P.unet_generator_forward(x, sd, 1, bn, stats_out=stats)
+    y64 = P.unet_generator_forward(x.double(), sd64, 1, bn)
+    crit = da.get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", softmax=True, eps=1e-6)
+    y = net(x.to(cuda))
+    loss = crit(y, lab.to(cuda))
+    loss.backward()
+    loss_ref = P.dice_multiclass(y_ref, lab.long(), n_classes, "Uniform", False, True, 1e-6)
+    loss_ref.backward()
+    assert y.shape == y_ref.shape
+    assert rel_err(y, y_ref) < max(TOL, 2 * rel_err(y_ref, y64)), f"logits rel err {rel_err(y, y_ref):.3e}"
+    assert rel_err(loss, loss_ref) < TOL
+    # label argmax indices: bit-exact wherever the oracle's own top-2 margin is above fp32 round-off
+    top2 = y64.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 1e-5 * y64.abs().max()
+    assert torch.equal(y.argmax(1).cpu()[decided], y_ref.argmax(1)[decided])
+    assert decided.float().mean() > 0.99
+    grads = _param_grads(net)
+    for k, gr in grads.items():
+        e = rel_err(gr, sd[k].grad)
+        assert e < GTOL, f"grad {k}: rel err {e:.3e}"
+    if bn:  # running statistics updated exactly like nn.BatchNorm3d
+        for k, v in stats.items():
+            assert rel_err(net.state_dict()[k], v) < 1e-4, k
+        assert int(net.state_dict()["encoders.0.0.BN.num_batches_tracked"]) == 1
+
+
+def test_unet_32base(cuda):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    torch.manual_seed(230)
+    net = da.get_network("UNet")(1, 4, bias=True, BN=True).to(cuda)
+    net.weights_init()
+    x = torch.rand((1, 1, 16, 16, 16), generator=torch.Generator().manual_seed(230))
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in cpu_state(net).items()}
+    y_ref = P.unet_forward(x, sd, True)
+    y = net(x.to(cuda))
+    assert rel_err(y, y_ref) < 5e-4, f"UNet logits rel err {rel_err(y, y_ref):.3e}"   # 19 conv layers, K up to 20736
+    cot = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(7))
+    (y * cot.to(cuda)).sum().backward()
+    (y_ref * cot).sum().backward()
+    for k, gr in _param_grads(net).items():
+        e = rel_err(gr, sd[k].grad)
+        assert e < 2e-3, f"grad {k}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("size", [(32, 48, 32), (16, 16, 16), (24, 20, 36)])
+def test_voxelmorph(cuda, size):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    torch.manual_seed(230)
+    net = da.get_network("voxel_morph_cvpr")().to(cuda)
+    net.weights_init()
+    g = torch.Generator().manual_seed(230)
+    s, t = torch.rand((1, 1) + size, generator=g), torch.rand((1, 1) + size, generator=g)
+    sd = {k: v.clone().requires_grad_(True) for k, v in cpu_state(net).items()}
+    ref = P.voxelmorph_forward(s, t, sd)
+    out = net(s.to(cuda), t.to(cuda))
+    for name, a, b in zip(("disp", "warped", "deform"), out, ref):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < TOL, f"{name}: rel err {rel_err(a, b):.3e}"
+    lncc, bend = da.get_loss_function("lncc")(), da.get_loss_function("bendingEnergy")()
+    (lncc(out[1], t.to(cuda)) + 1000.0 * bend(out[0])).backward()
+    (P.lncc(ref[1], t) + 1000.0 * P.bending_energy(ref[0])).backward()
+    for k, gr in _param_grads(net).items():
+        e = rel_err(gr, sd[k].grad)
+        assert e < GTOL, f"grad {k}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("C,size", [(4, (16, 16, 16)), (32, (16, 24, 16))])
+def test_joint_step(cuda, C, size):
+    from deepatlas_b200.joint import JointModel, make_synthetic_pair
+    from oracle import ref_port as P
+    torch.manual_seed(230)
+    model = JointModel(n_classes=C).to(cuda)
+    model.weights_init()
+    batch = make_synthetic_pair(size, C, seed=230, device=cuda)
+    loss, parts = model.joint_loss(*batch)
+    loss.backward()
+    ref_loss, ref_grads = oracle_joint_loss(model, batch, P)
+    assert rel_err(loss, ref_loss) < TOL
+    n = 0
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        e = rel_err(p.grad, ref_grads[k])
+        assert e < 2e-3, f"grad {k}: rel err {e:.3e}"
+        n += 1
+    assert n >= 60
+
+
+def test_registry_errors_and_install(built_lib):
+    import deepatlas_b200 as da
+    with pytest.raises(KeyError):
+        da.get_network("nope")
+    with pytest.raises(KeyError):
+        da.get_loss_function("nope")

@@ -1,0 +1,274 @@
+"""GPU parity tests, op by op: the CUDA path (through the C ABI) against the CPU oracle
+(oracle/ref_port.py) on the same seeded inputs.  Tolerance: 1e-4 max-norm relative (north star) for
+fp32 outputs and gradients unless a test states otherwise; index results bit-exact."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from parity_util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _g(seed=230):
+    return torch.Generator().manual_seed(seed)
+
+
+def _run_both(fn_gpu, fn_cpu, inputs, cuda, grad_mask=None):
+    """inputs: list of CPU tensors; float ones get requires_grad per grad_mask. Returns (out_gpu, grads_gpu, out_cpu, grads_cpu)."""
+    grad_mask = grad_mask or [t.is_floating_point() for t in inputs]
+    gi = [t.to(cuda).requires_grad_(m) if t.is_floating_point() else t.to(cuda) for t, m in zip(inputs, grad_mask)]
+    ci = [t.clone().requires_grad_(m) if t.is_floating_point() else t.clone() for t, m in zip(inputs, grad_mask)]
+    og, oc = fn_gpu(*gi), fn_cpu(*ci)
+    og_l = og if isinstance(og, (tuple, list)) else [og]
+    oc_l = oc if isinstance(oc, (tuple, list)) else [oc]
+    gen = _g(7)
+    cot = [torch.randn(o.shape, generator=gen) for o in oc_l]
+    sum((o * c.to(cuda)).sum() for o, c in zip(og_l, cot)).backward()
+    sum((o * c).sum() for o, c in zip(oc_l, cot)).backward()
+    gg = [t.grad if (t.is_floating_point() and m) else None for t, m in zip(gi, grad_mask)]
+    cg = [t.grad if (t.is_floating_point() and m) else None for t, m in zip(ci, grad_mask)]
+    return og_l, gg, oc_l, cg
+
+
+def _check(og, gg, oc, cg, tol=TOL, what=""):
+    for i, (a, b) in enumerate(zip(og, oc)):
+        e = rel_err(a, b)
+        assert e < tol, f"{what} output {i}: rel err {e:.3e}"
+    for i, (a, b) in enumerate(zip(gg, cg)):
+        if b is None:
+            continue
+        assert a is not None, f"{what} grad {i} missing"
+        e = rel_err(a, b)
+        assert e < tol, f"{what} grad {i}: rel err {e:.3e}"
+
+
+# ----------------------------------------------------------------------------------------------------------
+def test_no_cpu_fallback(built_lib):
+    from deepatlas_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.softmax(torch.zeros(1, 2, 4, 4, 4))
+
+
+@pytest.mark.parametrize("C,size", [(1, (12, 14, 16)), (5, (9, 10, 11))])
+@pytest.mark.parametrize("add_id", [True, False])
+def test_warp3d(cuda, C, size, add_id):
+    from deepatlas_b200 import ops
+    from oracle import ref_port as P
+    g = _g()
+    src = torch.rand((2, C) + size, generator=g)
+    field = torch.randn((2, 3) + size, generator=g) * 0.35   # large enough to leave the volume at the borders
+    if not add_id:
+        field = field + P.identity_transform(size)[None]
+
+    def cpu(s, f):
+        phi = f + P.identity_transform(size)[None] if add_id else f
+        return P.warp(s, phi), phi
+
+    def gpu(s, f):
+        return ops.warp3d(s, f, add_identity=add_id, want_phi=True)
+
+    res = _run_both(gpu, cpu, [src, field], cuda)
+    _check(*res, what="warp3d")
+    # independent closed form (fp64) as the truth rung
+    truth = P.warp_closed_form(src.double(), (field + P.identity_transform(size)[None] if add_id else field).double())
+    assert rel_err(res[0][0], truth) < TOL
+
+
+def test_warp3d_identity_reproduces_input(cuda):
+    from deepatlas_b200 import ops
+    src = torch.rand((1, 2, 8, 9, 10), generator=_g()).to(cuda)
+    out = ops.warp3d(src, torch.zeros((1, 3, 8, 9, 10), device=cuda), add_identity=True)
+    assert rel_err(out, src) < 1e-5
+
+
+@pytest.mark.parametrize("C", [2, 4, 7, 32])
+@pytest.mark.parametrize("softmax", [True, False])
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+def test_dice_hard_target(cuda, C, softmax, dtype):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    g = _g()
+    size = (10, 12, 14)
+    x = torch.randn((2, C) + size, generator=g)
+    if not softmax:
+        x = torch.softmax(x, 1)
+    t = torch.randint(0, C, (2,) + size, generator=g).to(dtype)
+    for wt in ("Uniform", "Simple", "Volume"):
+        for no_bg in (False, True):
+            crit = da.get_loss_function("dice")(n_class=C, weight_type=wt, no_bg=no_bg, softmax=softmax, eps=1e-6)
+            res = _run_both(lambda a, b: crit(a, b), lambda a, b: P.dice_multiclass(a, b.long(), C, wt, no_bg, softmax, 1e-6),
+                            [x, t], cuda)
+            _check(*res, what=f"dice {wt} no_bg={no_bg}")
+
+
+def test_dice_soft_target_and_identities(cuda):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    g = _g()
+    C, size = 4, (8, 8, 8)
+    s = torch.softmax(torch.randn((1, C) + size, generator=g), 1)
+    t = torch.softmax(torch.randn((1, C) + size, generator=g), 1)
+    crit = da.get_loss_function("dice")(n_class=C, weight_type="Uniform", softmax=False, eps=1e-6)
+    res = _run_both(lambda a, b: crit(a, b), lambda a, b: P.dice_multiclass(a, b, C, "Uniform", False, False, 1e-6), [s, t], cuda)
+    _check(*res, what="dice soft")
+    # Dice(one-hot(t), t) == 0 exactly-ish (SURVEY section 4 identity)
+    lab = torch.randint(0, C, (1,) + size, generator=g)
+    oh = P.mask_to_one_hot(lab.reshape(1, 1, -1), C).reshape((1, C) + size)
+    assert abs(float(crit(oh.to(cuda), lab.to(cuda)))) < 1e-6
+    with pytest.raises(ValueError):
+        crit(s.to(cuda), torch.zeros((1, C + 1) + size, device=cuda))
+
+
+def test_softmax_op(cuda):
+    from deepatlas_b200 import ops
+    x = torch.randn((2, 6, 5, 6, 7), generator=_g()) * 3
+    res = _run_both(ops.softmax, lambda a: torch.softmax(a, 1), [x], cuda)
+    _check(*res, what="softmax")
+
+
+@pytest.mark.parametrize("size", [(12, 14, 16), (9, 9, 9), (20, 11, 13)])
+def test_lncc(cuda, size):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    g = _g()
+    I = torch.rand((2, 1) + size, generator=g)
+    J = torch.rand((2, 1) + size, generator=g)
+    crit = da.get_loss_function("lncc")().to(cuda)
+    og, gg, oc, cg = _run_both(lambda a, b: crit(a, b), lambda a, b: P.lncc(a, b), [I, J], cuda)
+    # truth rung: fp64 oracle.  Parity rule for LNCC: our error vs fp64 <= max(1e-4, reference fp32 error vs fp64)
+    Id, Jd = I.double().requires_grad_(True), J.double().requires_grad_(True)
+    ld = P.lncc(Id, Jd)
+    cot = torch.randn(oc[0].shape, generator=_g(7))
+    (ld * cot.double()).sum().backward()
+    assert rel_err(og[0], ld) < max(TOL, rel_err(oc[0], ld))
+    for ours, ref32, truth in zip(gg, cg, (Id.grad, Jd.grad)):
+        assert rel_err(ours, truth) < max(TOL, rel_err(ref32, truth))
+    # identities: LNCC(I,I) == 0, LNCC(I, aI+b) ~ 0
+    Ic = I.to(cuda)
+    assert abs(float(crit(Ic, Ic))) < 1e-5
+    assert abs(float(crit(Ic, 2.0 * Ic + 0.5))) < 1e-4
+
+
+@pytest.mark.parametrize("size,spacing", [((10, 12, 14), (1, 1, 1)), ((7, 9, 8), (1, 2, 3))])
+def test_bending(cuda, size, spacing):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    u = torch.randn((2, 3) + size, generator=_g()) * 0.1
+    crit = da.get_loss_function("bendingEnergy")(spacing=spacing)
+    res = _run_both(lambda a: crit(a), lambda a: P.bending_energy(a, spacing), [u], cuda)
+    _check(*res, what="bending")
+    # affine field has zero bending energy
+    idt = P.identity_transform(size)[None].to(cuda)
+    assert float(crit(idt * 0.3 + 0.1)) < 1e-10
+
+
+CONV_CASES = [
+    # C1, C2, Cout, ks, stride, size, transposed
+    (1, 0, 8, 3, 1, (8, 10, 12), False),
+    (2, 0, 16, 3, 1, (8, 10, 12), False),
+    (8, 0, 16, 3, 1, (36, 20, 48), False),      # tiled path (V >= 32768, W >= 16)
+    (16, 32, 16, 3, 1, (32, 34, 40), False),    # tiled, two sources, ragged tiles
+    (8, 16, 3, 3, 1, (32, 32, 36), False),      # flow-like head Cout=3
+    (20, 0, 12, 3, 1, (33, 32, 35), False),     # odd extents, channel counts off the register tiles
+    (16, 0, 32, 3, 2, (16, 18, 20), False),     # stride 2
+    (32, 0, 32, 3, 2, (9, 11, 13), False),      # stride 2, odd extents
+    (16, 0, 7, 1, 1, (8, 9, 10), False),        # 1x1 head
+    (24, 8, 16, 3, 1, (8, 8, 8), True),         # ConvTranspose3d k3 s1 p1, two sources
+    (16, 0, 8, 3, 1, (32, 32, 32), True),       # ConvTranspose3d through the tiled kernel
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", ["auto", "direct"])
+@pytest.mark.parametrize("slope", [None, 0.0])
+def test_conv3d(cuda, case, impl, slope):
+    from deepatlas_b200 import _lib, ops
+    C1, C2, Cout, ks, stride, size, transposed = case
+    if impl == "direct" and slope is not None:
+        pytest.skip("activation epilogue covered by the auto run")
+    g = _g()
+    x1 = torch.randn((2, C1) + size, generator=g)
+    x2 = torch.randn((2, C2) + size, generator=g) if C2 else None
+    Cin = C1 + C2
+    w = torch.randn((Cin, Cout, ks, ks, ks) if transposed else (Cout, Cin, ks, ks, ks), generator=g) * (2.0 / (Cin * ks ** 3)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    pad = 1 if ks == 3 else 0
+
+    def cpu(*a):
+        a = list(a)
+        xx = torch.cat((a[0], a[1]), 1) if C2 else a[0]
+        ww, bb = a[-2], a[-1]
+        y = F.conv_transpose3d(xx, ww, bb, stride=1, padding=1) if transposed else F.conv3d(xx, ww, bb, stride=stride, padding=pad)
+        return y if slope is None else F.leaky_relu(y, slope)
+
+    def gpu(*a):
+        a = list(a)
+        return ops.conv3d(a[0], a[-2], a[-1], x2=a[1] if C2 else None, transposed=transposed, stride=stride, pad=pad, slope=slope)
+
+    ins = [x1] + ([x2] if C2 else []) + [w, b]
+    _lib.call("da_set_conv_impl", 1 if impl == "direct" else 0)
+    try:
+        res = _run_both(gpu, cpu, ins, cuda)
+    finally:
+        _lib.call("da_set_conv_impl", 0)
+    _check(*res, what=f"conv3d {case} {impl}")
+
+
+@pytest.mark.parametrize("slope", [0.01, 0.0, None])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act(cuda, slope, training):
+    from deepatlas_b200 import ops
+    g = _g()
+    C = 6
+    x = torch.randn((2, C, 6, 7, 9), generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    rm0, rv0 = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    rm_g, rv_g = rm0.clone().to(cuda), rv0.clone().to(cuda)
+    rm_c, rv_c = rm0.clone(), rv0.clone()
+
+    def cpu(a, ga, be):
+        y = F.batch_norm(a, rm_c, rv_c, ga, be, training=training, momentum=0.1, eps=1e-5)
+        return y if slope is None else F.leaky_relu(y, slope)
+
+    def gpu(a, ga, be):
+        return ops.bn_act(a, ga, be, rm_g, rv_g, training=training, momentum=0.1, eps=1e-5, slope=slope)
+
+    res = _run_both(gpu, cpu, [x, gamma, beta], cuda)
+    _check(*res, what="bn_act")
+    assert rel_err(rm_g, rm_c) < 1e-5 and rel_err(rv_g, rv_c) < 1e-5
+
+
+def test_maxpool2_first_max_tie_rule(cuda):
+    from deepatlas_b200 import ops
+    g = _g()
+    # heavy ties: ReLU-like data with many exact zeros and repeated values
+    x = torch.randint(0, 3, (2, 3, 8, 10, 12), generator=g).float()
+    res = _run_both(ops.maxpool2, lambda a: F.max_pool3d(a, 2), [x], cuda)
+    for a, b in zip(res[0], res[2]):
+        assert torch.equal(a.cpu(), b)
+    assert torch.equal(res[1][0].cpu(), res[3][0])      # gradient routed to the same (first) maximum
+    xo = torch.randn((1, 2, 7, 9, 11), generator=g)      # odd extents (floor)
+    res = _run_both(ops.maxpool2, lambda a: F.max_pool3d(a, 2), [xo], cuda)
+    assert torch.equal(res[0][0].cpu(), res[2][0]) and torch.equal(res[1][0].cpu(), res[3][0])
+
+
+@pytest.mark.parametrize("sin,sout", [((5, 6, 5), (10, 12, 10)), ((3, 4, 5), (7, 9, 10)), ((4, 4, 4), (5, 4, 13))])
+def test_upsample_nearest(cuda, sin, sout):
+    from deepatlas_b200 import ops
+    x = torch.randn((2, 3) + sin, generator=_g())
+    res = _run_both(lambda a: ops.upsample_nearest(a, sout), lambda a: F.interpolate(a, size=sout), [x], cuda)
+    assert torch.equal(res[0][0].cpu(), res[2][0])
+    assert rel_err(res[1][0], res[3][0]) < 1e-6
+
+
+@pytest.mark.parametrize("Cin,Cout,size", [(8, 8, (4, 5, 6)), (32, 32, (6, 6, 8)), (6, 10, (3, 4, 5)), (64, 64, (5, 6, 5))])
+def test_deconv_k2s2(cuda, Cin, Cout, size):
+    from deepatlas_b200 import ops
+    g = _g()
+    x = torch.randn((2, Cin) + size, generator=g)
+    w = torch.randn((Cin, Cout, 2, 2, 2), generator=g) * (1.0 / Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    res = _run_both(lambda a, ww, bb: ops.deconv_k2s2(a, ww, bb), lambda a, ww, bb: F.conv_transpose3d(a, ww, bb, stride=2), [x, w, b], cuda)
+    _check(*res, what="deconv_k2s2")
