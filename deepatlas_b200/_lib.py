@@ -20,6 +20,7 @@ SIGNATURES = {
     "da_version": ("", "int"),
     "da_last_error": ("", "str"),
     "da_memset_zero": ("pls", "rc"),
+    "da_launch_count": ("", "size"),
     # warp3d
     "da_warp3d_fwd": ("ppippiiiiiiiis", "rc"),
     "da_warp3d_bwd": ("pppippiiiiiiiis", "rc"),

@@ -123,7 +123,7 @@ DA_API int da_bending_fwd(const float* u, int N, int D, int H, int W, float* sum
   Geo g = make_geo(D, H, W);
   bending_fwd_kernel<<<BE_BLOCKS, BE_THREADS, 0, stream>>>(u, N, g, (double*)workspace);
   bending_finalize_kernel<<<(N * 18 + 63) / 64, 64, 0, stream>>>((const double*)workspace, BE_BLOCKS, N * 18, sums);
-  return da_check_launch("da_bending_fwd");
+  return da_check_launch("da_bending_fwd", 2);
 }
 
 // grad_sums [N,3,6] upstream; grad_u [N,3,D,H,W]
@@ -137,5 +137,5 @@ DA_API int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, 
   const int grid = (int)(b > (int64_t)DA_NUM_SMS * 16 ? (int64_t)DA_NUM_SMS * 16 : b);
   bending_resid_kernel<<<grid, BE_THREADS, 0, stream>>>(u, N, g, (float*)workspace);
   bending_gather_kernel<<<grid, BE_THREADS, 0, stream>>>((const float*)workspace, grad_sums, N, g, grad_u);
-  return da_check_launch("da_bending_bwd");
+  return da_check_launch("da_bending_bwd", 2);
 }

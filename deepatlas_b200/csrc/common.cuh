@@ -14,7 +14,8 @@
 #define DA_ERR_WORKSPACE (-3)
 
 void da_set_error(const char* fmt, ...);
-int da_check_launch(const char* what);
+// checks cudaGetLastError() and adds `nkernels` to the library's launch counter (da_launch_count)
+int da_check_launch(const char* what, int nkernels = 1);
 
 #define DA_REQUIRE(cond, ...)            \
   do {                                   \

@@ -180,7 +180,7 @@ DA_API int da_lncc_fwd(const float* I, const float* J, int N, int D, int H, int 
   lncc_zsum_cc_kernel<<<LNCC_RED_BLOCKS, 256, 0, stream>>>(t2, N, D, Dv, (int64_t)Hv * Wv, win, eps, need_grad,
                                                             (double*)coef, partials);
   lncc_finalize_kernel<<<1, 32, 0, stream>>>(partials, LNCC_RED_BLOCKS, (double)N * Dv * Hv * Wv, loss_out);
-  return da_check_launch("da_lncc_fwd");
+  return da_check_launch("da_lncc_fwd", 4);
 }
 
 // grad_out: 1 float on device (upstream gradient of the scalar loss).  which: 0 -> grad wrt I, 1 -> grad wrt J
@@ -203,5 +203,5 @@ DA_API int da_lncc_bwd(const float* I, const float* J, const float* grad_out, co
   const int64_t rows = (int64_t)N * D * H;
   lncc_bwd_x_kernel<<<gs_grid(rows * W), 256, 0, stream>>>(t2, which == 0 ? I : J, which == 0 ? J : I, grad_out,
                                                            -1.0 / (double)nw, grad, rows, W, Wv, win);
-  return da_check_launch("da_lncc_bwd");
+  return da_check_launch("da_lncc_bwd", 3);
 }

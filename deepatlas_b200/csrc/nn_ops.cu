@@ -283,7 +283,7 @@ DA_API int da_bn_stats(const float* x, int N, int C, int64_t V, float eps, float
   bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, (double*)workspace);
   bn_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean,
                                                         invstd, running_mean, running_var);
-  return da_check_launch("da_bn_stats");
+  return da_check_launch("da_bn_stats", 2);
 }
 
 // Eval-mode helper: mean = running_mean, invstd = rsqrt(running_var + eps) is formed by the caller.
@@ -308,7 +308,7 @@ DA_API int da_bn_act_bwd(const float* dy, const float* x, const float* mean, con
   dim3 g2(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
   bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)(1.0 / ((double)N * (double)V)),
                                             training, act, slope, dx);
-  return da_check_launch("da_bn_act_bwd");
+  return da_check_launch("da_bn_act_bwd", 3);
 }
 
 DA_API int da_act_bwd(const float* dy, const float* y, float slope, int64_t total, float* dx, cudaStream_t stream) {

@@ -29,6 +29,7 @@ typedef struct CUstream_st* da_stream_t; /* == cudaStream_t */
 int da_version(void);
 const char* da_last_error(void);
 int da_memset_zero(void* dst, int64_t bytes, da_stream_t stream);
+int64_t da_launch_count(void); /* kernels launched by this library so far in this process */
 
 /* ---- warp3d: identity grid + displacement + trilinear grid_sample in one pass ------------------------
  * replaces lib/utils.py:89-102 (get_identity_transform), lib/network_factory/voxel_morph.py:88 (disp + id)

@@ -313,3 +313,29 @@ def xavier_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int = 230) -> SD
         else:
             sd[k] = torch.zeros(shp)
     return sd
+
+
+# --------------------------------------------------------------------------------------------
+# the joint seg+reg step, assembled from the restated reference functions above
+# --------------------------------------------------------------------------------------------
+
+DEFAULT_LAMBDAS = dict(sim=1.0, reg=1000.0, ana=1.0, sup=1.0)
+
+
+def joint_loss(seg_sd: SD, reg_sd: SD, batch, n_classes: int, lambdas=None, dtype=torch.float32):
+    """P_m=seg(I_m); P_t=seg(I_t); disp,I_w,phi=reg(I_m,I_t); S_w=warp(softmax(P_m),phi);
+    L = l_sim*lncc(I_w,I_t) + l_reg*bending(disp) + l_ana*dice(S_w,onehot(S_t)) + l_sup*(dice(P_m,S_m)+dice(P_t,S_t)).
+    seg = UNet_light(1, C, bias=True, BN=True) in train mode, reg = VoxelMorphCVPR2018()."""
+    lam = dict(DEFAULT_LAMBDAS, **(lambdas or {}))
+    I_m, S_m, I_t, S_t = batch
+    I_m, I_t = I_m.to(dtype), I_t.to(dtype)
+    C = n_classes
+    P_m = unet_generator_forward(I_m, seg_sd, 1, True)
+    P_t = unet_generator_forward(I_t, seg_sd, 1, True)
+    disp, I_w, phi = voxelmorph_forward(I_m, I_t, reg_sd)
+    S_w = warp(torch.softmax(P_m, 1), phi)
+    onehot = mask_to_one_hot(S_t.reshape(1, 1, *S_t.shape[1:]), C, dtype=dtype)
+    return (lam["sim"] * lncc(I_w, I_t) + lam["reg"] * bending_energy(disp)
+            + lam["ana"] * dice_multiclass(S_w, onehot, C, "Uniform", False, False, 1e-6)
+            + lam["sup"] * (dice_multiclass(P_m, S_m.long(), C, "Uniform", False, True, 1e-6)
+                            + dice_multiclass(P_t, S_t.long(), C, "Uniform", False, True, 1e-6)))
