@@ -48,7 +48,8 @@ SIGNATURES = {
     "da_conv3d_fwd": ("pipipippiiiiiiiiifpls", "rc"),
     "da_conv3d_dgrad": ("ppipiiiiiiiiiiipls", "rc"),
     "da_conv3d_wgrad": ("pipipippiiiiiiiipls", "rc"),
-    "da_channel_sum": ("piilps", "rc"),
+    "da_channel_sum_workspace_bytes": ("i", "size"),
+    "da_channel_sum": ("piilppls", "rc"),
     # bn / act / pool / upsample
     "da_bn_workspace_bytes": ("i", "size"),
     "da_bn_stats": ("piilffpppppls", "rc"),

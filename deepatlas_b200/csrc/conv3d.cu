@@ -415,6 +415,193 @@ __global__ void __launch_bounds__(WG_THREADS) conv3d_wgrad_kernel(const float* _
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// tiled k3 s1 p1 weight gradient (the hot one: 1/3 of the step's FLOPs).
+//   dW[co][ci][kz][ky][kx] = sum_v dY[co][v] * X[ci][v + (kz,ky,kx) - 1]
+// Block = 9 warps, warp w owns (kz,ky) = (w/3, w%3) for one group of 4 input x 8 output channels
+// (96 register accumulators: 3 kx x 4 ci x 8 co).  The block walks a region of 4x8x32 output tiles;
+// per tile the X halo [4][6][10][36] and the dY tile [8][4][8][32] are staged in shared memory with
+// cp.async (double buffered, zero-filled outside the volume), each lane consumes 4 consecutive x
+// (LDS.128) -> 384 FFMA per 12 LDS.  Lanes are folded with the halving butterfly once per block.
+// The bias gradient (sum of dY) is accumulated by the centre warp of the ci-group-0 blocks.
+// ------------------------------------------------------------------------------------------------
+constexpr int WT_WARPS = 9, WT_THREADS = WT_WARPS * 32;
+constexpr int WT_SX = WG_CI * HZ * HY * HXP;   // 8640 floats
+constexpr int WT_SD = WG_CO * TZ * TY * TX;    // 8192 floats
+constexpr int WT_STAGE = WT_SX + WT_SD;
+constexpr size_t WT_SMEM = sizeof(float) * 2 * WT_STAGE;
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+struct WgTiledArgs {
+  const float* x;        // [N][C][Di][Hi][Wi]   (the operand that is read with the 3x3x3 halo)
+  const float* dy;       // [N][Cout][Di][Hi][Wi]
+  float* partials;       // [region][Cout_total? see strides]
+  float* bias_partials;  // [region][Cout] or null
+  int N, C, ci_off, Cin_total, Cout, co_off;
+  int64_t region_stride;
+  int D, H, W;
+  int tiles_x, tiles_y, tiles_z;
+  int tiles_per_region, ntiles;
+  int nCoB;
+};
+
+__global__ void __launch_bounds__(WT_THREADS, 1) conv3d_wgrad_tiled_kernel(WgTiledArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kz = warp / 3, ky = warp % 3;
+  const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
+  const int region = blockIdx.y;
+  const int64_t V = (int64_t)a.D * a.H * a.W;
+  const bool vec_ok = (a.W & 3) == 0;
+
+  float acc[96];
+#pragma unroll
+  for (int i = 0; i < 96; ++i) acc[i] = 0.f;
+  float bacc[WG_CO];
+#pragma unroll
+  for (int o = 0; o < WG_CO; ++o) bacc[o] = 0.f;
+  const bool do_bias = a.bias_partials != nullptr && cib == 0 && warp == 4;
+
+  const int t0 = region * a.tiles_per_region;
+  const int t1 = min(a.ntiles, t0 + a.tiles_per_region);
+
+  auto stage_tile = [&](int t, int s) {
+    float* sx = smem + s * WT_STAGE;
+    float* sd = sx + WT_SX;
+    int tb = t;
+    const int bx = tb % a.tiles_x; tb /= a.tiles_x;
+    const int by = tb % a.tiles_y; tb /= a.tiles_y;
+    const int bz = tb % a.tiles_z;
+    const int n = tb / a.tiles_z;
+    const int X0 = bx * TX, Y0 = by * TY, Z0 = bz * TZ;
+    // X halo: rows of 34 used floats (pitch 36)
+    for (int i = threadIdx.x; i < WG_CI * HZ * HY * (TX + 2); i += WT_THREADS) {
+      const int hx = i % (TX + 2);
+      int r = i / (TX + 2);
+      const int hy = r % HY; r /= HY;
+      const int hz = r % HZ;
+      const int cl = r / HZ;
+      const int gx = X0 - 1 + hx, gy = Y0 - 1 + hy, gz = Z0 - 1 + hz;
+      const int ci = cib * WG_CI + cl;
+      const bool ok = ci < a.C && gx >= 0 && gx < a.W && gy >= 0 && gy < a.H && gz >= 0 && gz < a.D;
+      const float* src = ok ? a.x + ((int64_t)n * a.C + ci) * V + ((int64_t)gz * a.H + gy) * a.W + gx : a.x;
+      cp_async4(sx + ((cl * HZ + hz) * HY + hy) * HXP + hx, src, ok);
+    }
+    // dY tile
+    if (vec_ok) {
+      for (int i = threadIdx.x; i < WG_CO * TZ * TY * (TX / 4); i += WT_THREADS) {
+        const int q = i % (TX / 4);
+        int r = i / (TX / 4);
+        const int ty = r % TY; r /= TY;
+        const int tz = r % TZ;
+        const int ol = r / TZ;
+        const int gx = X0 + q * 4, gy = Y0 + ty, gz = Z0 + tz;
+        const int co = cob * WG_CO + ol;
+        const bool ok = co < a.Cout && gx < a.W && gy < a.H && gz < a.D;
+        const float* src = ok ? a.dy + ((int64_t)n * a.Cout + co) * V + ((int64_t)gz * a.H + gy) * a.W + gx : a.dy;
+        cp_async16(sd + ((ol * TZ + tz) * TY + ty) * TX + q * 4, src, ok);
+      }
+    } else {
+      for (int i = threadIdx.x; i < WG_CO * TZ * TY * TX; i += WT_THREADS) {
+        const int tx = i % TX;
+        int r = i / TX;
+        const int ty = r % TY; r /= TY;
+        const int tz = r % TZ;
+        const int ol = r / TZ;
+        const int gx = X0 + tx, gy = Y0 + ty, gz = Z0 + tz;
+        const int co = cob * WG_CO + ol;
+        const bool ok = co < a.Cout && gx < a.W && gy < a.H && gz < a.D;
+        const float* src = ok ? a.dy + ((int64_t)n * a.Cout + co) * V + ((int64_t)gz * a.H + gy) * a.W + gx : a.dy;
+        cp_async4(sd + i, src, ok);
+      }
+    }
+  };
+
+  if (t0 < t1) {
+    stage_tile(t0, 0);
+    cp_async_commit();
+  }
+  for (int t = t0; t < t1; ++t) {
+    const int s = (t - t0) & 1;
+    if (t + 1 < t1) {
+      stage_tile(t + 1, s ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* sx = smem + s * WT_STAGE;
+    const float* sd = sx + WT_SX;
+#pragma unroll 1
+    for (int it = 0; it < (TZ * TY * TX / 4) / 32; ++it) {
+      const int q = it * 32 + lane;
+      const int tx4 = q & 7, ty = (q >> 3) & 7, tz = q >> 6;
+      float4 d[WG_CO];
+#pragma unroll
+      for (int o = 0; o < WG_CO; ++o)
+        d[o] = *reinterpret_cast<const float4*>(sd + ((o * TZ + tz) * TY + ty) * TX + tx4 * 4);
+      if (do_bias) {
+#pragma unroll
+        for (int o = 0; o < WG_CO; ++o) bacc[o] += (d[o].x + d[o].y) + (d[o].z + d[o].w);
+      }
+#pragma unroll
+      for (int c = 0; c < WG_CI; ++c) {
+        const float* row = sx + ((c * HZ + tz + kz) * HY + ty + ky) * HXP + tx4 * 4;
+        const float4 p = *reinterpret_cast<const float4*>(row);
+        const float2 r2 = *reinterpret_cast<const float2*>(row + 4);
+        const float in[6] = {p.x, p.y, p.z, p.w, r2.x, r2.y};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int o = 0; o < WG_CO; ++o) {
+            float v = acc[(kx * WG_CI + c) * WG_CO + o];
+            v = fmaf(in[kx + 0], d[o].x, v);
+            v = fmaf(in[kx + 1], d[o].y, v);
+            v = fmaf(in[kx + 2], d[o].z, v);
+            v = fmaf(in[kx + 3], d[o].w, v);
+            acc[(kx * WG_CI + c) * WG_CO + o] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  butterfly_reduce<96>(acc, lane);
+  float* pr = a.partials + (int64_t)region * a.region_stride;
+#pragma unroll
+  for (int gi = 0; gi < 3; ++gi) {
+    const int e = gi * 32 + lane;
+    const int o = e % WG_CO, c = (e / WG_CO) % WG_CI, kx = e / (WG_CO * WG_CI);
+    const int co = cob * WG_CO + o, ci = cib * WG_CI + c;
+    if (co < a.Cout && ci < a.C)
+      pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + (kz * 3 + ky) * 3 + kx] = acc[gi];
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int o = 0; o < WG_CO; ++o) {
+      const float b = warp_sum(bacc[o]);
+      const int co = cob * WG_CO + o;
+      if (lane == 0 && co < a.Cout) a.bias_partials[(int64_t)region * a.Cout + co] = b;
+    }
+  }
+}
+
 // out[i] = sum_r partials[r][i]  (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
                                        float* __restrict__ out) {
@@ -426,23 +613,51 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 }
 
 // per-channel sum over N and space (bias gradient):  out[c] = sum_{n,v} x[n][c][v]
-__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, int N, int C, int64_t V,
-                                                          float* __restrict__ out) {
+// two deterministic stages: CS_SPLITS blocks per channel write fp64 partials, then one warp per channel folds them.
+constexpr int CS_SPLITS = 64;
+__global__ void __launch_bounds__(256) channel_sum_partial_kernel(const float* __restrict__ x, int N, int C, int64_t V,
+                                                                  double* __restrict__ part) {
   __shared__ double red[8];
-  const int c = blockIdx.x;
+  const int c = blockIdx.x, sp = blockIdx.y;
+  const int64_t chunk = ((V + CS_SPLITS - 1) / CS_SPLITS + 3) & ~(int64_t)3;
+  const int64_t b = (int64_t)sp * chunk, e = min(V, b + chunk);
   double acc = 0;
   for (int n = 0; n < N; ++n) {
     const float* p = x + ((int64_t)n * C + c) * V;
     float a = 0.f;
     int k = 0;
-    for (int64_t i = threadIdx.x; i < V; i += 256) {
-      a += p[i];
-      if (++k == 64) { acc += (double)a; a = 0.f; k = 0; }
+    if ((((uintptr_t)p) & 15) == 0) {
+      const int64_t e4 = b + ((e > b ? e - b : 0) & ~(int64_t)3);
+      for (int64_t i = b + 4 * (int64_t)threadIdx.x; i < e4; i += 4 * 256) {
+        const float4 v = *reinterpret_cast<const float4*>(p + i);
+        a += (v.x + v.y) + (v.z + v.w);
+        if (++k == 32) { acc += (double)a; a = 0.f; k = 0; }
+      }
+      for (int64_t i = e4 + threadIdx.x; i < e; i += 256) a += p[i];
+    } else {
+      for (int64_t i = b + threadIdx.x; i < e; i += 256) {
+        a += p[i];
+        if (++k == 64) { acc += (double)a; a = 0.f; k = 0; }
+      }
     }
     acc += (double)a;
   }
-  const double b = block_sum<double, 8>(acc, red);
-  if (threadIdx.x == 0) out[c] = (float)b;
+  const double t = block_sum<double, 8>(acc, red);
+  if (threadIdx.x == 0) part[(int64_t)c * CS_SPLITS + sp] = t;
+}
+__global__ void channel_sum_final_kernel(const double* __restrict__ part, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double a = part[(int64_t)c * CS_SPLITS + lane] + part[(int64_t)c * CS_SPLITS + 32 + lane];
+  a = warp_sum(a);
+  if (lane == 0) out[c] = (float)a;
+}
+inline int64_t channel_sum_scratch_bytes(int C) { return (int64_t)sizeof(double) * C * CS_SPLITS + 256; }
+inline int run_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* scratch, cudaStream_t stream) {
+  double* part = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
+  channel_sum_partial_kernel<<<dim3(C, CS_SPLITS), 256, 0, stream>>>(x, N, C, V, part);
+  channel_sum_final_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, C, out);
+  return da_check_launch("channel_sum", 2);
 }
 
 inline int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
@@ -548,7 +763,8 @@ DA_API int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks) {
 }
 DA_API int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
   const int64_t count = (int64_t)Cin * Cout * ks * ks * ks;
-  return (int64_t)sizeof(float) * wg_region_cap(count) * count + 256;
+  const int m = Cin > Cout ? Cin : Cout;
+  return (int64_t)sizeof(float) * ((int64_t)wg_region_cap(count) * count + (int64_t)WG_MAX_REGIONS * m) + 512;
 }
 
 // Forward.  x1 [N,C1,Di,Hi,Wi], x2 [N,C2,...] or null (C2=0): the conv sees cat(x1,x2) along channels.
@@ -619,8 +835,60 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
   const int Do = conv_out(Di, ks, stride, pad), Ho = conv_out(Hi, ks, stride, pad), Wo = conv_out(Wi, ks, stride, pad);
   float* partials = (float*)workspace;
   const int64_t count = (int64_t)Cin * Cout * T;
-  const int64_t total_rows = (int64_t)N * Do * Ho * ((Wo + 31) / 32);
   const int cap = wg_region_cap(count);
+  if (ks == 3 && stride == 1 && pad == 1 && !force_direct()) {
+    // tiled kernel: regions of 4x8x32 tiles; bias gradient folded in (non-transposed layers)
+    const int tiles_x = (Wi + TX - 1) / TX, tiles_y = (Hi + TY - 1) / TY, tiles_z = (Di + TZ - 1) / TZ;
+    const int ntiles = N * tiles_x * tiles_y * tiles_z;
+    const int a_ch = transposed ? Cout : Cin, b_ch = transposed ? Cin : Cout;   // halo-side / plain-side channels
+    const int groups = ((a_ch + WG_CI - 1) / WG_CI) * ((b_ch + WG_CO - 1) / WG_CO);
+    int nregions = (4 * DA_NUM_SMS + groups / 2) / groups;
+    if (nregions > cap) nregions = cap;
+    if (nregions > ntiles) nregions = ntiles;
+    if (nregions < 1) nregions = 1;
+    const int tpr = (ntiles + nregions - 1) / nregions;
+    nregions = (ntiles + tpr - 1) / tpr;
+    float* bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(conv3d_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM);
+      configured = true;
+    }
+    auto launch_t = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off,
+                        float* bp) -> int {
+      WgTiledArgs a;
+      a.x = xin; a.dy = gout; a.partials = partials; a.bias_partials = bp;
+      a.N = N; a.C = C; a.ci_off = ci_off; a.Cin_total = Cin_total_; a.Cout = Cout_; a.co_off = co_off;
+      a.region_stride = count; a.D = Di; a.H = Hi; a.W = Wi;
+      a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_z = tiles_z; a.tiles_per_region = tpr; a.ntiles = ntiles;
+      a.nCoB = (Cout_ + WG_CO - 1) / WG_CO;
+      dim3 grid(((C + WG_CI - 1) / WG_CI) * a.nCoB, nregions);
+      conv3d_wgrad_tiled_kernel<<<grid, WT_THREADS, WT_SMEM, stream>>>(a);
+      return da_check_launch("conv3d_wgrad_tiled");
+    };
+    int rc;
+    if (!transposed) {
+      rc = launch_t(x1, C1, 0, Cin, dy, Cout, 0, bias_partials);
+      if (!rc && C2) rc = launch_t(x2, C2, C1, Cin, dy, Cout, 0, nullptr);
+    } else {
+      rc = launch_t(dy, Cout, 0, Cout, x1, C1, 0, nullptr);
+      if (!rc && C2) rc = launch_t(dy, Cout, 0, Cout, x2, C2, C1, nullptr);
+    }
+    if (rc) return rc;
+    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+    rc = da_check_launch("conv3d_wgrad/reduce");
+    if (rc) return rc;
+    if (grad_bias) {
+      if (bias_partials) {
+        reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, nregions, Cout, grad_bias);
+        rc = da_check_launch("conv3d_wgrad/bias-reduce");
+      } else {
+        rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);
+      }
+    }
+    return rc;
+  }
+  const int64_t total_rows = (int64_t)N * Do * Ho * ((Wo + 31) / 32);
   int nregions = (int)(total_rows < cap ? total_rows : cap);
   if (nregions < 1) nregions = 1;
   const int64_t rpr = da_cdiv(total_rows, nregions);
@@ -649,16 +917,15 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
   reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
   rc = da_check_launch("conv3d_wgrad/reduce");
   if (rc) return rc;
-  if (grad_bias) {
-    channel_sum_kernel<<<Cout, 256, 0, stream>>>(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias);
-    rc = da_check_launch("conv3d_wgrad/bias");
-  }
+  if (grad_bias) rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);
   return rc;
 }
 
-// out[c] = sum over batch and space of x[n][c][:]
-DA_API int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, cudaStream_t stream) {
-  DA_REQUIRE(x && out, "da_channel_sum: null pointer");
-  channel_sum_kernel<<<C, 256, 0, stream>>>(x, N, C, V, out);
-  return da_check_launch("da_channel_sum");
+// out[c] = sum over batch and space of x[n][c][:]; workspace of da_channel_sum_workspace_bytes(C)
+DA_API int64_t da_channel_sum_workspace_bytes(int C) { return channel_sum_scratch_bytes(C); }
+DA_API int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* workspace, int64_t workspace_bytes,
+                          cudaStream_t stream) {
+  DA_REQUIRE(x && out && workspace, "da_channel_sum: null pointer");
+  if (workspace_bytes < channel_sum_scratch_bytes(C)) { da_set_error("da_channel_sum: workspace too small"); return DA_ERR_WORKSPACE; }
+  return run_channel_sum(x, N, C, V, out, workspace, stream);
 }

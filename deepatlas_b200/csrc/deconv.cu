@@ -236,11 +236,13 @@ inline int dc_region_cap(int64_t count) {
 
 }  // namespace
 
-extern "C" int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, cudaStream_t stream);
+extern "C" int64_t da_channel_sum_workspace_bytes(int C);
+extern "C" int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* workspace, int64_t workspace_bytes,
+                              cudaStream_t stream);
 
 DA_API int64_t da_deconv_k2s2_wgrad_workspace_bytes(int Cin, int Cout) {
   const int64_t count = (int64_t)Cin * Cout * 8;
-  return (int64_t)sizeof(float) * dc_region_cap(count) * count + 256;
+  return (int64_t)sizeof(float) * dc_region_cap(count) * count + 256 + da_channel_sum_workspace_bytes(Cout);
 }
 
 // x [N,Cin,D,H,W]; weight (Cin,Cout,2,2,2); out [N,Cout,2D,2H,2W]
@@ -280,5 +282,6 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
   dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
   rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
   if (rc || !grad_bias) return rc;
-  return da_channel_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, stream);
+  // the weight partials have been consumed by the reduce above (same stream): reuse the workspace head
+  return da_channel_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, workspace, workspace_bytes, stream);
 }

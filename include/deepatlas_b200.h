@@ -101,7 +101,9 @@ int da_conv3d_dgrad(const float* dy, const float* weight, int transposed, float*
 int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
                     float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                     int stride, int pad, void* workspace, int64_t workspace_bytes, da_stream_t stream);
-int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, da_stream_t stream);
+int64_t da_channel_sum_workspace_bytes(int C);
+int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* workspace, int64_t workspace_bytes,
+                   da_stream_t stream);
 
 /* ---- batch norm (train mode) + activation; max-pool; nearest upsampling ---------------------------------
  * nn.BatchNorm3d (unets.py:31,51,116,130), nn.LeakyReLU / nn.ReLU (unets.py:32, modules.py:58),

@@ -196,16 +196,30 @@ def test_conv3d(cuda, case, impl, slope):
     b = torch.randn(Cout, generator=g) * 0.1
     pad = 1 if ks == 3 else 0
 
+    mask_box = {}
+
     def cpu(*a):
         a = list(a)
         xx = torch.cat((a[0], a[1]), 1) if C2 else a[0]
         ww, bb = a[-2], a[-1]
         y = F.conv_transpose3d(xx, ww, bb, stride=1, padding=1) if transposed else F.conv3d(xx, ww, bb, stride=stride, padding=pad)
-        return y if slope is None else F.leaky_relu(y, slope)
+        if slope is None:
+            return y
+        # The activation is discontinuous in its derivative at 0: a pre-activation within fp32 round-off of zero may
+        # land on either side depending on summation order.  Those voxels (checked below to be round-off cases)
+        # take the GPU's side so that the gradient comparison is not dominated by a legitimate mask flip.
+        pos = y.detach() > 0
+        flipped = pos != mask_box["gpu_pos"]
+        mask_box["flipped"] = int(flipped.sum())
+        if mask_box["flipped"]:
+            assert float(y.detach()[flipped].abs().max()) < 1e-5 * float(y.detach().abs().max()), "mask differs away from zero"
+        return torch.where(mask_box["gpu_pos"], y, y * slope)
 
     def gpu(*a):
         a = list(a)
-        return ops.conv3d(a[0], a[-2], a[-1], x2=a[1] if C2 else None, transposed=transposed, stride=stride, pad=pad, slope=slope)
+        out = ops.conv3d(a[0], a[-2], a[-1], x2=a[1] if C2 else None, transposed=transposed, stride=stride, pad=pad, slope=slope)
+        mask_box["gpu_pos"] = out.detach().cpu() > 0
+        return out
 
     ins = [x1] + ([x2] if C2 else []) + [w, b]
     _lib.call("da_set_conv_impl", 1 if impl == "direct" else 0)
@@ -213,12 +227,9 @@ def test_conv3d(cuda, case, impl, slope):
         res = _run_both(gpu, cpu, ins, cuda)
     finally:
         _lib.call("da_set_conv_impl", 0)
-    if slope is None:
-        _check(*res, what=f"conv3d {case} {impl}")
-    else:
-        # a ReLU mask may flip on pre-activations within fp32 round-off of zero: judge all but the worst 1e-4 of elements
-        for a, b in zip(list(res[0]) + [g_ for g_ in res[1] if g_ is not None], list(res[2]) + [g_ for g_ in res[3] if g_ is not None]):
-            assert rel_err_quantile(a, b) < TOL, f"conv3d+act {case}"
+    _check(*res, what=f"conv3d {case} {impl} slope={slope}")
+    if slope is not None:
+        assert mask_box["flipped"] <= 4, f"{mask_box['flipped']} activation-mask flips"
 
 
 @pytest.mark.parametrize("slope", [0.01, 0.0, None])

@@ -1,0 +1,134 @@
+"""Pins the CPU port (oracle/ref_port.py) and the host-side mirror classes to the REAL reference modules,
+imported from /root/reference where they lie (build container only; skipped on the GPU box, where the golden
+fixtures made by oracle/make_golden.py take over).  fp32 on CPU; the port must be BIT-identical because it
+restates the reference on top of the same ATen calls."""
+import pytest
+import torch
+
+from oracle import ref_import
+from oracle import ref_port as P
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    torch.set_num_threads(4)
+    return ref_import.load()
+
+
+def _g(seed=230):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("name,args", [("UNet_light", (1, 4)), ("UNet_light", (1, 32)), ("UNet", (1, 4)), ("voxel_morph_cvpr", ())])
+def test_mirror_state_dict_matches_reference(ref, name, args):
+    """Same keys, shapes and -- under the same seed -- the same xavier RNG stream as the reference classes
+    (checkpoints are the on-disk contract: models/base.py:98-108 loads with strict=True)."""
+    import deepatlas_b200 as da
+    kw = dict(bias=True, BN=True) if args else {}
+    torch.manual_seed(230)
+    r = ref.get_network(name)(*args, **kw)
+    r.weights_init()
+    torch.manual_seed(230)
+    m = da.get_network(name)(*args, **kw)
+    m.weights_init()
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert rs[k].shape == ms[k].shape, k
+        assert torch.equal(rs[k], ms[k]), k
+    m.load_state_dict(rs, strict=True)
+    r.load_state_dict(ms, strict=True)
+
+
+@pytest.mark.parametrize("classes,bn", [(4, True), (3, False)])
+def test_port_unet_light(ref, classes, bn):
+    torch.manual_seed(230)
+    net = ref.get_network("UNet_light")(1, classes, bias=True, BN=bn)
+    net.weights_init()
+    net.train()
+    x = torch.rand((1, 1, 16, 24, 16), generator=_g())
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    stats = {}
+    y = P.unet_generator_forward(x, sd, 1, bn, stats_out=stats)
+    y_ref = net(x)
+    assert torch.equal(y, y_ref)
+    after = net.state_dict()
+    for k, v in stats.items():   # running statistics move exactly as nn.BatchNorm3d moves them
+        assert torch.equal(v, after[k]), k
+
+
+def test_port_unet32(ref):
+    torch.manual_seed(230)
+    net = ref.get_network("UNet")(1, 4, bias=True, BN=True)
+    net.weights_init()
+    net.train()
+    x = torch.rand((1, 1, 16, 16, 16), generator=_g())
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    assert torch.equal(P.unet_forward(x, sd, True), net(x))
+
+
+def test_port_voxelmorph_and_identity(ref):
+    torch.manual_seed(230)
+    net = ref.get_network("voxel_morph_cvpr")()
+    net.weights_init()
+    g = _g()
+    s, t = torch.rand((1, 1, 16, 24, 20), generator=g), torch.rand((1, 1, 16, 24, 20), generator=g)
+    out = P.voxelmorph_forward(s, t, dict(net.state_dict()))
+    out_ref = net(s, t)
+    for a, b in zip(out, out_ref):
+        assert torch.equal(a, b)
+    assert torch.equal(P.identity_transform((5, 6, 7)), ref.utils.get_identity_transform((5, 6, 7)))
+    # closed-form trilinear formula agrees with the ATen call the reference makes (fp64: 1e-12)
+    phi = out_ref[2].double()
+    cf = P.warp_closed_form(s.double(), phi)
+    assert float((cf - P.warp(s.double(), phi)).abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize("wt", ["Uniform", "Simple", "Volume"])
+@pytest.mark.parametrize("softmax", [True, False])
+@pytest.mark.parametrize("no_bg", [True, False])
+def test_port_dice(ref, wt, softmax, no_bg):
+    g = _g()
+    C = 5
+    logits = torch.randn((2, C, 6, 7, 8), generator=g)
+    labels = torch.randint(0, C, (2, 6, 7, 8), generator=g)
+    soft = torch.softmax(torch.randn((2, C, 6, 7, 8), generator=g), 1)
+    x = logits if softmax else torch.softmax(logits, 1)
+    crit = ref.get_loss_function("dice")(n_class=C, weight_type=wt, no_bg=no_bg, softmax=softmax, eps=1e-6)
+    for tgt in (labels, soft):
+        assert torch.equal(P.dice_multiclass(x, tgt, C, wt, no_bg, softmax, 1e-6), crit(x, tgt))
+    assert torch.equal(P.mask_to_one_hot(labels.reshape(2, 1, -1), C), ref.transforms.mask_to_one_hot(labels.reshape(2, 1, -1), C))
+    with pytest.raises(ValueError):
+        crit(x, labels[:, None, None])
+
+
+def test_port_lncc_bending(ref):
+    g = _g()
+    I, J = torch.rand((2, 1, 12, 13, 14), generator=g), torch.rand((2, 1, 12, 13, 14), generator=g)
+    assert torch.equal(P.lncc(I, J), ref.get_loss_function("lncc")()(I, J))
+    u = torch.randn((2, 3, 8, 9, 10), generator=g) * 0.1
+    for sp in ((1, 1, 1), (1.0, 1.5, 2.0)):
+        assert torch.equal(P.bending_energy(u, sp), ref.get_loss_function("bendingEnergy")(spacing=sp)(u))
+    # analytic identities of SURVEY.md section 4
+    assert float(P.lncc(I, I)) < 1e-5
+    idt = P.identity_transform((8, 9, 10))[None]
+    assert float(P.bending_energy(idt * 0.3 + 0.1)) < 1e-10
+
+
+def test_registry_seams(ref):
+    """install() overwrites the reference's own registries and nothing else; bad names keep raising KeyError."""
+    import deepatlas_b200 as da
+    keep_n, keep_l = dict(ref.network_dic), dict(ref.loss_dict)
+    try:
+        replaced = da.install(ref.network_factory, ref.loss)
+        assert {"network:UNet_light", "network:UNet", "network:voxel_morph_cvpr", "loss:dice", "loss:lncc", "loss:bendingEnergy"} <= set(replaced)
+        assert ref.get_network("UNet_light") is da.UNet_light
+        assert ref.get_loss_function("dice") is da.DiceLossMultiClass
+        assert set(ref.loss_dict) == set(keep_l)      # the un-replaced reference losses stay registered
+        with pytest.raises(KeyError):
+            ref.get_network("nope")
+    finally:
+        ref.network_dic.clear(); ref.network_dic.update(keep_n)
+        ref.loss_dict.clear(); ref.loss_dict.update(keep_l)
