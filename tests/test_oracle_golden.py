@@ -1,7 +1,7 @@
 """The CPU port (oracle/ref_port.py) against the committed golden fixtures (tests/golden/, produced from the
 real reference modules by oracle/make_golden.py).  Runs anywhere -- in particular on the GPU box, where
-/root/reference does not exist.  Bit-exact where the same ATen kernels run (same torch build as meta.json);
-1e-6 relative otherwise."""
+/root/reference does not exist.  1e-6 relative for single ops; whole networks get NET_TOL because ATen's CPU reductions
+(batch-norm statistics, conv accumulation) change summation order with the host's thread count."""
 import json
 import os
 
@@ -11,6 +11,7 @@ import torch
 
 from oracle import ref_port as P
 
+NET_TOL, NET_GRAD_TOL = 2e-5, 1e-4
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -33,9 +34,11 @@ def _t(a):
     return torch.from_numpy(np.asarray(a))
 
 
-def _close(a, b, tol=1e-6):
+def _close(a, b, tol=1e-6, floor=1e-30):
+    """max-norm relative; `floor` puts analytically-zero quantities (a conv bias in front of a BatchNorm has a
+    round-off-only gradient) on an absolute scale."""
     a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
-    return float((a - b).abs().max()) <= tol * max(float(b.abs().max()), 1e-30)
+    return float((a - b).abs().max()) <= tol * max(float(b.abs().max()), floor)
 
 
 def test_warp_identity_onehot(ops_gold):
@@ -99,14 +102,14 @@ def test_unet_light(nets_gold, meta):
     sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
     stats = {}
     logits = P.unet_generator_forward(_t(g["ul_x"]), sd, 1, True, stats_out=stats)
-    assert _close(logits, g["ul_logits"])
+    assert _close(logits, g["ul_logits"], NET_TOL)
     assert np.array_equal(torch.max(logits, 1)[1].numpy().astype(np.uint8), g["ul_argmax"])   # label indices bit-exact
     loss = P.dice_multiclass(logits, _t(g["ul_labels"]).long(), 4, "Uniform", False, True, 1e-6)
     loss.backward()
-    assert _close(loss, g["ul_loss"])
-    assert _close(stats["encoders.0.0.BN.running_mean"], g["ul_running_mean0"]) and _close(stats["encoders.0.0.BN.running_var"], g["ul_running_var0"])
+    assert _close(loss, g["ul_loss"], NET_TOL)
+    assert _close(stats["encoders.0.0.BN.running_mean"], g["ul_running_mean0"], NET_TOL) and _close(stats["encoders.0.0.BN.running_var"], g["ul_running_var0"], NET_TOL)
     for k in [k for k in g if k.startswith("ul_grad/")]:
-        assert _close(sd[k[len("ul_grad/"):]].grad, g[k], 2e-5), k
+        assert _close(sd[k[len("ul_grad/"):]].grad, g[k], NET_GRAD_TOL, 1e-3), k
 
 
 def test_voxelmorph_unet32_joint(nets_gold, meta):
@@ -114,14 +117,14 @@ def test_voxelmorph_unet32_joint(nets_gold, meta):
     _, sd = _mirror("voxel_morph_cvpr", (), {}, meta["voxelmorph_checksums"])
     sd = {k: v.requires_grad_(True) for k, v in sd.items()}
     disp, warped, deform = P.voxelmorph_forward(_t(g["vm_s"]), _t(g["vm_t"]), sd)
-    assert _close(disp, g["vm_disp"]) and _close(warped, g["vm_warped"]) and _close(deform, g["vm_deform"])
+    assert _close(disp, g["vm_disp"], NET_TOL) and _close(warped, g["vm_warped"], NET_TOL) and _close(deform, g["vm_deform"], NET_TOL)
     loss = P.lncc(warped, _t(g["vm_t"])) + 1000.0 * P.bending_energy(disp)
     loss.backward()
-    assert _close(loss, g["vm_loss"])
+    assert _close(loss, g["vm_loss"], NET_TOL)
     for k in [k for k in g if k.startswith("vm_grad/")]:
-        assert _close(sd[k[len("vm_grad/"):]].grad, g[k], 2e-5), k
+        assert _close(sd[k[len("vm_grad/"):]].grad, g[k], NET_GRAD_TOL, 1e-3), k
     _, sdu = _mirror("UNet", (1, 4), dict(bias=True, BN=True), meta["unet_checksums"])
-    assert _close(P.unet_forward(_t(g["un_x"]), sdu, True), g["un_logits"])
+    assert _close(P.unet_forward(_t(g["un_x"]), sdu, True), g["un_logits"], NET_TOL)
     # joint step
     from deepatlas_b200.joint import make_synthetic_pair
     torch.manual_seed(230)
@@ -133,6 +136,6 @@ def test_voxelmorph_unet32_joint(nets_gold, meta):
     batch = make_synthetic_pair((16, 16, 16), 4, seed=230)
     loss = P.joint_loss(seg_sd, reg_sd, batch, 4)
     loss.backward()
-    assert _close(loss, g["joint_loss"])
-    assert _close(seg_sd["encoders.0.0.conv.weight"].grad, g["joint_grad/seg.encoders.0.0.conv.weight"], 2e-5)
-    assert _close(reg_sd["flow.weight"].grad, g["joint_grad/reg.flow.weight"], 2e-5)
+    assert _close(loss, g["joint_loss"], NET_TOL)
+    assert _close(seg_sd["encoders.0.0.conv.weight"].grad, g["joint_grad/seg.encoders.0.0.conv.weight"], NET_GRAD_TOL)
+    assert _close(reg_sd["flow.weight"].grad, g["joint_grad/reg.flow.weight"], NET_GRAD_TOL)
