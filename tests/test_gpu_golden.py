@@ -106,9 +106,14 @@ def test_voxelmorph_unet32_joint(cuda, ng):
     un.weights_init()
     un = un.to(cuda).train()
     assert _rel(un(_c(ng["un_x"], cuda)), ng["un_logits"]) < TOL
-    torch.manual_seed(230)
+    torch.manual_seed(230)    # same construction / init order as make_golden.py: seg, seg.weights_init, reg, reg.weights_init
+    seg = da.get_network("UNet_light")(1, 4, bias=True, BN=True)
+    seg.weights_init()
+    reg = da.get_network("voxel_morph_cvpr")()
+    reg.weights_init()
     model = JointModel(n_classes=4)
-    model.weights_init()      # seg then reg: the order make_golden.py used
+    model.seg.load_state_dict(seg.state_dict())
+    model.reg.load_state_dict(reg.state_dict())
     model = model.to(cuda)
     batch = make_synthetic_pair((16, 16, 16), 4, seed=230, device=cuda)
     loss, parts = model.joint_loss(*batch)
