@@ -19,6 +19,7 @@
 //   conv3d_wgrad_kernel<KS,CI,CO>   lane = voxel along W, register accumulators, butterfly reduce
 //   reduce_partials_kernel          fixed-order second stage (deterministic)
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -602,6 +603,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv3d_wgrad_tiled_kernel(WgTil
   }
 }
 
+#include "conv3d_tma.inc.cuh"
+
 // out[i] = sum_r partials[r][i]  (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
                                        float* __restrict__ out) {
@@ -698,6 +701,65 @@ int launch_direct(const float* x1, const float* x2, const float* wp, const float
   return da_check_launch("conv3d_direct");
 }
 
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+int g_force_no_tma = -1;
+inline bool tma_disabled() {
+  if (g_force_no_tma < 0) {
+    const char* e = getenv("DA_CONV_TMA");
+    g_force_no_tma = (e && strcmp(e, "0") == 0) ? 1 : 0;
+  }
+  return g_force_no_tma == 1 || da_get_encode_tiled() == nullptr;
+}
+
+// k3 s1 p1 forward/dgrad through the TMA-staged kernel?  (geometry already in g; KS == 3)
+inline bool fwd_tma_ok(const float* x1, const float* x2, const float* out, const ConvGeom& g) {
+  const int Cin = g.C1 + g.C2;
+  return !force_direct() && !tma_disabled() && g.stride == 1 && g.pad == 1 && Cin >= 3 && (g.Wi & 3) == 0 && g.Wo >= 16 &&
+         (int64_t)g.Do * g.Ho * g.Wo >= 32768 && aligned16(x1) && aligned16(x2) && aligned16(out) &&
+         (g.C2 == 0 || g.C1 % TMA_CK == 0);
+}
+
+template <int CO>
+int launch_fwd_tma(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g,
+                   int cin_pad, cudaStream_t stream) {
+  using Cfg = FwdTmaCfg<CO>;
+  CUtensorMap m1, m2;
+  int rc = da_make_volume_map(&m1, x1, g.N, g.C1, g.Di, g.Hi, g.Wi, HXT, HY, HZ, TMA_CK);
+  if (rc) return rc;
+  if (g.C2) {
+    rc = da_make_volume_map(&m2, x2, g.N, g.C2, g.Di, g.Hi, g.Wi, HXT, HY, HZ, TMA_CK);
+    if (rc) return rc;
+  } else {
+    m2 = m1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3d_fwd_tma_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    configured = true;
+  }
+  const int tiles_x = (g.Wo + TX - 1) / TX, tiles_y = (g.Ho + TY - 1) / TY, tiles_z = (g.Do + TZ - 1) / TZ;
+  dim3 grid(tiles_x * tiles_y * tiles_z, g.Cop / CO, g.N);
+  conv3d_fwd_tma_kernel<CO><<<grid, TILED_THREADS, Cfg::SMEM_BYTES, stream>>>(m1, m2, wp, bias, out, g, tiles_x, tiles_y, cin_pad);
+  return da_check_launch("conv3d_fwd_tma");
+}
+
+// repack (layout [cog][cin_pad][27][CO]) + launch; weight indexing arguments as for repack()
+int run_conv_tma(const float* x1, const float* x2, const float* weight, float* wp, const float* bias, float* out, const ConvGeom& g,
+                 int d0, int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
+  const int Cin = g.C1 + g.C2;
+  const int cin_pad = (Cin + TMA_CK - 1) / TMA_CK * TMA_CK;
+  const int CO = (g.Cop % 16 == 0) ? 16 : (g.Cop % 8 == 0 ? 8 : 4);
+  const int64_t total = (int64_t)cin_pad * 27 * g.Cop;
+  int blocks = (int)da_cdiv(total, 256);
+  if (blocks > 4096) blocks = 4096;
+  repack_weights_tma_kernel<<<blocks, 256, 0, stream>>>(weight, wp, d0, d1, 27, a_is_dim0, flip, Cin, 0, cin_pad, g.Cout, b_off, g.Cop, CO);
+  int rc = da_check_launch("repack_weights_tma");
+  if (rc) return rc;
+  if (CO == 16) return launch_fwd_tma<16>(x1, x2, wp, bias, out, g, cin_pad, stream);
+  if (CO == 8) return launch_fwd_tma<8>(x1, x2, wp, bias, out, g, cin_pad, stream);
+  return launch_fwd_tma<4>(x1, x2, wp, bias, out, g, cin_pad, stream);
+}
+
 int run_conv(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g, int KS,
              cudaStream_t stream) {
   if (KS == 1) return launch_direct<1>(x1, x2, wp, bias, out, g, stream);
@@ -747,6 +809,21 @@ inline int wg_region_cap(int64_t count) {
 // C ABI
 // ---------------------------------------------------------------------------------------------------------------
 
+da_encode_tiled_fn da_get_encode_tiled() {
+  static da_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (da_encode_tiled_fn)p;
+    else
+      (void)cudaGetLastError();
+    tried = true;
+  }
+  return fn;
+}
+
 // Kernel selection for k3 s1 p1 convolutions: 0 = automatic (tiled where it applies), 1 = always the generic
 // direct kernel (used by the parity tests to cross-check the two implementations).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
@@ -759,7 +836,7 @@ DA_API int da_set_conv_impl(int impl) {
 // workspace for da_conv3d_fwd / da_conv3d_dgrad: one packed weight copy
 DA_API int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks) {
   const int m = Cin > Cout ? Cin : Cout;
-  return (int64_t)sizeof(float) * (int64_t)m * ks * ks * ks * cpad(m) + 256;
+  return (int64_t)sizeof(float) * (int64_t)(m + 3) * ks * ks * ks * cpad(m) + 256;
 }
 DA_API int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
   const int64_t count = (int64_t)Cin * Cout * ks * ks * ks;
@@ -784,6 +861,9 @@ DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const
   ConvGeom g{N, C1, C2, Di, Hi, Wi, conv_out(Di, ks, stride, pad), conv_out(Hi, ks, stride, pad), conv_out(Wi, ks, stride, pad),
              Cout, cpad(Cout), stride, pad, act, slope};
   float* wp = (float*)workspace;
+  if (ks == 3 && aligned16(wp) && fwd_tma_ok(x1, x2, out, g))
+    return transposed ? run_conv_tma(x1, x2, weight, wp, bias, out, g, Cin, Cout, 1, 1, 0, stream)
+                      : run_conv_tma(x1, x2, weight, wp, bias, out, g, Cout, Cin, 0, 0, 0, stream);
   int rc = transposed ? repack(weight, wp, Cin, Cout, T, 1, 1, Cin, 0, Cout, 0, g.Cop, stream)
                       : repack(weight, wp, Cout, Cin, T, 0, 0, Cin, 0, Cout, 0, g.Cop, stream);
   if (rc) return rc;
@@ -805,11 +885,14 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
   const int Cp = cpad(Cdx);
   if (stride == 1) {
     // dgrad = conv of dy (Cout channels) with [co][flip tap][ci]; for a transposed layer: no flip, dims swapped
+    ConvGeom g{N, Cout, 0, Do, Ho, Wo, Di, Hi, Wi, Cdx, Cp, 1, ks == 3 ? 1 : 0, 0, 0.f};
+    DA_REQUIRE(ks == 1 || pad == 1, "da_conv3d_dgrad: k3 needs pad 1");
+    if (ks == 3 && aligned16(wp) && fwd_tma_ok(dy, nullptr, dx, g))
+      return transposed ? run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, Cout, 0, 0, ci_off, stream)
+                        : run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, Cin_total, 1, 1, ci_off, stream);
     int rc = transposed ? repack(weight, wp, Cin_total, Cout, T, 0, 0, Cout, 0, Cdx, ci_off, Cp, stream)
                         : repack(weight, wp, Cout, Cin_total, T, 1, 1, Cout, 0, Cdx, ci_off, Cp, stream);
     if (rc) return rc;
-    ConvGeom g{N, Cout, 0, Do, Ho, Wo, Di, Hi, Wi, Cdx, Cp, 1, ks == 3 ? 1 : 0, 0, 0.f};
-    DA_REQUIRE(ks == 1 || pad == 1, "da_conv3d_dgrad: k3 needs pad 1");
     return run_conv(dy, nullptr, wp, nullptr, dx, g, ks, stream);
   }
   int rc = repack(weight, wp, Cout, Cin_total, T, 1, 0, Cout, 0, Cdx, ci_off, Cp, stream);
@@ -852,8 +935,10 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
     static bool configured = false;
     if (!configured) {
       cudaFuncSetAttribute(conv3d_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM);
+      cudaFuncSetAttribute(conv3d_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTM_SMEM_BYTES);
       configured = true;
     }
+    const bool use_tma = !tma_disabled() && (Wi & 3) == 0;
     auto launch_t = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off,
                         float* bp) -> int {
       WgTiledArgs a;
@@ -863,6 +948,14 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
       a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_z = tiles_z; a.tiles_per_region = tpr; a.ntiles = ntiles;
       a.nCoB = (Cout_ + WG_CO - 1) / WG_CO;
       dim3 grid(((C + WG_CI - 1) / WG_CI) * a.nCoB, nregions);
+      if (use_tma && aligned16(xin) && aligned16(gout)) {
+        CUtensorMap mx, mdy;
+        int r = da_make_volume_map(&mx, xin, N, C, Di, Hi, Wi, HXT, HY, HZ, WG_CI);
+        if (!r) r = da_make_volume_map(&mdy, gout, N, Cout_, Di, Hi, Wi, TX, TY, TZ, WG_CO);
+        if (r) return r;
+        conv3d_wgrad_tma_kernel<<<grid, WT_THREADS, WTM_SMEM_BYTES, stream>>>(mx, mdy, a);
+        return da_check_launch("conv3d_wgrad_tma");
+      }
       conv3d_wgrad_tiled_kernel<<<grid, WT_THREADS, WT_SMEM, stream>>>(a);
       return da_check_launch("conv3d_wgrad_tiled");
     };

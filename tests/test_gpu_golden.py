@@ -63,7 +63,15 @@ def test_lncc_bending(cuda, og):
     I, J = _c(og["lncc_I"], cuda, True), _c(og["lncc_J"], cuda, True)
     loss = da.get_loss_function("lncc")()(I, J)
     loss.backward()
-    assert _rel(loss, og["lncc_loss"]) < TOL and _rel(I.grad, og["lncc_gI"]) < TOL and _rel(J.grad, og["lncc_gJ"]) < TOL
+    assert _rel(loss, og["lncc_loss"]) < TOL
+    # The reference's cancellation-form variance has its own fp32 noise: judge the gradient on the
+    # precision ladder -- our error against the fp64 restatement must not exceed max(TOL, 3 x the reference's own).
+    from oracle import ref_port as P
+    I64 = torch.from_numpy(og["lncc_I"]).double().requires_grad_(True)
+    J64 = torch.from_numpy(og["lncc_J"]).double().requires_grad_(True)
+    P.lncc(I64, J64).backward()
+    for ours, gold, truth in ((I.grad, og["lncc_gI"], I64.grad), (J.grad, og["lncc_gJ"], J64.grad)):
+        assert _rel(ours, truth.numpy()) < max(TOL, 3 * _rel(torch.from_numpy(gold), truth.numpy()))
     for name in ("iso", "aniso"):
         u = _c(og[f"bend_{name}_u"], cuda, True)
         loss = da.get_loss_function("bendingEnergy")(spacing=tuple(float(s) for s in og[f"bend_{name}_spacing"]))(u)
@@ -86,10 +94,23 @@ def test_unet_light_and_argmax(cuda, ng):
     sd = net.state_dict()
     assert _rel(sd["encoders.0.0.BN.running_mean"], ng["ul_running_mean0"]) < TOL
     assert _rel(sd["encoders.0.0.BN.running_var"], ng["ul_running_var0"]) < TOL
+    # Whole-network gradients sit on the precision ladder: the golden values are the REFERENCE's fp32
+    # results, which carry their own round-off (batch-1 BatchNorm, 20 layers); the fp64 restatement is the truth and
+    # our error against it must stay within max(1e-3, 3 x the reference's own error) -- same rule as test_gpu_nets.
+    from oracle import ref_port as P
+    from parity_util import check_grads_vs_truth, cpu_state
+    torch.manual_seed(230)
+    fresh = da.get_network("UNet_light")(1, 4, bias=True, BN=True)
+    fresh.weights_init()
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else (v.double() if v.is_floating_point() else v))
+            for k, v in cpu_state(fresh).items()}
+    l64 = P.dice_multiclass(P.unet_generator_forward(torch.from_numpy(ng["ul_x"]).double(), sd64, 1, True),
+                            torch.from_numpy(ng["ul_labels"]).long(), 4, "Uniform", False, True, 1e-6)
+    l64.backward()
+    keys = [k[len("ul_grad/"):] for k in ng if k.startswith("ul_grad/")]
     params = dict(net.named_parameters())
-    gmax = max(float(np.abs(ng[k]).max()) for k in ng if k.startswith("ul_grad/"))
-    for k in [k for k in ng if k.startswith("ul_grad/")]:
-        assert _rel(params[k[len("ul_grad/"):]].grad, ng[k], floor=1e-3 * gmax) < 5 * TOL, k   # whole-net gradients: see test_gpu_nets
+    check_grads_vs_truth({k: params[k].grad for k in keys}, {k: torch.from_numpy(ng["ul_grad/" + k]) for k in keys},
+                         {k: sd64[k].grad for k in keys}, 1e-3)
 
 
 def test_voxelmorph_unet32_joint(cuda, ng):

@@ -177,6 +177,10 @@ CONV_CASES = [
     (16, 0, 7, 1, 1, (8, 9, 10), False),        # 1x1 head
     (24, 8, 16, 3, 1, (8, 8, 8), True),         # ConvTranspose3d k3 s1 p1, two sources
     (16, 0, 8, 3, 1, (32, 32, 32), True),       # ConvTranspose3d through the tiled kernel
+    (6, 0, 16, 3, 1, (32, 32, 32), False),      # TMA path, last channel chunk partial (zero-filled by the TMA unit)
+    (8, 6, 8, 3, 1, (32, 36, 32), False),       # TMA path, two sources, second one partial
+    (32, 16, 16, 3, 1, (8, 64, 160), False),    # full-width rows of the benchmark volume (decBlock2.0 channels)
+    (64, 64, 64, 3, 1, (20, 24, 20), False),    # deepest decoder level of UNet_light at the benchmark size
 ]
 
 

@@ -1,0 +1,34 @@
+"""One conv3d forward + backward at a hot-layer shape, for ncu (single kernels):
+  ncu --set full --clock-control none --import-source on -k regex:wgrad_tiled -c 1 -o gpurun_out/wg python tools/profile_conv.py
+Env: DA_SHAPE="C1,C2,Cout,D,H,W" (default decBlock2.1: 16,0,16,160,192,160)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from deepatlas_b200 import ops  # noqa: E402
+
+C1, C2, Cout, D, H, W = (int(v) for v in os.environ.get("DA_SHAPE", "16,0,16,160,192,160").split(","))
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(230)
+x1 = torch.rand((1, C1, D, H, W), device=dev, generator=g, requires_grad=True)
+x2 = torch.rand((1, C2, D, H, W), device=dev, generator=g, requires_grad=True) if C2 else None
+w = (torch.randn((Cout, C1 + C2, 3, 3, 3), device=dev, generator=g) * 0.05).requires_grad_(True)
+b = torch.zeros(Cout, device=dev, requires_grad=True)
+reps = int(os.environ.get("DA_REPS", "2"))
+for _ in range(reps):
+    y = ops.conv3d(x1, w, b, x2=x2)
+    y.backward(torch.ones_like(y))
+torch.cuda.synchronize()
+# timing without a profiler attached (meaningless under ncu)
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+y = None
+ev[0].record(); y = ops.conv3d(x1, w, b, x2=x2); ev[1].record()
+gy = torch.ones_like(y)
+torch.cuda.synchronize()
+ev[2].record(); y.backward(gy); ev[3].record()
+torch.cuda.synchronize()
+fl = 2.0 * 27 * (C1 + C2) * Cout * D * H * W
+print(f"shape {C1}+{C2}->{Cout} @{D}x{H}x{W}: fwd {ev[0].elapsed_time(ev[1]):.3f} ms ({fl / ev[0].elapsed_time(ev[1]) / 1e9:.1f} TFLOP/s), "
+      f"bwd {ev[2].elapsed_time(ev[3]):.3f} ms ({2 * fl / ev[2].elapsed_time(ev[3]) / 1e9:.1f} TFLOP/s)")
