@@ -24,6 +24,7 @@ SIGNATURES = {
     # warp3d
     "da_warp3d_fwd": ("ppippiiiiiiiis", "rc"),
     "da_warp3d_bwd": ("pppippiiiiiiiis", "rc"),
+    "da_warp3d_bwd_cl": ("pppippiiiiiiiis", "rc"),
     # dice
     "da_dice_workspace_bytes": ("iil", "size"),
     "da_dice_sums_fwd": ("ppiiiilppls", "rc"),

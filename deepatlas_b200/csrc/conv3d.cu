@@ -603,6 +603,64 @@ __global__ void __launch_bounds__(WT_THREADS, 1) conv3d_wgrad_tiled_kernel(WgTil
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 1x1 weight gradient (the class head: 16 -> n_classes at full resolution).  HBM/L2 streaming:
+//   dW[co][ci] = sum_v dY[co][v] * X[ci][v];  block = one (4 ci x 8 co) task over one region of voxels,
+// every thread walks float4 voxel-quads (12 LDG.128 per 128 FFMA), block-level shuffle reduce at the end.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            float* __restrict__ partials, int N, int C, int ci_off,
+                                                            int Cin_total, int Cout, int64_t V, int64_t quads_per_region,
+                                                            int64_t region_stride) {
+  __shared__ float red[8][32];
+  const int nCoB = (Cout + WG_CO - 1) / WG_CO;
+  const int cob = blockIdx.y % nCoB, cib = blockIdx.y / nCoB;
+  const int64_t nq = V / 4;
+  const int64_t q0 = (int64_t)blockIdx.x * quads_per_region, q1 = min(nq, q0 + quads_per_region);
+  float acc[WG_CI][WG_CO];
+#pragma unroll
+  for (int c = 0; c < WG_CI; ++c)
+#pragma unroll
+    for (int o = 0; o < WG_CO; ++o) acc[c][o] = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float4* xp[WG_CI];
+    const float4* dp[WG_CO];
+#pragma unroll
+    for (int c = 0; c < WG_CI; ++c) xp[c] = reinterpret_cast<const float4*>(x + ((int64_t)n * C + min(cib * WG_CI + c, C - 1)) * V);
+#pragma unroll
+    for (int o = 0; o < WG_CO; ++o) dp[o] = reinterpret_cast<const float4*>(dy + ((int64_t)n * Cout + min(cob * WG_CO + o, Cout - 1)) * V);
+    for (int64_t q = q0 + threadIdx.x; q < q1; q += 256) {
+      float4 xv[WG_CI], dv[WG_CO];
+#pragma unroll
+      for (int c = 0; c < WG_CI; ++c) xv[c] = __ldg(xp[c] + q);
+#pragma unroll
+      for (int o = 0; o < WG_CO; ++o) dv[o] = __ldg(dp[o] + q);
+#pragma unroll
+      for (int c = 0; c < WG_CI; ++c)
+#pragma unroll
+        for (int o = 0; o < WG_CO; ++o)
+          acc[c][o] = fmaf(xv[c].x, dv[o].x, fmaf(xv[c].y, dv[o].y, fmaf(xv[c].z, dv[o].z, fmaf(xv[c].w, dv[o].w, acc[c][o]))));
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < WG_CI; ++c)
+#pragma unroll
+    for (int o = 0; o < WG_CO; ++o) {
+      const float t = warp_sum(acc[c][o]);
+      if (lane == 0) red[warp][c * WG_CO + o] = t;
+    }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int c = threadIdx.x / WG_CO, o = threadIdx.x % WG_CO;
+    const int ci = cib * WG_CI + c, co = cob * WG_CO + o;
+    if (ci < C && co < Cout) partials[(int64_t)blockIdx.x * region_stride + (int64_t)co * Cin_total + ci_off + ci] = t;
+  }
+}
+
 #include "conv3d_tma.inc.cuh"
 
 // out[i] = sum_r partials[r][i]  (fixed order)
@@ -979,6 +1037,26 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
         rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);
       }
     }
+    return rc;
+  }
+  const int64_t Vk1 = (int64_t)Di * Hi * Wi;
+  if (ks == 1 && stride == 1 && pad == 0 && (Vk1 & 3) == 0 && aligned16(x1) && aligned16(x2) && aligned16(dy) && !force_direct()) {
+    const int64_t nq = Vk1 / 4;
+    int nregions = cap < 64 ? cap : 64;
+    if (nregions > nq) nregions = (int)nq;
+    const int64_t qpr = da_cdiv(nq, nregions);
+    nregions = (int)da_cdiv(nq, qpr);
+    auto launch1 = [&](const float* xin, int C, int ci_off) -> int {
+      dim3 grid(nregions, ((C + WG_CI - 1) / WG_CI) * ((Cout + WG_CO - 1) / WG_CO));
+      conv1x1_wgrad_kernel<<<grid, 256, 0, stream>>>(xin, dy, partials, N, C, ci_off, Cin, Cout, Vk1, qpr, count);
+      return da_check_launch("conv1x1_wgrad");
+    };
+    int rc = launch1(x1, C1, 0);
+    if (!rc && C2) rc = launch1(x2, C2, C1);
+    if (rc) return rc;
+    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+    rc = da_check_launch("conv1x1_wgrad/reduce");
+    if (!rc && grad_bias) rc = run_channel_sum(dy, N, Cout, Vk1, grad_bias, partials + (int64_t)nregions * count, stream);
     return rc;
   }
   const int64_t total_rows = (int64_t)N * Do * Ho * ((Wo + 31) / 32);

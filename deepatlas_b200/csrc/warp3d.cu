@@ -144,6 +144,58 @@ __global__ void __launch_bounds__(256) warp3d_bwd_kernel(const float* __restrict
   }
 }
 
+// Channels-last scatter for multi-channel sources (the 32-class probability warp of the anatomy loss):
+// grad_src_cl is [N][Vs][C] so that the C contributions to one source voxel are contiguous and four of them go out
+// in ONE vector reduction (red.global.add.v4.f32, sm_90+): 8*C/4 reductions per output voxel instead of 8*C.
+// The caller hands the buffer back to autograd as a permuted (N,C,D,H,W) view.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool ADD_ID>
+__global__ void __launch_bounds__(256) warp3d_bwd_cl_kernel(const float* __restrict__ gout, const float* __restrict__ src,
+                                                            const float* __restrict__ field, float* __restrict__ gsrc_cl,
+                                                            float* __restrict__ gfield, WarpGeom g) {
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo, Vs = (int64_t)g.D * g.H * g.W;
+  const int64_t total = (int64_t)g.N * Vo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Vo);
+    const int64_t v = i - (int64_t)n * Vo;
+    const int x = (int)(v % g.Wo), y = (int)((v / g.Wo) % g.Ho), z = (int)(v / ((int64_t)g.Wo * g.Ho));
+    float px, py, pz;
+    load_phi<ADD_ID>(field + (int64_t)n * 3 * Vo, Vo, v, x, y, z, g, px, py, pz);
+    Corners c;
+    make_corners(unnormalize(px, g.W), unnormalize(py, g.H), unnormalize(pz, g.D), g, c);
+    const float* s = src + (int64_t)n * g.C * Vs;
+    float* gs = gsrc_cl + (int64_t)n * Vs * g.C;
+    const float* go = gout + (int64_t)n * g.C * Vo + v;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int ch = 0; ch < g.C; ch += 4, go += 4 * Vo) {
+      const float g0 = go[0], g1 = go[Vo], g2 = go[2 * Vo], g3 = go[3 * Vo];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!c.ok[k]) continue;
+        const int dx = k & 1, dy = (k >> 1) & 1, dz = k >> 2;
+        const float w = c.w[k];
+        red_add_v4(gs + c.off[k] * g.C + ch, w * g0, w * g1, w * g2, w * g3);
+        if (gfield) {
+          const float* sp = s + (int64_t)ch * Vs + c.off[k];
+          const float val = __ldg(sp) * g0 + __ldg(sp + Vs) * g1 + __ldg(sp + 2 * Vs) * g2 + __ldg(sp + 3 * Vs) * g3;
+          gx += (dx ? val : -val) * c.fy[dy] * c.fz[dz];
+          gy += (dy ? val : -val) * c.fx[dx] * c.fz[dz];
+          gz += (dz ? val : -val) * c.fx[dx] * c.fy[dy];
+        }
+      }
+    }
+    if (gfield) {
+      float* gf = gfield + (int64_t)n * 3 * Vo;
+      gf[v] = gx * (0.5f * (float)(g.W - 1));
+      gf[Vo + v] = gy * (0.5f * (float)(g.H - 1));
+      gf[2 * Vo + v] = gz * (0.5f * (float)(g.D - 1));
+    }
+  }
+}
+
 inline int grid_for(int64_t total, int threads) {
   int64_t b = da_cdiv(total, threads);
   const int64_t cap = (int64_t)DA_NUM_SMS * 16;
@@ -190,4 +242,24 @@ DA_API int da_warp3d_bwd(const float* grad_out, const float* src, const float* f
   else
     warp3d_bwd_kernel<false><<<grid, 256, 0, stream>>>(grad_out, src, field, grad_src, grad_field, g);
   return da_check_launch("da_warp3d_bwd");
+}
+
+// Same as da_warp3d_bwd, but grad_src is written CHANNELS-LAST: grad_src_cl [N, D*H*W, C] (zeroed here).  Requires
+// C % 4 == 0 and a 16-byte aligned buffer; used for the multi-channel (probability-map) warp where the vectorised
+// reductions cut the scatter cost about four-fold.
+DA_API int da_warp3d_bwd_cl(const float* grad_out, const float* src, const float* field, int add_identity,
+                            float* grad_src_cl, float* grad_field, int N, int C, int D, int H, int W, int Do, int Ho,
+                            int Wo, cudaStream_t stream) {
+  DA_REQUIRE(grad_out && src && field && grad_src_cl, "da_warp3d_bwd_cl: null pointer");
+  DA_REQUIRE((C & 3) == 0 && (((uintptr_t)grad_src_cl) & 15) == 0, "da_warp3d_bwd_cl: needs C %% 4 == 0 and a 16-byte aligned buffer");
+  WarpGeom g{N, C, D, H, W, Do, Ho, Wo};
+  cudaError_t e = cudaMemsetAsync(grad_src_cl, 0, sizeof(float) * (size_t)N * C * D * H * W, stream);
+  if (e != cudaSuccess) { da_set_error("da_warp3d_bwd_cl memset: %s", cudaGetErrorString(e)); return (int)e; }
+  const int64_t total = (int64_t)N * Do * Ho * Wo;
+  const int grid = grid_for(total, 256);
+  if (add_identity)
+    warp3d_bwd_cl_kernel<true><<<grid, 256, 0, stream>>>(grad_out, src, field, grad_src_cl, grad_field, g);
+  else
+    warp3d_bwd_cl_kernel<false><<<grid, 256, 0, stream>>>(grad_out, src, field, grad_src_cl, grad_field, g);
+  return da_check_launch("da_warp3d_bwd_cl");
 }

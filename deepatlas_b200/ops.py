@@ -69,10 +69,17 @@ class Warp3dFunction(torch.autograd.Function):
         g_src = g_field = None
         if g_out is not None and (need_src or need_field):
             g_out = _f32(g_out, "grad_out")
-            g_src = torch.empty_like(src) if need_src else None
             g_field = torch.empty_like(field) if need_field else None
-            _lib.call("da_warp3d_bwd", _p(g_out), _p(src), _p(field), int(ctx.add_identity), _p(g_src),
-                      _p(g_field), N, C, D, H, W, Do, Ho, Wo, _stream())
+            if need_src and C % 4 == 0:
+                # multi-channel scatter: channels-last buffer + vector reductions, returned as a permuted view
+                g_cl = torch.empty((N, D, H, W, C), dtype=torch.float32, device=src.device)
+                _lib.call("da_warp3d_bwd_cl", _p(g_out), _p(src), _p(field), int(ctx.add_identity), _p(g_cl),
+                          _p(g_field), N, C, D, H, W, Do, Ho, Wo, _stream())
+                g_src = g_cl.permute(0, 4, 1, 2, 3)
+            else:
+                g_src = torch.empty_like(src) if need_src else None
+                _lib.call("da_warp3d_bwd", _p(g_out), _p(src), _p(field), int(ctx.add_identity), _p(g_src),
+                          _p(g_field), N, C, D, H, W, Do, Ho, Wo, _stream())
         if need_field and g_phi is not None:
             g_field = g_phi if g_field is None else g_field + g_phi
         return g_src, g_field, None, None

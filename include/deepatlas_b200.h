@@ -42,6 +42,11 @@ int da_warp3d_bwd(const float* grad_out, const float* src, const float* field, i
                   float* grad_src, float* grad_field, int N, int C, int D, int H, int W, int Do, int Ho,
                   int Wo, da_stream_t stream);
 
+/* grad_src written channels-last [N, D*H*W, C] with vector reductions (C % 4 == 0); same arguments otherwise */
+int da_warp3d_bwd_cl(const float* grad_out, const float* src, const float* field, int add_identity,
+                     float* grad_src_cl, float* grad_field, int N, int C, int D, int H, int W, int Do, int Ho,
+                     int Wo, da_stream_t stream);
+
 /* ---- softmax + Dice sums -----------------------------------------------------------------------------
  * replaces F.softmax (lib/loss.py:427), mask_to_one_hot (lib/transforms.py:675-689) and the three
  * spatial sums of DiceLossMultiClass.forward (lib/loss.py:449-450,472).

@@ -147,8 +147,8 @@ def warp(source, deform_field):
 def _vm_block(x, sd: SD, prefix: str, stride: int):
     """modules.convBlock as VoxelMorph uses it (lib/network_factory/modules.py:28-62,
     voxel_morph.py:44-55): Conv3d k3 p1 bias -> ReLU, no BN, no residual."""
-    return F.relu(F.conv3d(x, sd[prefix + ".conv.weight"], sd.get(prefix + ".conv.bias"),
-                           stride=stride, padding=1))
+    return _act(F.conv3d(x, sd[prefix + ".conv.weight"], sd.get(prefix + ".conv.bias"),
+                         stride=stride, padding=1), "ReLU")
 
 
 def voxelmorph_forward(source, target, sd: SD):

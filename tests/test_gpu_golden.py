@@ -85,7 +85,9 @@ def test_unet_light_and_argmax(cuda, ng):
     net = da.get_network("UNet_light")(1, 4, bias=True, BN=True)
     net.weights_init()
     net = net.to(cuda).train()
-    logits = net(_c(ng["ul_x"], cuda))
+    from parity_util import MaskRecorder, MaskReplay
+    with MaskRecorder() as rec:
+        logits = net(_c(ng["ul_x"], cuda))
     assert _rel(logits, ng["ul_logits"]) < TOL
     assert np.array_equal(torch.max(logits, 1)[1].cpu().numpy().astype(np.uint8), ng["ul_argmax"])
     loss = da.get_loss_function("dice")(n_class=4, weight_type="Uniform", softmax=True, eps=1e-6)(logits, _c(ng["ul_labels"], cuda))
@@ -104,8 +106,9 @@ def test_unet_light_and_argmax(cuda, ng):
     fresh.weights_init()
     sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else (v.double() if v.is_floating_point() else v))
             for k, v in cpu_state(fresh).items()}
-    l64 = P.dice_multiclass(P.unet_generator_forward(torch.from_numpy(ng["ul_x"]).double(), sd64, 1, True),
-                            torch.from_numpy(ng["ul_labels"]).long(), 4, "Uniform", False, True, 1e-6)
+    with MaskReplay(rec.masks):   # the fp64 truth takes the CUDA path's activation branches (parity_util)
+        l64 = P.dice_multiclass(P.unet_generator_forward(torch.from_numpy(ng["ul_x"]).double(), sd64, 1, True),
+                                torch.from_numpy(ng["ul_labels"]).long(), 4, "Uniform", False, True, 1e-6)
     l64.backward()
     keys = [k[len("ul_grad/"):] for k in ng if k.startswith("ul_grad/")]
     params = dict(net.named_parameters())

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from parity_util import check_grads_vs_truth, cpu_state, oracle_joint_loss, rel_err
+from parity_util import MaskRecorder, MaskReplay, check_grads_vs_truth, cpu_state, oracle_joint_loss, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4        # forward outputs (north star)
@@ -27,15 +27,20 @@ def test_unet_light(cuda, n_classes, size, bn):
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in cpu_state(net).items()}
     sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else (v.double() if v.is_floating_point() else v))
             for k, v in cpu_state(net).items()}
-    stats = {}
-    y_ref = P.unet_generator_forward(x, sd, 1, bn, stats_out=stats)
-    y64 = P.unet_generator_forward(x.double(), sd64, 1, bn)
-    P.dice_multiclass(y64, lab.long(), n_classes, "Uniform", False, True, 1e-6).backward()
-    y64 = y64.detach()
     crit = da.get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", softmax=True, eps=1e-6)
-    y = net(x.to(cuda))
+    with MaskRecorder() as rec:   # the oracle takes the CUDA path's activation branches (parity_util.MaskReplay)
+        y = net(x.to(cuda))
     loss = crit(y, lab.to(cuda))
     loss.backward()
+    stats = {}
+    replay = MaskReplay(rec.masks)
+    with replay:
+        y_ref = P.unet_generator_forward(x, sd, 1, bn, stats_out=stats)
+        replay.restart()
+        y64 = P.unet_generator_forward(x.double(), sd64, 1, bn)
+    assert replay.flips <= 64, f"{replay.flips} activation-mask flips"  # each verified to sit within round-off of zero
+    P.dice_multiclass(y64, lab.long(), n_classes, "Uniform", False, True, 1e-6).backward()
+    y64 = y64.detach()
     loss_ref = P.dice_multiclass(y_ref, lab.long(), n_classes, "Uniform", False, True, 1e-6)
     loss_ref.backward()
     assert y.shape == y_ref.shape
@@ -64,9 +69,13 @@ def test_unet_32base(cuda):
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in cpu_state(net).items()}
     sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else (v.double() if v.is_floating_point() else v))
             for k, v in cpu_state(net).items()}
-    y_ref = P.unet_forward(x, sd, True)
-    y64 = P.unet_forward(x.double(), sd64, True)
-    y = net(x.to(cuda))
+    with MaskRecorder() as rec:
+        y = net(x.to(cuda))
+    replay = MaskReplay(rec.masks)
+    with replay:
+        y_ref = P.unet_forward(x, sd, True)
+        replay.restart()
+        y64 = P.unet_forward(x.double(), sd64, True)
     assert rel_err(y, y64) < max(TOL, 3 * rel_err(y_ref, y64)), f"UNet logits rel err {rel_err(y, y64):.3e}"
     cot = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(7))
     (y * cot.to(cuda)).sum().backward()
@@ -86,8 +95,11 @@ def test_voxelmorph(cuda, size):
     g = torch.Generator().manual_seed(230)
     s, t = torch.rand((1, 1) + size, generator=g), torch.rand((1, 1) + size, generator=g)
     sd = {k: v.clone().requires_grad_(True) for k, v in cpu_state(net).items()}
-    ref = P.voxelmorph_forward(s, t, sd)
-    out = net(s.to(cuda), t.to(cuda))
+    with MaskRecorder() as rec:
+        out = net(s.to(cuda), t.to(cuda))
+    replay = MaskReplay(rec.masks)
+    with replay:
+        ref = P.voxelmorph_forward(s, t, sd)
     for name, a, b in zip(("disp", "warped", "deform"), out, ref):
         assert a.shape == b.shape
         assert rel_err(a, b) < TOL, f"{name}: rel err {rel_err(a, b):.3e}"
@@ -95,7 +107,9 @@ def test_voxelmorph(cuda, size):
     (lncc(out[1], t.to(cuda)) + 1000.0 * bend(out[0])).backward()
     (P.lncc(ref[1], t) + 1000.0 * P.bending_energy(ref[0])).backward()
     sd64 = {k: v.double().requires_grad_(True) for k, v in cpu_state(net).items()}
-    r64 = P.voxelmorph_forward(s.double(), t.double(), sd64)
+    replay.restart()
+    with replay:
+        r64 = P.voxelmorph_forward(s.double(), t.double(), sd64)
     (P.lncc(r64[1], t.double()) + 1000.0 * P.bending_energy(r64[0])).backward()
     check_grads_vs_truth(_param_grads(net), {k: v.grad for k, v in sd.items()}, {k: v.grad for k, v in sd64.items()}, GTOL)
 
@@ -108,10 +122,12 @@ def test_joint_step(cuda, C, size):
     model = JointModel(n_classes=C).to(cuda)
     model.weights_init()
     batch = make_synthetic_pair(size, C, seed=230, device=cuda)
-    loss, parts = model.joint_loss(*batch)
+    with MaskRecorder() as rec:
+        loss, parts = model.joint_loss(*batch)
     loss.backward()
-    ref_loss, ref_grads = oracle_joint_loss(model, batch, P)
-    true_loss, true_grads = oracle_joint_loss(model, batch, P, dtype=torch.float64)
+    replay = MaskReplay(rec.masks)
+    ref_loss, ref_grads = oracle_joint_loss(model, batch, P, replay=replay)
+    true_loss, true_grads = oracle_joint_loss(model, batch, P, dtype=torch.float64, replay=replay)
     assert rel_err(loss, true_loss) < max(TOL, 3 * rel_err(ref_loss, true_loss))
     ours = _param_grads(model)
     assert len(true_grads) >= 60

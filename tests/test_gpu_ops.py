@@ -51,7 +51,7 @@ def test_no_cpu_fallback(built_lib):
         ops.softmax(torch.zeros(1, 2, 4, 4, 4))
 
 
-@pytest.mark.parametrize("C,size", [(1, (12, 14, 16)), (5, (9, 10, 11))])
+@pytest.mark.parametrize("C,size", [(1, (12, 14, 16)), (5, (9, 10, 11)), (8, (9, 10, 12))])
 @pytest.mark.parametrize("add_id", [True, False])
 def test_warp3d(cuda, C, size, add_id):
     from deepatlas_b200 import ops
@@ -175,6 +175,7 @@ CONV_CASES = [
     (16, 0, 32, 3, 2, (16, 18, 20), False),     # stride 2
     (32, 0, 32, 3, 2, (9, 11, 13), False),      # stride 2, odd extents
     (16, 0, 7, 1, 1, (8, 9, 10), False),        # 1x1 head
+    (16, 0, 32, 1, 1, (16, 20, 24), False),     # 1x1 head, 32 classes (streaming k1 weight-gradient kernel)
     (24, 8, 16, 3, 1, (8, 8, 8), True),         # ConvTranspose3d k3 s1 p1, two sources
     (16, 0, 8, 3, 1, (32, 32, 32), True),       # ConvTranspose3d through the tiled kernel
     (6, 0, 16, 3, 1, (32, 32, 32), False),      # TMA path, last channel chunk partial (zero-filled by the TMA unit)
