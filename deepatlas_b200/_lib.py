@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeepatlas_b200.so")
+LIB_PATH = os.environ.get("DA_LIB_PATH") or os.path.join(_HERE, "libdeepatlas_b200.so")  # override: kernel experiments
 
 _T = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
       "d": ctypes.c_double, "s": ctypes.c_void_p}

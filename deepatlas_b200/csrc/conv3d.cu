@@ -777,27 +777,41 @@ inline bool fwd_tma_ok(const float* x1, const float* x2, const float* out, const
          (g.C2 == 0 || g.C1 % TMA_CK == 0);
 }
 
+int g_fwd_tiling = -1;  // 2 = thread owns 4 channels x 16/8 voxels (default), 1 = 4 voxels x CO channels (DA_FWD_TILING=1)
 template <int CO>
 int launch_fwd_tma(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g,
                    int cin_pad, cudaStream_t stream) {
-  using Cfg = FwdTmaCfg<CO>;
+  if (g_fwd_tiling < 0) {
+    const char* e = getenv("DA_FWD_TILING");
+    g_fwd_tiling = (e && strcmp(e, "1") == 0) ? 1 : 2;
+  }
+  const bool v2 = (CO >= 8) && g_fwd_tiling == 2;
+  const int pitch = v2 ? HXW : HXT;
   CUtensorMap m1, m2;
-  int rc = da_make_volume_map(&m1, x1, g.N, g.C1, g.Di, g.Hi, g.Wi, HXT, HY, HZ, TMA_CK);
+  int rc = da_make_volume_map(&m1, x1, g.N, g.C1, g.Di, g.Hi, g.Wi, pitch, HY, HZ, TMA_CK);
   if (rc) return rc;
   if (g.C2) {
-    rc = da_make_volume_map(&m2, x2, g.N, g.C2, g.Di, g.Hi, g.Wi, HXT, HY, HZ, TMA_CK);
+    rc = da_make_volume_map(&m2, x2, g.N, g.C2, g.Di, g.Hi, g.Wi, pitch, HY, HZ, TMA_CK);
     if (rc) return rc;
   } else {
     m2 = m1;
   }
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(conv3d_fwd_tma_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_fwd_tma_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdTmaCfg<CO>::SMEM_BYTES);
+    if constexpr (CO >= 8)
+      cudaFuncSetAttribute(conv3d_fwd_tma2_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Cfg<CO>::SMEM_BYTES);
     configured = true;
   }
   const int tiles_x = (g.Wo + TX - 1) / TX, tiles_y = (g.Ho + TY - 1) / TY, tiles_z = (g.Do + TZ - 1) / TZ;
   dim3 grid(tiles_x * tiles_y * tiles_z, g.Cop / CO, g.N);
-  conv3d_fwd_tma_kernel<CO><<<grid, TILED_THREADS, Cfg::SMEM_BYTES, stream>>>(m1, m2, wp, bias, out, g, tiles_x, tiles_y, cin_pad);
+  if constexpr (CO >= 8) {
+    if (v2) {
+      conv3d_fwd_tma2_kernel<CO><<<grid, TILED_THREADS, Fwd2Cfg<CO>::SMEM_BYTES, stream>>>(m1, m2, wp, bias, out, g, tiles_x, tiles_y, cin_pad);
+      return da_check_launch("conv3d_fwd_tma2");
+    }
+  }
+  conv3d_fwd_tma_kernel<CO><<<grid, TILED_THREADS, FwdTmaCfg<CO>::SMEM_BYTES, stream>>>(m1, m2, wp, bias, out, g, tiles_x, tiles_y, cin_pad);
   return da_check_launch("conv3d_fwd_tma");
 }
 
@@ -1011,7 +1025,7 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
         int r = da_make_volume_map(&mx, xin, N, C, Di, Hi, Wi, HXT, HY, HZ, WG_CI);
         if (!r) r = da_make_volume_map(&mdy, gout, N, Cout_, Di, Hi, Wi, TX, TY, TZ, WG_CO);
         if (r) return r;
-        conv3d_wgrad_tma_kernel<<<grid, WT_THREADS, WTM_SMEM_BYTES, stream>>>(mx, mdy, a);
+        conv3d_wgrad_tma_kernel<<<grid, WTM_THREADS, WTM_SMEM_BYTES, stream>>>(mx, mdy, a);
         return da_check_launch("conv3d_wgrad_tma");
       }
       conv3d_wgrad_tiled_kernel<<<grid, WT_THREADS, WT_SMEM, stream>>>(a);

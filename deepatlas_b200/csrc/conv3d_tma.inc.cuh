@@ -93,10 +93,18 @@ __global__ void __launch_bounds__(TILED_THREADS, 2)
           const float in[6] = {a.w, b.x, b.y, b.z, b.w, e.x};
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
+#ifdef DA_W_LDG
+            const float4* w4 = reinterpret_cast<const float4*>(wp + (((int64_t)cog * cin_pad + (int64_t)c * TMA_CK + cl) * 27 + (kz * 3 + ky) * 3 + kx) * CO);
+#else
             const float4* w4 = reinterpret_cast<const float4*>(sw + (cl * 27 + (kz * 3 + ky) * 3 + kx) * CO);
+#endif
 #pragma unroll
             for (int q = 0; q < CO / 4; ++q) {
+#ifdef DA_W_LDG
+              const float4 w = __ldg(w4 + q);
+#else
               const float4 w = w4[q];
+#endif
 #pragma unroll
               for (int i = 0; i < VX; ++i) {
                 acc[i][4 * q + 0] = fmaf(in[i + kx], w.x, acc[i][4 * q + 0]);
@@ -133,6 +141,140 @@ __global__ void __launch_bounds__(TILED_THREADS, 2)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Forward / dgrad, second register tiling: a thread owns 4 output channels x VT consecutive voxels of one row
+// (VT = 16 for 16-channel blocks, 8 for 8-channel blocks).  Per (ci, kz, ky) it reads its input row segment with
+// aligned LDS.128 (distinct per lane, conflict-free at a 44-float pitch) and three broadcast LDS.128 of weights:
+// 192 FFMA per 36 shared-memory wavefronts, versus 60 for the 4-voxel x 16-channel tiling above (whose broadcast
+// weight loads cost a full 4 wavefronts each and held the LSU at 86 % while the FMA pipe sat at 70 %, ncu r11).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int HXW = 44;  // halo row pitch (floats) of this kernel: X0-4 .. X0+39
+
+template <int CO_BLK>
+struct Fwd2Cfg {
+  static constexpr int NCG = CO_BLK / 4;            // channel groups of 4 per block
+  static constexpr int NVS = 8 / NCG;               // voxel sets (warps per channel group)
+  static constexpr int VT = 32 / NVS;               // voxels per thread along x
+  static constexpr int SEGS = TX / VT;              // threads per row
+  static constexpr int NLD = (VT + 2 + 3 + 3) / 4;  // aligned float4 loads covering halo idx seg*VT+3 .. seg*VT+VT+4
+  static constexpr int SX_BYTES = round128(TMA_CK * HZ * HY * HXW * 4);
+  static constexpr int SW_BYTES = round128(TMA_CK * 27 * CO_BLK * 4);
+  static constexpr int STAGE_BYTES = SX_BYTES + SW_BYTES;
+  static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;
+  static constexpr uint32_t TX_BYTES = TMA_CK * HZ * HY * HXW * 4 + TMA_CK * 27 * CO_BLK * 4;
+};
+
+template <int CO_BLK>
+__global__ void __launch_bounds__(TILED_THREADS, 2)
+    conv3d_fwd_tma2_kernel(const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap mx2,
+                           const float* __restrict__ wp, const float* __restrict__ bias, float* __restrict__ out, ConvGeom g,
+                           int tiles_x, int tiles_y, int cin_pad) {
+  using Cfg = Fwd2Cfg<CO_BLK>;
+  constexpr int VT = Cfg::VT, NLD = Cfg::NLD;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[2];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int n = blockIdx.z, cog = blockIdx.y;
+  int tb = blockIdx.x;
+  const int bx = tb % tiles_x; tb /= tiles_x;
+  const int by = tb % tiles_y;
+  const int bz = tb / tiles_y;
+  const int X0 = bx * TX, Y0 = by * TY, Z0 = bz * TZ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = warp % Cfg::NCG, vs = warp / Cfg::NCG;
+  const int seg = lane % Cfg::SEGS;
+  const int row = vs * (32 / Cfg::SEGS) + lane / Cfg::SEGS;  // 0..31 = tz*8 + ty
+  const int tz = row >> 3, ty = row & 7;
+  const int nchunks = cin_pad / TMA_CK;
+  const int chunks1 = (g.C1 + TMA_CK - 1) / TMA_CK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&mx1);
+    if (g.C2) tma_prefetch_desc(&mx2);
+  }
+  __syncthreads();
+
+  auto issue = [&](int c, int s) {
+    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+    mbar_expect_tx(&full[s], Cfg::TX_BYTES);
+    if (c < chunks1)
+      tma_load_5d(st, &mx1, &full[s], X0 - HX0, Y0 - 1, Z0 - 1, c * TMA_CK, n);
+    else
+      tma_load_5d(st, &mx2, &full[s], X0 - HX0, Y0 - 1, Z0 - 1, (c - chunks1) * TMA_CK, n);
+    bulk_load_1d(st + Cfg::SX_BYTES, wp + ((int64_t)cog * cin_pad + (int64_t)c * TMA_CK) * 27 * CO_BLK, TMA_CK * 27 * CO_BLK * 4,
+                 &full[s]);
+  };
+
+  float acc[4][VT];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int i = 0; i < VT; ++i) acc[o][i] = 0.f;
+
+  if (threadIdx.x == 0) issue(0, 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1;
+    if (threadIdx.x == 0 && c + 1 < nchunks) issue(c + 1, s ^ 1);
+    mbar_wait(&full[s], (c >> 1) & 1);
+    const float* sx = reinterpret_cast<const float*>(smem + s * Cfg::STAGE_BYTES);
+    const float* sw = reinterpret_cast<const float*>(smem + s * Cfg::STAGE_BYTES + Cfg::SX_BYTES) + cg * 4;
+#pragma unroll 1
+    for (int cl = 0; cl < TMA_CK; ++cl) {
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4* rowp = reinterpret_cast<const float4*>(sx + ((cl * HZ + tz + kz) * HY + ty + ky) * HXW + seg * VT);
+          float in[NLD * 4];
+#pragma unroll
+          for (int j = 0; j < NLD; ++j) {
+            const float4 v = rowp[j];
+            in[4 * j + 0] = v.x; in[4 * j + 1] = v.y; in[4 * j + 2] = v.z; in[4 * j + 3] = v.w;
+          }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w = *reinterpret_cast<const float4*>(sw + (cl * 27 + (kz * 3 + ky) * 3 + kx) * CO_BLK);
+#pragma unroll
+            for (int i = 0; i < VT; ++i) {
+              const float xv = in[i + kx + 3];  // halo idx 3 = voxel x-1
+              acc[0][i] = fmaf(xv, w.x, acc[0][i]);
+              acc[1][i] = fmaf(xv, w.y, acc[1][i]);
+              acc[2][i] = fmaf(xv, w.z, acc[2][i]);
+              acc[3][i] = fmaf(xv, w.w, acc[3][i]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int z = Z0 + tz, y = Y0 + ty, x = X0 + seg * VT;
+  if (z >= g.Do || y >= g.Ho) return;
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    const int co = cog * CO_BLK + cg * 4 + o;
+    if (co >= g.Cout) break;
+    const float bv = bias ? bias[co] : 0.f;
+    float* op = out + ((int64_t)n * g.Cout + co) * Vo + ((int64_t)z * g.Ho + y) * g.Wo + x;
+#pragma unroll
+    for (int q = 0; q < VT / 4; ++q) {
+      if (x + 4 * q >= g.Wo) break;  // W % 4 == 0: quads are all-in or all-out
+      float r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[i] = acc[o][4 * q + i] + bv;
+        if (g.act) r[i] = r[i] > 0.f ? r[i] : r[i] * g.slope;
+      }
+      *reinterpret_cast<float4*>(op + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // weight gradient, TMA staged (see conv3d_wgrad_tiled_kernel for the mapping)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int WTM_SX_BYTES = WG_CI * HZ * HY * HXT * 4;  // 38400
@@ -141,13 +283,18 @@ constexpr int WTM_STAGE_BYTES = WTM_SX_BYTES + WTM_SD_BYTES;
 constexpr int WTM_SMEM_BYTES = 2 * WTM_STAGE_BYTES + 128;
 static_assert(WTM_SX_BYTES % 128 == 0 && WTM_SD_BYTES % 128 == 0, "TMA destinations must stay 128-byte aligned");
 
-__global__ void __launch_bounds__(WT_THREADS, 1)
+constexpr int WTM_WARPS = 12, WTM_THREADS = WTM_WARPS * 32;
+
+// Warp w owns (kz = w / 4, ci = w % 4): all nine (ky,kx) taps x 8 output channels = 72 accumulators.  Twelve warps
+// are three per SM sub-partition (the nine-warp (kz,ky) split of the cp.async kernel leaves one sub-partition with
+// three warps and three with two: 25 % of the FMA issue slots idle at every tile barrier, ncu r11).
+__global__ void __launch_bounds__(WTM_THREADS, 1)
     conv3d_wgrad_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mdy, WgTiledArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full[2];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int kz = warp / 3, ky = warp % 3;
+  const int kz = warp >> 2, cl = warp & 3;
   const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
   const int region = blockIdx.y;
 
@@ -160,7 +307,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
   }
   __syncthreads();
 
-  float acc[96];
+  float acc[96];  // 72 used: [(ky*3+kx)*8 + o]; padded to 96 for the butterfly
 #pragma unroll
   for (int i = 0; i < 96; ++i) acc[i] = 0.f;
   float bacc[WG_CO];
@@ -188,7 +335,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
     const int k = t - t0, s = k & 1;
     if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, s ^ 1);
     mbar_wait(&full[s], (k >> 1) & 1);
-    const float* sx = reinterpret_cast<const float*>(smem + s * WTM_STAGE_BYTES);
+    const float* sx = reinterpret_cast<const float*>(smem + s * WTM_STAGE_BYTES) + cl * HZ * HY * HXT;
     const float* sd = reinterpret_cast<const float*>(smem + s * WTM_STAGE_BYTES + WTM_SX_BYTES);
 #pragma unroll 1
     for (int it = 0; it < (TZ * TY * TX / 4) / 32; ++it) {
@@ -203,8 +350,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
         for (int o = 0; o < WG_CO; ++o) bacc[o] += (d[o].x + d[o].y) + (d[o].z + d[o].w);
       }
 #pragma unroll
-      for (int c = 0; c < WG_CI; ++c) {
-        const float* row = sx + ((c * HZ + tz + kz) * HY + ty + ky) * HXT + tx4 * 4;
+      for (int ky = 0; ky < 3; ++ky) {
+        const float* row = sx + ((tz + kz) * HY + ty + ky) * HXT + tx4 * 4;
         const float4 p = *reinterpret_cast<const float4*>(row);
         const float4 p1 = *reinterpret_cast<const float4*>(row + 4);
         const float4 p2 = *reinterpret_cast<const float4*>(row + 8);
@@ -213,12 +360,12 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
           for (int o = 0; o < WG_CO; ++o) {
-            float v = acc[(kx * WG_CI + c) * WG_CO + o];
+            float v = acc[(ky * 3 + kx) * WG_CO + o];
             v = fmaf(in[kx + 0], d[o].x, v);
             v = fmaf(in[kx + 1], d[o].y, v);
             v = fmaf(in[kx + 2], d[o].z, v);
             v = fmaf(in[kx + 3], d[o].w, v);
-            acc[(kx * WG_CI + c) * WG_CO + o] = v;
+            acc[(ky * 3 + kx) * WG_CO + o] = v;
           }
         }
       }
@@ -228,13 +375,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1)
 
   butterfly_reduce<96>(acc, lane);
   float* pr = a.partials + (int64_t)region * a.region_stride;
+  const int ci = cib * WG_CI + cl;
 #pragma unroll
   for (int gi = 0; gi < 3; ++gi) {
     const int e = gi * 32 + lane;
-    const int o = e % WG_CO, c = (e / WG_CO) % WG_CI, kx = e / (WG_CO * WG_CI);
-    const int co = cob * WG_CO + o, ci = cib * WG_CI + c;
-    if (co < a.Cout && ci < a.C)
-      pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + (kz * 3 + ky) * 3 + kx] = acc[gi];
+    if (e >= 72) continue;
+    const int o = e % WG_CO, kyx = e / WG_CO;
+    const int co = cob * WG_CO + o;
+    if (co < a.Cout && ci < a.C) pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + kz * 9 + kyx] = acc[gi];
   }
   if (do_bias) {
 #pragma unroll
