@@ -49,11 +49,11 @@ class JointModel(nn.Module):
         P_m = self.seg(I_m)
         P_t = self.seg(I_t)
         disp, I_w, phi = self.reg(I_m, I_t)
-        S_w = ops.warp3d(ops.softmax(P_m), phi, add_identity=False)
         parts = {
             "sim": self.sim_loss(I_w, I_t),
             "reg": self.reg_loss(disp),
-            "ana": self.ana_dice(S_w, S_t),   # labels stand for onehot(S_t): same sums, no 629 MB one-hot
+            # dice(grid_sample(softmax(P_m), phi), onehot(S_t)): warp and Dice sums fused, labels stand for the one-hot
+            "ana": self.ana_dice.forward_warped(ops.softmax(P_m), phi, S_t),
             "sup": self.sup_dice(P_m, S_m) + self.sup_dice(P_t, S_t),
         }
         loss = lam["sim"] * parts["sim"] + lam["reg"] * parts["reg"] + lam["ana"] * parts["ana"] + lam["sup"] * parts["sup"]

@@ -36,6 +36,23 @@ class DiceLossMultiClass(nn.Module):
         if self.n_class is None:
             self.n_class = shape[1]
         sums = ops.dice_sums(source, target, apply_softmax=self.softmax)  # (B, 3, C)
+        return self._closing(sums)
+
+    def forward_warped(self, source, deform_field, target):
+        """``forward(grid_sample(source, deform_field), target)`` for a label-mask ``target`` and probability ``source``
+        (the anatomy term of the joint step, same F.grid_sample call as voxel_morph.py:90-91) without materialising the
+        warped C-channel map.  Falls back to warp + forward when the fused kernel does not apply."""
+        if self.softmax or target.is_floating_point() or target.dim() != source.dim() - 1 or source.shape[1] > 32:
+            return self.forward(ops.warp3d(source, deform_field, add_identity=False), target)
+        if self.weight_type not in ("Simple", "Volume", "Uniform"):
+            raise ValueError("Class weighting type {} does not exists!".format(self.weight_type))
+        assert source.shape[0] == target.shape[0] and tuple(deform_field.shape[-3:]) == tuple(target.shape[-3:])
+        if self.n_class is None:
+            self.n_class = source.shape[1]
+        return self._closing(ops.warped_dice_sums(source, deform_field, target, add_identity=False))
+
+    def _closing(self, sums):
+        """lib/loss.py:444-476 on the per-class sums (B, 3, C) = (source volume, target volume, intersection)."""
         if self.no_bg:
             sums = sums[:, :, 1:]
         source_volume, target_volume, intersection = sums[:, 0], sums[:, 1], sums[:, 2]

@@ -60,6 +60,20 @@ int da_dice_sums_bwd(const float* source, const void* target, int target_kind, i
                      int C, int64_t V, const float* gS, const float* gT, const float* gI,
                      float* grad_source, float* grad_target, da_stream_t stream);
 
+/* ---- warped Dice sums: the anatomy term dice(grid_sample(P, phi), onehot(S_t)) of the joint step, fused ------
+ * (F.grid_sample as at voxel_morph.py:90-91 + DiceLossMultiClass label-target sums, lib/loss.py:433-450,472).
+ * prob [N,C,D,H,W]; field [N,3,Do,Ho,Wo]; labels [N,Do,Ho,Wo] (kind 0 uint8, 1 int64, 3 int32); sums [N,3,C].
+ * The warped map is never materialised; backward scatters 16 scalars per voxel (see csrc/warp_dice.cu). */
+int64_t da_warp_dice_fwd_workspace_bytes(int N, int C, int64_t Vo);
+int64_t da_warp_dice_bwd_workspace_bytes(int N, int64_t Vs);
+int da_warp_dice_sums_fwd(const float* prob, const float* field, int add_identity, const void* labels, int label_kind,
+                          int N, int C, int D, int H, int W, int Do, int Ho, int Wo, float* sums, void* workspace,
+                          int64_t workspace_bytes, da_stream_t stream);
+int da_warp_dice_sums_bwd(const float* prob, const float* field, int add_identity, const void* labels, int label_kind,
+                          const float* gS, const float* gI, int N, int C, int D, int H, int W, int Do, int Ho, int Wo,
+                          float* grad_prob, float* grad_field, void* workspace, int64_t workspace_bytes,
+                          da_stream_t stream);
+
 /* channel softmax (F.softmax(dim=1)) materialised for the anatomy branch, where probabilities are warped */
 int da_softmax_fwd(const float* x, float* y, int N, int C, int64_t V, da_stream_t stream);
 int da_softmax_bwd(const float* y, const float* dy, float* dx, int N, int C, int64_t V, da_stream_t stream);

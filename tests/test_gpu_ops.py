@@ -293,3 +293,28 @@ def test_deconv_k2s2(cuda, Cin, Cout, size):
     b = torch.randn(Cout, generator=g) * 0.1
     res = _run_both(lambda a, ww, bb: ops.deconv_k2s2(a, ww, bb), lambda a, ww, bb: F.conv_transpose3d(a, ww, bb, stride=2), [x, w, b], cuda)
     _check(*res, what="deconv_k2s2")
+
+
+@pytest.mark.parametrize("C,size,dtype", [(4, (9, 10, 12), torch.uint8), (32, (8, 12, 16), torch.int64), (6, (7, 9, 11), torch.uint8)])
+def test_warped_dice_fused_vs_oracle(cuda, C, size, dtype):
+    """The fused anatomy term against the oracle's grid_sample + Dice, all three weightings, values and both gradients."""
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    g = _g()
+    prob = torch.softmax(torch.randn((2, C) + size, generator=g), 1)
+    phi = P.identity_transform(size)[None] + torch.randn((2, 3) + size, generator=g) * 0.3
+    lab = torch.randint(0, C, (2,) + size, generator=g).to(dtype)
+    for wt in ("Uniform", "Simple", "Volume"):
+        crit = da.get_loss_function("dice")(n_class=C, weight_type=wt, softmax=False, eps=1e-6)
+        pg, fg = prob.to(cuda).requires_grad_(True), phi.to(cuda).requires_grad_(True)
+        loss = crit.forward_warped(pg, fg, lab.to(cuda))
+        loss.backward()
+        pc, fc = prob.clone().requires_grad_(True), phi.clone().requires_grad_(True)
+        ref = P.dice_multiclass(P.warp(pc, fc), lab.long(), C, wt, False, False, 1e-6)
+        ref.backward()
+        assert rel_err(loss, ref) < TOL, wt
+        assert rel_err(pg.grad, pc.grad) < TOL and rel_err(fg.grad, fc.grad) < TOL, wt
+        # and against the unfused CUDA path (warp3d + dice_sums)
+        p2, f2 = prob.to(cuda).requires_grad_(True), phi.to(cuda).requires_grad_(True)
+        crit(da.ops.warp3d(p2, f2), lab.to(cuda)).backward()
+        assert rel_err(pg.grad, p2.grad) < TOL and rel_err(fg.grad, f2.grad) < TOL
