@@ -47,6 +47,7 @@ SIGNATURES = {
     "da_bending_fwd": ("piiiippls", "rc"),
     "da_bending_bwd": ("ppiiiippls", "rc"),
     # conv
+    "da_umma_debug_read": ("p", "rc"),
     "da_set_conv_impl": ("i", "rc"),
     "da_conv3d_pack_bytes": ("iii", "size"),
     "da_conv3d_wgrad_workspace_bytes": ("iii", "size"),

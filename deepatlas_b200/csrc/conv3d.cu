@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restr
 }
 
 #include "conv3d_tma.inc.cuh"
+#include "conv3d_umma.inc.cuh"
 
 // out[i] = sum_r partials[r][i]  (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
@@ -832,6 +833,80 @@ int run_conv_tma(const float* x1, const float* x2, const float* weight, float* w
   return launch_fwd_tma<4>(x1, x2, wp, bias, out, g, cin_pad, stream);
 }
 
+// ---- tensor-core (tcgen05 3xTF32) path: opt-in with DA_CONV_UMMA=1 until it is the default ----------------------
+int g_use_umma = -1;
+inline bool umma_enabled() {
+  if (g_use_umma < 0) {
+    const char* e = getenv("DA_CONV_UMMA");
+    g_use_umma = (e && strcmp(e, "1") == 0) ? 1 : 0;
+  }
+  return g_use_umma == 1;
+}
+constexpr int64_t UMMA_IMG_BYTES = UmmaCfg::W_BYTES;  // 92160
+inline bool fwd_umma_ok(const ConvGeom& g) {
+  return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 &&
+         (int64_t)g.Do * g.Ho * g.Wo >= 32768;
+}
+inline int64_t umma_workspace_bytes(int Cin, int Cout) {
+  return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + UM_KC - 1) / UM_KC) * UMMA_IMG_BYTES + 256;
+}
+
+unsigned long long* g_umma_dbg = nullptr;
+inline unsigned long long* umma_dbg_buffer() {
+  static int want = -1;
+  if (want < 0) {
+    const char* e = getenv("DA_UMMA_DEBUG");
+    want = (e && strcmp(e, "1") == 0) ? 1 : 0;
+    if (want && cudaMalloc(&g_umma_dbg, 16 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(g_umma_dbg, 0, 16 * sizeof(unsigned long long));
+  }
+  return g_umma_dbg;
+}
+
+int launch_umma(const UmmaArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
+    configured = true;
+  }
+  dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N);
+  conv3d_umma_kernel<<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+  return da_check_launch("conv3d_umma");
+}
+
+// weight source indexing arguments as for repack(); wp must hold umma_workspace_bytes(Cin, Cout)
+int run_conv_umma(const float* x1, const float* x2, const float* weight, float* wp, const float* bias, float* out, const ConvGeom& g,
+                  int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
+  const int Cin = g.C1 + g.C2;
+  constexpr int CB = UM_CB, KC = UM_KC;
+  const int nco = (g.Cout + CB - 1) / CB, nk = (Cin + KC - 1) / KC;
+  for (int ib = 0; ib < nco; ++ib)
+    for (int ik = 0; ik < nk; ++ik) {
+      float* img = wp + (int64_t)(ib * nk + ik) * (UMMA_IMG_BYTES / 4);
+      umma_prep_weights_kernel<<<45, 256, 0, stream>>>(weight, img, d1, a_is_dim0, flip, Cin, ik * KC, g.Cout, b_off, ib * CB);
+    }
+  int rc = da_check_launch("umma_prep_weights", nco * nk);
+  if (rc) return rc;
+  UmmaArgs a;
+  a.dbg = umma_dbg_buffer();
+  a.x1 = x1; a.x2 = x2; a.C1 = g.C1; a.C2 = g.C2; a.bias = bias; a.out = out;
+  a.N = g.N; a.D = g.Do; a.H = g.Ho; a.W = g.Wo; a.Cout = g.Cout;
+  a.act = g.act; a.slope = g.slope;
+  a.tiles_x = (g.Wo + UM_TX - 1) / UM_TX; a.tiles_y = (g.Ho + UM_TY - 1) / UM_TY;
+  // planes per CTA: enough CTAs for ~4 waves, at least 8 planes to amortise the two-plane pipeline fill
+  int zg = g.Do;
+  const int xy = a.tiles_x * a.tiles_y * g.N;
+  while (zg > 8 && (int64_t)xy * ((g.Do + zg - 1) / zg) < 4 * DA_NUM_SMS) zg = (zg + 1) / 2;
+  a.zg = zg;
+  for (int ib = 0; ib < nco; ++ib)
+    for (int ik = 0; ik < nk; ++ik) {
+      a.wimg = wp + (int64_t)(ib * nk + ik) * (UMMA_IMG_BYTES / 4);
+      a.c0 = ik * KC; a.co0 = ib * CB; a.accumulate = ik > 0; a.last = ik == nk - 1;
+      rc = launch_umma(a, stream);
+      if (rc) return rc;
+    }
+  return DA_OK;
+}
+
 int run_conv(const float* x1, const float* x2, const float* wp, const float* bias, float* out, const ConvGeom& g, int KS,
              cudaStream_t stream) {
   if (KS == 1) return launch_direct<1>(x1, x2, wp, bias, out, g, stream);
@@ -896,6 +971,21 @@ da_encode_tiled_fn da_get_encode_tiled() {
   return fn;
 }
 
+// Debug aid (DA_UMMA_DEBUG=1): cycle counters accumulated by the MMA-issuing warps of conv3d_umma_kernel since the last
+// call: out[0..8] = MMA warp: waiting for a free accumulator, for input planes, issuing, total, plane steps, CTAs;
+// epilogue warp 0: waiting for the MMAs, TMEM read + clear, total.
+DA_API int da_umma_debug_read(int64_t* out6) {
+  DA_REQUIRE(out6, "da_umma_debug_read: null pointer");
+  for (int i = 0; i < 9; ++i) out6[i] = 0;
+  if (!g_umma_dbg) return DA_OK;
+  unsigned long long h[16];
+  cudaError_t e = cudaMemcpy(h, g_umma_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemset(g_umma_dbg, 0, sizeof(h));
+  if (e != cudaSuccess) { da_set_error("da_umma_debug_read: %s", cudaGetErrorString(e)); return (int)e; }
+  for (int i = 0; i < 9; ++i) out6[i] = (int64_t)h[i];
+  return DA_OK;
+}
+
 // Kernel selection for k3 s1 p1 convolutions: 0 = automatic (tiled where it applies), 1 = always the generic
 // direct kernel (used by the parity tests to cross-check the two implementations).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
@@ -908,7 +998,9 @@ DA_API int da_set_conv_impl(int impl) {
 // workspace for da_conv3d_fwd / da_conv3d_dgrad: one packed weight copy
 DA_API int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks) {
   const int m = Cin > Cout ? Cin : Cout;
-  return (int64_t)sizeof(float) * (int64_t)(m + 3) * ks * ks * ks * cpad(m) + 256;
+  const int64_t base = (int64_t)sizeof(float) * (int64_t)(m + 3) * ks * ks * ks * cpad(m) + 256;
+  const int64_t um = ks == 3 ? umma_workspace_bytes(m, m) : 0;
+  return base > um ? base : um;
 }
 DA_API int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
   const int64_t count = (int64_t)Cin * Cout * ks * ks * ks;
@@ -933,6 +1025,9 @@ DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const
   ConvGeom g{N, C1, C2, Di, Hi, Wi, conv_out(Di, ks, stride, pad), conv_out(Hi, ks, stride, pad), conv_out(Wi, ks, stride, pad),
              Cout, cpad(Cout), stride, pad, act, slope};
   float* wp = (float*)workspace;
+  if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
+    return transposed ? run_conv_umma(x1, x2, weight, wp, bias, out, g, Cout, 1, 1, 0, stream)
+                      : run_conv_umma(x1, x2, weight, wp, bias, out, g, Cin, 0, 0, 0, stream);
   if (ks == 3 && aligned16(wp) && fwd_tma_ok(x1, x2, out, g))
     return transposed ? run_conv_tma(x1, x2, weight, wp, bias, out, g, Cin, Cout, 1, 1, 0, stream)
                       : run_conv_tma(x1, x2, weight, wp, bias, out, g, Cout, Cin, 0, 0, 0, stream);
@@ -959,6 +1054,9 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
     // dgrad = conv of dy (Cout channels) with [co][flip tap][ci]; for a transposed layer: no flip, dims swapped
     ConvGeom g{N, Cout, 0, Do, Ho, Wo, Di, Hi, Wi, Cdx, Cp, 1, ks == 3 ? 1 : 0, 0, 0.f};
     DA_REQUIRE(ks == 1 || pad == 1, "da_conv3d_dgrad: k3 needs pad 1");
+    if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
+      return transposed ? run_conv_umma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, 0, 0, ci_off, stream)
+                        : run_conv_umma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
     if (ks == 3 && aligned16(wp) && fwd_tma_ok(dy, nullptr, dx, g))
       return transposed ? run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, Cout, 0, 0, ci_off, stream)
                         : run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, Cin_total, 1, 1, ci_off, stream);

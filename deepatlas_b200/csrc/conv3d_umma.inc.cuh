@@ -1,0 +1,369 @@
+// Tensor-core (tcgen05, 3xTF32) variant of the k3 s1 p1 convolution forward / data gradient.
+// Included by conv3d.cu inside its anonymous namespace.
+//
+// Implicit GEMM, output-stationary in TMEM:
+//   D[f][(kx,co)] = sum_{kz,ky,ci} X[ci][plane zo+kz-1][f + (ky-1)*PX] * W[co][ci][kz][ky][kx]      f = in-plane position
+//   Y[co][q]      = D[q-1][(0,co)] + D[q][(1,co)] + D[q+1][(2,co)]                                 (kx fold in the epilogue)
+// * M = 128 positions per MMA: consecutive positions of a (TY+2) x PX plane tile flattened row-major, so a (ky) shift
+//   is just a start-address offset of +-PX rows in the A descriptor (un-swizzled K-major canonical layout
+//   [ci/4][position][4 floats]; measured to work, tools/probes/umma_probe.cu) and kz selects one of three ring slots.
+// * N = 144 = 3 planes x 3 kx x 16 co.  One tcgen05.mma costs >= 97 cycles regardless of N <= 128 (shared-memory A-read
+//   floor, same probe), so as many taps as possible are folded into N: kx (resolved in the epilogue) and kz.  The kz fold
+//   makes the accumulator three rotating 48-column blocks: input plane p adds its kz = 0/1/2 contribution to the blocks
+//   of output planes p+1, p, p-1 with ONE instruction, because the weight rows are stored in kz order 2,1,0,2,1 and the
+//   B descriptor starts at the rotation the step needs.  After step p the block of output plane p-1 is complete: the
+//   epilogue reads it, zeroes it (tcgen05.st) and hands it back.  36 MMAs per plane instead of 108.
+// * fp32 accuracy from three TF32 MMAs per K step: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with hi = x & 0xffffe000 (the unit
+//   truncates), lo = x - hi, both computed by the producer warps while they restage the planar input.
+// * z streaming: a CTA owns a TY x TX column and walks ZG output planes; each input plane is staged once (3-slot ring,
+//   only the current plane is read by a step, so the producers run two planes ahead).
+// Warp roles: 0-7 epilogue (M tile w/4, TMEM lane quadrant w%4), 8 MMA issue + TMEM allocation, 9-16 producers.
+// Channel blocking: 16 output x 16 input channels per launch; further input-channel chunks accumulate into the output
+// in global memory (bias / activation applied by the last chunk), further output blocks are separate launches.
+
+constexpr int UM_TX = 40, UM_TY = 5;
+constexpr int UM_PX = 48;                      // row pitch in positions: TX + 2 halo columns, padded so that a (ky) shift of the A start
+                                               // address is a multiple of 128 bytes (8 rows) -- misaligned starts halve the MMA rate
+constexpr int UM_PLANE = (UM_TY + 2) * UM_PX;  // 336 positions staged per plane
+constexpr int UM_PFA = 352;                    // allocated positions per channel chunk (>= 2*128 + 2*PX)
+constexpr int UM_MT = 2;                       // M tiles per plane (2*128 >= TY*PX = 240)
+constexpr int UM_NPROD = 224;                  // producer threads (7 warps): 512 threads in total -> 128 registers each
+constexpr int UM_NEPI = 256;                   // epilogue threads: warp w handles M tile w/4, TMEM lane quadrant w%4
+constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-7 epilogue, 8 MMA issue, 9.. producers
+constexpr int UM_CB = 16, UM_KC = 16;          // output channels per launch, input channels per launch
+constexpr int UM_NB = 3 * UM_CB;               // columns of one accumulator block: (kx, co)
+constexpr int UM_N = 3 * UM_NB;                // MMA N: three blocks = three output planes in flight
+constexpr int UM_NCH = UM_KC / 4;
+constexpr int UM_WROWS = 5 * UM_NB;            // weight rows: kz blocks in the order 2,1,0,2,1 (any cyclic rotation is contiguous)
+static_assert(UM_MT * 128 + 2 * UM_PX <= UM_PFA, "shifted A rows must stay inside the slot");
+static_assert(UM_PX % 8 == 0 && UM_PX >= UM_TX + 2, "row pitch");
+static_assert(UM_MT * 128 >= UM_TY * UM_PX, "M tiles must cover the output rows");
+
+struct UmmaCfg {
+  static constexpr int SLOT_FLOATS = 2 * UM_NCH * UM_PFA * 4;        // hi + lo
+  static constexpr int RING_BYTES = 3 * SLOT_FLOATS * 4;
+  static constexpr int W_FLOATS = 2 * 3 * UM_NCH * UM_WROWS * 4;     // [hi|lo][ky][ci/4][row][4]
+  static constexpr int W_BYTES = W_FLOATS * 4;
+  static constexpr int EDGE_BYTES = 2 * 8 * 2 * 16 * 4;
+  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + EDGE_BYTES + 128;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(UM_MT * UM_N <= 512, "accumulators exceed TMEM");
+};
+
+struct UmmaArgs {
+  const float* x1; const float* x2; int C1, C2;
+  const float* wimg;          // prepared weight image for this (co block, channel chunk)
+  const float* bias; float* out;
+  int N, D, H, W, Cout;
+  int c0, co0;                // first input channel of this chunk, first output channel of this block
+  int accumulate, last;       // add to the existing output; apply bias + activation
+  int act; float slope;
+  int tiles_x, tiles_y, zg;   // z planes per CTA
+  unsigned long long* dbg;    // optional cycle counters of the MMA warp (DA_UMMA_DEBUG=1): acc wait, plane wait, issue, total, steps
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// descriptor with the constant fields (LBO, SBO, version) pre-assembled: only the 14-bit start address changes per MMA
+__device__ __forceinline__ uint64_t umma_desc_at(uint64_t base_no_addr, uint32_t saddr) {
+  return base_no_addr | (uint64_t)((saddr >> 4) & 0x3fff);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) {
+  using Cfg = UmmaCfg;
+  constexpr int N = UM_N, NCH = UM_NCH, NB = UM_NB;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t plane_full[3], plane_empty[3], acc_full[UM_MT], acc_empty[UM_MT];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  float* ring = reinterpret_cast<float*>(smem);
+  float* sw = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);
+  float* edge = reinterpret_cast<float*>(smem + Cfg::RING_BYTES + Cfg::W_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int tb = blockIdx.x;
+  const int bx = tb % a.tiles_x, by = tb / a.tiles_x;
+  const int X0 = bx * UM_TX, Y0 = by * UM_TY;
+  const int z0 = blockIdx.y * a.zg;
+  const int zcount = min(a.zg, a.D - z0);
+  const int nsteps = zcount + 2;  // input planes z0-1 .. z0+zcount
+  const int n = blockIdx.z;
+  const int64_t HW = (int64_t)a.H * a.W, V = HW * a.D;
+
+  // ---- one-time setup: barriers, weights, zero the ring tails, TMEM (allocated, then zeroed by the epilogue warps) --
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], UM_NPROD); mbar_init(&plane_empty[i], 1); }
+    for (int i = 0; i < UM_MT; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], UM_NEPI / UM_MT); }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < Cfg::W_FLOATS / 4; i += UM_THREADS)
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(a.wimg) + i);
+  // rows UM_PLANE .. UM_PFA of every chunk are only read by discarded accumulator rows; zero them once (no NaN patterns)
+  for (int i = threadIdx.x; i < 3 * 2 * NCH * (UM_PFA - UM_PLANE); i += UM_THREADS) {
+    const int t = i % (UM_PFA - UM_PLANE), c = i / (UM_PFA - UM_PLANE);
+    reinterpret_cast<float4*>(ring)[c * UM_PFA + UM_PLANE + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (warp < 8) {  // every MMA accumulates: the rotating blocks start from zero
+    const uint32_t t0 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * N);
+#pragma unroll
+    for (int c = 0; c < N; c += 16) tmem_st16_zero(t0 + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp >= 9) {
+    // =============================== producers ===============================
+    // thread = one 4-channel chunk (grp) x UM_PPT fixed in-plane positions: everything but the plane offset is loop invariant
+    constexpr int TPG = UM_NPROD / NCH;          // 56 threads per channel chunk
+    constexpr int PPT = UM_PLANE / TPG;          // 6 positions per thread
+    static_assert(TPG * NCH == UM_NPROD && PPT * TPG == UM_PLANE, "producer mapping must tile the plane exactly");
+    const int tp = threadIdx.x - (UM_NEPI + 32);
+    const int grp = tp / TPG, ti = tp - grp * TPG;
+    const int cend = min(a.c0 + UM_KC, a.C1 + a.C2);
+    const float* cb[4];
+    bool cok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = a.c0 + 4 * grp + e;
+      cok[e] = c < cend;
+      cb[e] = !cok[e] ? a.x1 : ((c < a.C1) ? a.x1 + ((int64_t)n * a.C1 + c) * V : a.x2 + ((int64_t)n * a.C2 + (c - a.C1)) * V);
+    }
+    int oxy[PPT];
+#pragma unroll
+    for (int b = 0; b < PPT; ++b) {
+      const int f = ti + TPG * b;
+      const int hy = f / UM_PX, hx = f - hy * UM_PX;
+      const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
+      oxy[b] = (hx < UM_TX + 2 && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? gy * a.W + gx : -1;
+    }
+    for (int pi = 0; pi < nsteps; ++pi) {
+      const int slot = pi % 3, use = pi / 3;
+      if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
+      const int zi = z0 - 1 + pi;
+      float4* shi = reinterpret_cast<float4*>(ring + slot * Cfg::SLOT_FLOATS) + grp * UM_PFA;
+      float4* slo = shi + NCH * UM_PFA;
+      const bool zok = zi >= 0 && zi < a.D;
+      const int64_t zoff = (int64_t)zi * HW;
+      float v[PPT][4];
+#pragma unroll
+      for (int b = 0; b < PPT; ++b)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[b][e] = (zok && oxy[b] >= 0 && cok[e]) ? __ldg(cb[e] + zoff + oxy[b]) : 0.f;
+#pragma unroll
+      for (int b = 0; b < PPT; ++b) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __uint_as_float(__float_as_uint(v[b][e]) & 0xffffe000u);
+          l[e] = v[b][e] - h[e];
+        }
+        shi[ti + TPG * b] = make_float4(h[0], h[1], h[2], h[3]);
+        slo[ti + TPG * b] = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      mbar_arrive(&plane_full[slot]);
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issue ===============================
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t ring_s = smem_u32(ring), sw_s = smem_u32(sw);
+    constexpr uint32_t A_LBO = UM_PFA * 16, B_LBO = UM_WROWS * 16;
+    const uint64_t adesc0 = umma_desc(0, A_LBO, 128), bdesc0 = umma_desc(0, B_LBO, 128);
+    long long t_acc = 0, t_plane = 0, t_issue = 0;
+    const long long t_begin = clock64();
+    for (int pi = 0; pi < nsteps; ++pi) {
+      const long long t0 = clock64();
+      mbar_wait(&plane_full[pi % 3], (pi / 3) & 1);
+      const long long t1 = clock64();
+      t_plane += t1 - t0;
+      const uint32_t slot_s = ring_s + (uint32_t)(pi % 3) * (Cfg::SLOT_FLOATS * 4);
+      const uint32_t brot = sw_s + (uint32_t)(2 - pi % 3) * (NB * 16);  // block b of this step holds kz = (pi - b) mod 3
+#pragma unroll 1
+      for (int mt = 0; mt < UM_MT; ++mt) {
+        const long long t2 = clock64();
+        if (pi > 0) mbar_wait(&acc_empty[mt], (pi - 1) & 1);  // the epilogue has read + zeroed the block finished by step pi-1
+        t_acc += clock64() - t2;
+        tc_fence_after();
+        if (elected) {
+          const uint32_t dcol = tmem + (uint32_t)mt * N;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t arow = slot_s + (uint32_t)(mt * 128 + ky * UM_PX) * 16;  // (PX + mt*128) + (ky-1)*PX
+            const uint32_t wt = brot + (uint32_t)(ky * NCH * UM_WROWS) * 16;
+#pragma unroll
+            for (int j2 = 0; j2 < UM_KC / 8; ++j2) {
+              const uint64_t a_hi = umma_desc_at(adesc0, arow + (uint32_t)(2 * j2) * A_LBO);
+              const uint64_t a_lo = umma_desc_at(adesc0, arow + (uint32_t)(2 * j2) * A_LBO + NCH * UM_PFA * 16);
+              const uint64_t b_hi = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO);
+              const uint64_t b_lo = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO + 3 * NCH * UM_WROWS * 16);
+              umma_tf32(dcol, a_hi, b_hi, idesc, 1u);
+              umma_tf32(dcol, a_lo, b_hi, idesc, 1u);
+              umma_tf32(dcol, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          umma_commit(&acc_full[mt]);
+          if (mt == UM_MT - 1) umma_commit(&plane_empty[pi % 3]);
+        }
+        __syncwarp();
+      }
+      t_issue += clock64() - t1;
+    }
+    if (a.dbg && lane == 0) {
+      atomicAdd(a.dbg + 0, (unsigned long long)t_acc); atomicAdd(a.dbg + 1, (unsigned long long)t_plane);
+      atomicAdd(a.dbg + 2, (unsigned long long)t_issue); atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - t_begin));
+      atomicAdd(a.dbg + 4, (unsigned long long)nsteps); atomicAdd(a.dbg + 5, 1ull);
+    }
+  } else {
+    // =============================== epilogue ===============================
+    static_assert(UM_MT == 2 && UM_NEPI == 256, "one epilogue warp per (M tile, lane quadrant)");
+    const int w = warp & 3, mt = warp >> 2, wg = warp;  // wg = mt*4 + w: rows [32*wg, 32*wg + 32) of the 256-row range
+    const int fc = UM_PX + wg * 32 + lane;
+    const int hy = fc / UM_PX, hx = fc - hy * UM_PX;
+    const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
+    const bool valid = hx >= 1 && hx <= UM_TX && hy <= UM_TY && gy < a.H && gx < a.W;
+    const uint32_t trow = tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)mt * N;
+    long long e_wait = 0, e_tmem = 0;
+    const long long e_begin = clock64();
+    for (int pi = 0; pi < nsteps; ++pi) {
+      const int ol = pi - 2;                 // output plane completed by this step (local index), if >= 0
+      const int blk = (pi + 1) % 3;          // = (pi - 2) mod 3
+      const bool live = ol >= 0;             // ol < zcount always (nsteps = zcount + 2)
+      float* op = a.out + ((int64_t)n * a.Cout + a.co0) * V + (int64_t)(z0 + ol) * HW + (int64_t)gy * a.W + gx;
+      // the previous chunks' partial output does not depend on this step's MMAs: fetch it before waiting for them
+      float old[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) old[c] = (a.accumulate && live && valid && a.co0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
+      const long long e0 = clock64();
+      mbar_wait(&acc_full[mt], pi & 1);
+      const long long e1 = clock64();
+      tc_fence_after();
+      float v[3][16];
+      if (live) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) tmem_ld16(trow + (uint32_t)(blk * NB + kx * UM_CB), v[kx]);
+        tmem_ld_wait();
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) tmem_st16_zero(trow + (uint32_t)(blk * NB + kx * UM_CB));
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[mt]);  // block read and cleared: the next step may accumulate into it
+      e_wait += e1 - e0; e_tmem += clock64() - e1;
+      if (!live) continue;          // uniform over the CTA
+      // kx fold needs row f-1 (tap 0) and f+1 (tap 2): neighbours by shuffle, warp edges through shared memory
+      float* eb = edge + (pi & 1) * (8 * 2 * 16);
+      if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) eb[(wg * 2 + 0) * 16 + c] = v[0][c];
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) eb[(wg * 2 + 1) * 16 + c] = v[2][c];
+      }
+      named_bar_sync(1, UM_NEPI);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float left = __shfl_up_sync(0xffffffffu, v[0][c], 1);
+        float right = __shfl_down_sync(0xffffffffu, v[2][c], 1);
+        if (lane == 0) left = (wg > 0) ? eb[((wg - 1) * 2 + 0) * 16 + c] : 0.f;
+        if (lane == 31) right = (wg < 7) ? eb[((wg + 1) * 2 + 1) * 16 + c] : 0.f;
+        float r = v[1][c] + left + right + old[c];
+        const int co = a.co0 + c;
+        if (valid && co < a.Cout) {
+          if (a.last) {
+            if (a.bias) r += a.bias[co];
+            if (a.act) r = r > 0.f ? r : r * a.slope;
+          }
+          op[(int64_t)c * V] = r;
+        }
+      }
+    }
+    if (a.dbg && threadIdx.x == 0) {
+      atomicAdd(a.dbg + 6, (unsigned long long)e_wait); atomicAdd(a.dbg + 7, (unsigned long long)e_tmem);
+      atomicAdd(a.dbg + 8, (unsigned long long)(clock64() - e_begin));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
+}
+
+// Weight image of one (16-output-channel block, 16-input-channel chunk):
+//   [hi|lo][ky][ci/4][row = t*48 + kx*16 + co][4 floats],  t = 0..4 <-> kz = 2,1,0,2,1.
+// Source indexing as repack_weights_kernel (a = this conv's input channel, b = its output channel).
+__global__ void umma_prep_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int d1, int a_is_dim0, int flip,
+                                         int A, int c0, int B, int b_off, int co0) {
+  const int total = UmmaCfg::W_FLOATS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 3;
+    int r = i >> 2;
+    const int row = r % UM_WROWS; r /= UM_WROWS;
+    const int j = r % UM_NCH; r /= UM_NCH;
+    const int ky = r % 3;
+    const int s = r / 3;
+    const int t = row / UM_NB, kx = (row % UM_NB) / UM_CB, b = co0 + row % UM_CB, ai = c0 + 4 * j + e;
+    const int kz = (t == 0 || t == 3) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
+    float v = 0.f;
+    if (ai < A && ai < c0 + UM_KC && b < B) {
+      const int tap = (kz * 3 + ky) * 3 + kx;
+      const int ts = flip ? (26 - tap) : tap;
+      const int i0 = a_is_dim0 ? ai : (b + b_off);
+      const int i1 = a_is_dim0 ? (b + b_off) : ai;
+      v = src[((int64_t)i0 * d1 + i1) * 27 + ts];
+    }
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    dst[i] = s ? (v - hi) : hi;
+  }
+}

@@ -182,6 +182,8 @@ CONV_CASES = [
     (8, 6, 8, 3, 1, (32, 36, 32), False),       # TMA path, two sources, second one partial
     (32, 16, 16, 3, 1, (8, 64, 160), False),    # full-width rows of the benchmark volume (decBlock2.0 channels)
     (64, 64, 64, 3, 1, (20, 24, 20), False),    # deepest decoder level of UNet_light at the benchmark size
+    (16, 0, 32, 3, 1, (32, 32, 40), False),     # 32-channel output blocks (tensor-core path: CB = 32, KC = 8)
+    (24, 0, 48, 3, 1, (30, 33, 44), False),     # ragged everything: partial channel chunk / block, odd extents
 ]
 
 

@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(128) check_kernel(const float* A, const float*
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tm) : "memory");
 }
 
-__global__ void __launch_bounds__(128) rate_kernel(int N, int reps, int nbuf, int nacc, long long* cycles, int* status) {
+__global__ void __launch_bounds__(128) rate_kernel(int N, int reps, int nbuf, int nacc, int albo, int blbo, int nbbuf, long long* cycles, int* status) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base;
   float* s = reinterpret_cast<float*>(smem);
-  const int total = nbuf * (2 * 144 * 4) + 2 * 256 * 4 + 64;
+  const int total = (nbuf * 2 * albo + nbbuf * 2 * blbo) / 4 + 64;
   for (int i = threadIdx.x; i < total; i += blockDim.x) s[i] = (float)((i * 37) % 17) * 0.125f;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -130,14 +130,15 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int reps, int nbuf, in
   const uint32_t tm = tmem_base;
   if (warp == 0) {   // warp-uniform branch: descriptors are uniform values, one elected lane issues (CUTLASS pattern)
     const uint32_t idesc = make_idesc(128, N);
-    const uint32_t a0 = smem_u32(s), b0 = a0 + nbuf * (2 * 144 * 16);
+    const uint32_t a0 = smem_u32(s), b0 = a0 + nbuf * (2 * albo);
     uint32_t elected;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
     const long long t0 = clock64();
-    int ib = 0, ish = 0, iacc = 0;
+    int ib = 0, ish = 0, iacc = 0, ibb = 0;
     for (int r = 0; r < reps; ++r) {
-      const uint64_t ad = make_desc(a0 + ib * (2 * 144 * 16) + ish * 16, 144 * 16, 128);  // rotating A buffers, shifted starts
-      const uint64_t bd = make_desc(b0, 256 * 16, 128);
+      const uint64_t ad = make_desc(a0 + ib * (2 * albo) + ish * 16, albo, 128);  // rotating A buffers, shifted starts
+      const uint64_t bd = make_desc(b0 + ibb * (2 * blbo), blbo, 128);  // rotating B buffers: defeats any operand reuse
+      if (++ibb == nbbuf) ibb = 0;
       if (elected) umma_tf32(tm + iacc * N, ad, bd, idesc, r >= nacc);
       if (++ib == nbuf) ib = 0;
       if (++ish == 3) ish = 0;
@@ -190,16 +191,16 @@ int main(int argc, char** argv) {
     printf("check N=%d shift=%d: max|D|=%.3f err vs exact %.3e, vs tf32-truncated inputs %.3e, vs tf32-rounded inputs %.3e\n", N, shift, mx, e_exact, e_trunc, e_round);
     return 0;
   }
-  const int N = atoi(argv[2]), reps = atoi(argv[3]), nbuf = argc > 4 ? atoi(argv[4]) : 8, nacc = argc > 5 ? atoi(argv[5]) : 1;
+  const int N = atoi(argv[2]), reps = atoi(argv[3]), nbuf = argc > 4 ? atoi(argv[4]) : 8, nacc = argc > 5 ? atoi(argv[5]) : 1, albo = argc > 6 ? atoi(argv[6]) : 2304, blbo = argc > 7 ? atoi(argv[7]) : 4096, nbbuf = argc > 8 ? atoi(argv[8]) : 1;
   long long* cyc; cudaMalloc(&cyc, 148 * 8);
-  const int smem = (nbuf * (2 * 144 * 4) + 2 * 256 * 4 + 64) * 4;
+  const int smem = nbuf * 2 * albo + nbbuf * 2 * blbo + 256;
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int it = 0; it < 2; ++it) rate_kernel<<<148, 128, smem>>>(N, reps, nbuf, nacc, cyc, status);
+  for (int it = 0; it < 2; ++it) rate_kernel<<<148, 128, smem>>>(N, reps, nbuf, nacc, albo, blbo, nbbuf, cyc, status);
   cudaError_t e = cudaDeviceSynchronize();
   int st = 0; cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost);
   std::vector<long long> h(148); cudaMemcpy(h.data(), cyc, 148 * 8, cudaMemcpyDeviceToHost);
   long long mn = h[0], mxc = h[0]; for (auto v : h) { mn = v < mn ? v : mn; mxc = v > mxc ? v : mxc; }
-  printf("rate N=%d reps=%d nbuf=%d nacc=%d: %s status %d; cycles/MMA min %.2f max %.2f (floor 128*N/256 = %.1f; A bytes/MMA 4096 -> %.1f B/cycle)\n", N, reps, nbuf, nacc,
+  printf("rate N=%d reps=%d nbuf=%d nacc=%d albo=%d blbo=%d nbbuf=%d: %s status %d; cycles/MMA min %.2f max %.2f (floor 128*N/256 = %.1f; A bytes/MMA 4096 -> %.1f B/cycle)\n", N, reps, nbuf, nacc, albo, blbo, nbbuf,
          cudaGetErrorString(e), st, (double)mn / reps, (double)mxc / reps, 128.0 * N / 256.0, 4096.0 / ((double)mn / reps));
   return 0;
 }

@@ -32,3 +32,13 @@ torch.cuda.synchronize()
 fl = 2.0 * 27 * (C1 + C2) * Cout * D * H * W
 print(f"shape {C1}+{C2}->{Cout} @{D}x{H}x{W}: fwd {ev[0].elapsed_time(ev[1]):.3f} ms ({fl / ev[0].elapsed_time(ev[1]) / 1e9:.1f} TFLOP/s), "
       f"bwd {ev[2].elapsed_time(ev[3]):.3f} ms ({2 * fl / ev[2].elapsed_time(ev[3]) / 1e9:.1f} TFLOP/s)")
+
+if os.environ.get("DA_UMMA_DEBUG") == "1":
+    import ctypes
+    from deepatlas_b200 import _lib
+    buf = (ctypes.c_int64 * 9)()
+    _lib.call("da_umma_debug_read", ctypes.cast(buf, ctypes.c_void_p))
+    acc, plane, issue, total, steps, ctas, ew, et, etot = list(buf)
+    if steps:
+        print(f"  umma MMA warp per plane step: wait-accumulator {acc / steps:.0f}, wait-planes {plane / steps:.0f}, issue {issue / steps:.0f}, "
+              f"total {total / steps:.0f} cycles; epilogue warp 0: wait-MMA {ew / steps:.0f}, tmem {et / steps:.0f}, total {etot / steps:.0f} ({steps} steps, {ctas} CTAs)")
