@@ -833,14 +833,15 @@ int run_conv_tma(const float* x1, const float* x2, const float* weight, float* w
   return launch_fwd_tma<4>(x1, x2, wp, bias, out, g, cin_pad, stream);
 }
 
-// ---- tensor-core (tcgen05 3xTF32) path: opt-in with DA_CONV_UMMA=1 until it is the default ----------------------
+// ---- tensor-core (tcgen05 3xTF32) path: the default for k3 s1 p1 forward / dgrad; DA_CONV_UMMA=0 or
+// da_set_conv_impl(2) select the exact-FFMA kernels instead ---------------------------------------------------------
 int g_use_umma = -1;
 inline bool umma_enabled() {
   if (g_use_umma < 0) {
     const char* e = getenv("DA_CONV_UMMA");
-    g_use_umma = (e && strcmp(e, "1") == 0) ? 1 : 0;
+    g_use_umma = (e && strcmp(e, "0") == 0) ? 0 : 1;
   }
-  return g_use_umma == 1;
+  return g_use_umma == 1 && g_force_direct != 2;
 }
 constexpr int64_t UMMA_IMG_BYTES = UmmaCfg::W_BYTES;  // 92160
 inline bool fwd_umma_ok(const ConvGeom& g) {
@@ -888,6 +889,7 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, float* 
   if (rc) return rc;
   UmmaArgs a;
   a.dbg = umma_dbg_buffer();
+  { static int fl = -1; if (fl < 0) { const char* e = getenv("DA_UMMA_FLAGS"); fl = e ? atoi(e) : 0; } a.flags = fl; }
   a.x1 = x1; a.x2 = x2; a.C1 = g.C1; a.C2 = g.C2; a.bias = bias; a.out = out;
   a.N = g.N; a.D = g.Do; a.H = g.Ho; a.W = g.Wo; a.Cout = g.Cout;
   a.act = g.act; a.slope = g.slope;
@@ -976,21 +978,22 @@ da_encode_tiled_fn da_get_encode_tiled() {
 // epilogue warp 0: waiting for the MMAs, TMEM read + clear, total.
 DA_API int da_umma_debug_read(int64_t* out6) {
   DA_REQUIRE(out6, "da_umma_debug_read: null pointer");
-  for (int i = 0; i < 9; ++i) out6[i] = 0;
+  for (int i = 0; i < 11; ++i) out6[i] = 0;
   if (!g_umma_dbg) return DA_OK;
   unsigned long long h[16];
   cudaError_t e = cudaMemcpy(h, g_umma_dbg, sizeof(h), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemset(g_umma_dbg, 0, sizeof(h));
   if (e != cudaSuccess) { da_set_error("da_umma_debug_read: %s", cudaGetErrorString(e)); return (int)e; }
-  for (int i = 0; i < 9; ++i) out6[i] = (int64_t)h[i];
+  for (int i = 0; i < 11; ++i) out6[i] = (int64_t)h[i];
   return DA_OK;
 }
 
-// Kernel selection for k3 s1 p1 convolutions: 0 = automatic (tiled where it applies), 1 = always the generic
-// direct kernel (used by the parity tests to cross-check the two implementations).  Also settable through the
+// Kernel selection for k3 s1 p1 convolutions: 0 = automatic (tcgen05 3xTF32 forward/dgrad + TMA-staged FFMA weight
+// gradient where they apply), 1 = always the generic direct kernels, 2 = tiled exact-FFMA kernels only (the parity
+// tests cross-check all three).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
 DA_API int da_set_conv_impl(int impl) {
-  DA_REQUIRE(impl == 0 || impl == 1, "da_set_conv_impl: impl must be 0 (auto) or 1 (direct)");
+  DA_REQUIRE(impl >= 0 && impl <= 2, "da_set_conv_impl: impl must be 0 (auto), 1 (direct) or 2 (tiled FFMA, no tensor cores)");
   g_force_direct = impl;
   return DA_OK;
 }

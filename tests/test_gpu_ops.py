@@ -188,12 +188,12 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", ["auto", "direct"])
+@pytest.mark.parametrize("impl", ["auto", "direct", "ffma"])
 @pytest.mark.parametrize("slope", [None, 0.0])
 def test_conv3d(cuda, case, impl, slope):
     from deepatlas_b200 import _lib, ops
     C1, C2, Cout, ks, stride, size, transposed = case
-    if impl == "direct" and slope is not None:
+    if impl != "auto" and slope is not None:
         pytest.skip("activation epilogue covered by the auto run")
     g = _g()
     x1 = torch.randn((2, C1) + size, generator=g)
@@ -229,7 +229,7 @@ def test_conv3d(cuda, case, impl, slope):
         return out
 
     ins = [x1] + ([x2] if C2 else []) + [w, b]
-    _lib.call("da_set_conv_impl", 1 if impl == "direct" else 0)
+    _lib.call("da_set_conv_impl", {"auto": 0, "direct": 1, "ffma": 2}[impl])
     try:
         res = _run_both(gpu, cpu, ins, cuda)
     finally:

@@ -36,9 +36,9 @@ print(f"shape {C1}+{C2}->{Cout} @{D}x{H}x{W}: fwd {ev[0].elapsed_time(ev[1]):.3f
 if os.environ.get("DA_UMMA_DEBUG") == "1":
     import ctypes
     from deepatlas_b200 import _lib
-    buf = (ctypes.c_int64 * 9)()
+    buf = (ctypes.c_int64 * 11)()
     _lib.call("da_umma_debug_read", ctypes.cast(buf, ctypes.c_void_p))
-    acc, plane, issue, total, steps, ctas, ew, et, etot = list(buf)
+    acc, plane, issue, total, steps, ctas, ew, et, etot, ebar, eout = list(buf)
     if steps:
         print(f"  umma MMA warp per plane step: wait-accumulator {acc / steps:.0f}, wait-planes {plane / steps:.0f}, issue {issue / steps:.0f}, "
-              f"total {total / steps:.0f} cycles; epilogue warp 0: wait-MMA {ew / steps:.0f}, tmem {et / steps:.0f}, total {etot / steps:.0f} ({steps} steps, {ctas} CTAs)")
+              f"total {total / steps:.0f} cycles; epilogue warp 0: wait-MMA {ew / steps:.0f}, tmem {et / steps:.0f}, edge-barrier {ebar / steps:.0f}, fold+store {eout / steps:.0f}, total {etot / steps:.0f} ({steps} steps, {ctas} CTAs)")
