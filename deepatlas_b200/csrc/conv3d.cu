@@ -1154,6 +1154,50 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
     }
     return rc;
   }
+  if (ks == 3 && stride == 2 && pad == 1 && !transposed && !force_direct() && !tma_disabled() && (Wi & 3) == 0 && (Wo & 3) == 0 &&
+      aligned16(x1) && aligned16(x2) && aligned16(dy)) {
+    // stride-2 encoder convolutions: TMA-staged tiled kernel over 2x4x32 OUTPUT tiles
+    const int tiles_x = (Wo + S2_TX - 1) / S2_TX, tiles_y = (Ho + S2_TY - 1) / S2_TY, tiles_z = (Do + S2_TZ - 1) / S2_TZ;
+    const int ntiles = N * tiles_x * tiles_y * tiles_z;
+    const int groups = ((Cin + WG_CI - 1) / WG_CI) * ((Cout + WG_CO - 1) / WG_CO);
+    int nregions = (4 * DA_NUM_SMS + groups / 2) / groups;
+    if (nregions > cap) nregions = cap;
+    if (nregions > ntiles) nregions = ntiles;
+    if (nregions < 1) nregions = 1;
+    const int tpr = (ntiles + nregions - 1) / nregions;
+    nregions = (ntiles + tpr - 1) / tpr;
+    float* bias_partials = grad_bias ? partials + (int64_t)nregions * count : nullptr;
+    static bool configured_s2 = false;
+    if (!configured_s2) {
+      cudaFuncSetAttribute(conv3d_wgrad_s2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_BYTES);
+      configured_s2 = true;
+    }
+    auto launch_s2 = [&](const float* xin, int C, int ci_off, float* bp) -> int {
+      WgTiledArgs a;
+      a.x = xin; a.dy = dy; a.partials = partials; a.bias_partials = bp;
+      a.N = N; a.C = C; a.ci_off = ci_off; a.Cin_total = Cin; a.Cout = Cout; a.co_off = 0;
+      a.region_stride = count; a.D = Do; a.H = Ho; a.W = Wo;
+      a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_z = tiles_z; a.tiles_per_region = tpr; a.ntiles = ntiles;
+      a.nCoB = (Cout + WG_CO - 1) / WG_CO;
+      CUtensorMap mx, mdy;
+      int r = da_make_volume_map(&mx, xin, N, C, Di, Hi, Wi, S2_HX, S2_HY, S2_HZ, WG_CI);
+      if (!r) r = da_make_volume_map(&mdy, dy, N, Cout, Do, Ho, Wo, S2_TX, S2_TY, S2_TZ, WG_CO);
+      if (r) return r;
+      dim3 grid(((C + WG_CI - 1) / WG_CI) * a.nCoB, nregions);
+      conv3d_wgrad_s2_tma_kernel<<<grid, WTM_THREADS, S2_SMEM_BYTES, stream>>>(mx, mdy, a);
+      return da_check_launch("conv3d_wgrad_s2_tma");
+    };
+    int rc = launch_s2(x1, C1, 0, bias_partials);
+    if (!rc && C2) rc = launch_s2(x2, C2, C1, nullptr);
+    if (rc) return rc;
+    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+    rc = da_check_launch("conv3d_wgrad_s2/reduce");
+    if (!rc && grad_bias) {
+      reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, nregions, Cout, grad_bias);
+      rc = da_check_launch("conv3d_wgrad_s2/bias-reduce");
+    }
+    return rc;
+  }
   const int64_t Vk1 = (int64_t)Di * Hi * Wi;
   if (ks == 1 && stride == 1 && pad == 0 && (Vk1 & 3) == 0 && aligned16(x1) && aligned16(x2) && aligned16(dy) && !force_direct()) {
     const int64_t nq = Vk1 / 4;

@@ -394,6 +394,124 @@ __global__ void __launch_bounds__(WTM_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient of the stride-2 (k3, pad 1) convolutions of the registration encoder (voxel_morph.py:46), TMA staged.
+//   dW[co][ci][kz][ky][kx] = sum_o dY[co][o] * X[ci][2*o + k - 1]
+// Same warp mapping as conv3d_wgrad_tma_kernel (12 warps = (kz, ci), 72 accumulators = 9 (ky,kx) x 8 co); the output
+// tile is 2 x 4 x 32 so that its 5 x 9 x 72 input box (x from 2*X0-4: 16-byte aligned) fits two pipeline stages.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int S2_TZ = 2, S2_TY = 4, S2_TX = 32;
+constexpr int S2_HZ = 2 * S2_TZ + 1, S2_HY = 2 * S2_TY + 1, S2_HX = 72;
+constexpr int S2_SX_BYTES = WG_CI * S2_HZ * S2_HY * S2_HX * 4;  // 51840
+constexpr int S2_SD_BYTES = WG_CO * S2_TZ * S2_TY * S2_TX * 4;  // 8192
+constexpr int S2_STAGE_BYTES = round128(S2_SX_BYTES) + S2_SD_BYTES;
+constexpr int S2_SMEM_BYTES = 2 * S2_STAGE_BYTES + 128;
+
+__global__ void __launch_bounds__(WTM_THREADS, 1)
+    conv3d_wgrad_s2_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mdy, WgTiledArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[2];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kz = warp >> 2, cl = warp & 3;
+  const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
+  const int region = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&mx);
+    tma_prefetch_desc(&mdy);
+  }
+  __syncthreads();
+
+  float acc[96];
+#pragma unroll
+  for (int i = 0; i < 96; ++i) acc[i] = 0.f;
+  float bacc[WG_CO];
+#pragma unroll
+  for (int o = 0; o < WG_CO; ++o) bacc[o] = 0.f;
+  const bool do_bias = a.bias_partials != nullptr && cib == 0 && warp == 4;
+
+  const int t0 = region * a.tiles_per_region;
+  const int t1 = min(a.ntiles, t0 + a.tiles_per_region);
+
+  auto issue = [&](int t, int s) {   // tiles enumerate the OUTPUT volume (a.tiles_* / a.D,H,W are output extents here)
+    int tb = t;
+    const int bx = tb % a.tiles_x; tb /= a.tiles_x;
+    const int by = tb % a.tiles_y; tb /= a.tiles_y;
+    const int bz = tb % a.tiles_z;
+    const int n = tb / a.tiles_z;
+    uint8_t* st = smem + s * S2_STAGE_BYTES;
+    mbar_expect_tx(&full[s], S2_SX_BYTES + S2_SD_BYTES);
+    tma_load_5d(st, &mx, &full[s], 2 * bx * S2_TX - 4, 2 * by * S2_TY - 1, 2 * bz * S2_TZ - 1, cib * WG_CI, n);
+    tma_load_5d(st + round128(S2_SX_BYTES), &mdy, &full[s], bx * S2_TX, by * S2_TY, bz * S2_TZ, cob * WG_CO, n);
+  };
+
+  if (threadIdx.x == 0 && t0 < t1) issue(t0, 0);
+  for (int t = t0; t < t1; ++t) {
+    const int k = t - t0, s = k & 1;
+    if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, s ^ 1);
+    mbar_wait(&full[s], (k >> 1) & 1);
+    const float* sx = reinterpret_cast<const float*>(smem + s * S2_STAGE_BYTES) + cl * S2_HZ * S2_HY * S2_HX;
+    const float* sd = reinterpret_cast<const float*>(smem + s * S2_STAGE_BYTES + round128(S2_SX_BYTES));
+#pragma unroll 1
+    for (int it = 0; it < (S2_TZ * S2_TY * S2_TX / 4) / 32; ++it) {
+      const int q = it * 32 + lane;
+      const int tx4 = q & 7, ty = (q >> 3) & 3, tz = q >> 5;
+      float4 d[WG_CO];
+#pragma unroll
+      for (int o = 0; o < WG_CO; ++o)
+        d[o] = *reinterpret_cast<const float4*>(sd + ((o * S2_TZ + tz) * S2_TY + ty) * S2_TX + tx4 * 4);
+      if (do_bias) {
+#pragma unroll
+        for (int o = 0; o < WG_CO; ++o) bacc[o] += (d[o].x + d[o].y) + (d[o].z + d[o].w);
+      }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float4* row = reinterpret_cast<const float4*>(sx + ((2 * tz + kz) * S2_HY + 2 * ty + ky) * S2_HX + tx4 * 8);
+        const float4 p0 = row[0], p1 = row[1], p2 = row[2];
+        // box x starts at 2*X0-4: input x = 2*(4*tx4+i) + kx - 1  <->  float 8*tx4 + 2*i + kx + 3
+        const float in[9] = {p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int o = 0; o < WG_CO; ++o) {
+            float v = acc[(ky * 3 + kx) * WG_CO + o];
+            v = fmaf(in[kx + 0], d[o].x, v);
+            v = fmaf(in[kx + 2], d[o].y, v);
+            v = fmaf(in[kx + 4], d[o].z, v);
+            v = fmaf(in[kx + 6], d[o].w, v);
+            acc[(ky * 3 + kx) * WG_CO + o] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  butterfly_reduce<96>(acc, lane);
+  float* pr = a.partials + (int64_t)region * a.region_stride;
+  const int ci = cib * WG_CI + cl;
+#pragma unroll
+  for (int gi = 0; gi < 3; ++gi) {
+    const int e = gi * 32 + lane;
+    if (e >= 72) continue;
+    const int o = e % WG_CO, kyx = e / WG_CO;
+    const int co = cob * WG_CO + o;
+    if (co < a.Cout && ci < a.C) pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + kz * 9 + kyx] = acc[gi];
+  }
+  if (do_bias) {
+#pragma unroll
+    for (int o = 0; o < WG_CO; ++o) {
+      const float b = warp_sum(bacc[o]);
+      const int co = cob * WG_CO + o;
+      if (lane == 0 && co < a.Cout) a.bias_partials[(int64_t)region * a.Cout + co] = b;
+    }
+  }
+}
+
 // weight repack for the TMA forward kernel: dst[cog][a (cin_pad)][tap'][CO], zero padded in both channel dims
 __global__ void repack_weights_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, int d0, int d1, int T,
                                           int a_is_dim0, int flip, int A, int a_off, int Apad, int B, int b_off, int Bpad,

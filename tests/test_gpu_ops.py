@@ -174,6 +174,8 @@ CONV_CASES = [
     (20, 0, 12, 3, 1, (33, 32, 35), False),     # odd extents, channel counts off the register tiles
     (16, 0, 32, 3, 2, (16, 18, 20), False),     # stride 2
     (32, 0, 32, 3, 2, (9, 11, 13), False),      # stride 2, odd extents
+    (16, 0, 32, 3, 2, (20, 24, 40), False),     # stride 2 through the TMA-staged tiled weight gradient (W % 8 == 0)
+    (6, 0, 12, 3, 2, (10, 18, 72), False),      # stride 2, ragged channel groups, two x tiles
     (16, 0, 7, 1, 1, (8, 9, 10), False),        # 1x1 head
     (16, 0, 32, 1, 1, (16, 20, 24), False),     # 1x1 head, 32 classes (streaming k1 weight-gradient kernel)
     (24, 8, 16, 3, 1, (8, 8, 8), True),         # ConvTranspose3d k3 s1 p1, two sources
