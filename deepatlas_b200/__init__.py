@@ -12,7 +12,7 @@ include/deepatlas_b200.h); importing this package without the built library rais
 """
 from __future__ import annotations
 
-from . import _lib, ops  # noqa: F401
+from . import _lib, evaluation, ops  # noqa: F401
 from .losses import (BendingEnergyLoss, DiceLossMultiClass, VoxelMorphLNCC, get_available_losses,  # noqa: F401
                      get_loss_function, loss_dict)
 from .networks import (UNet, UNet_generator, UNet_light, VoxelMorphCVPR2018, get_available_networks,  # noqa: F401

@@ -35,6 +35,7 @@ SIGNATURES = {
     "da_warp_dice_sums_bwd": ("ppipippiiiiiiiipppls", "rc"),
     "da_softmax_fwd": ("ppiils", "rc"),
     "da_softmax_bwd": ("pppiils", "rc"),
+    "da_argmax_counts": ("ppiiilpps", "rc"),
     # lncc
     "da_lncc_coef_bytes": ("iiiiii", "size"),
     "da_lncc_fwd_workspace_bytes": ("iiiii", "size"),

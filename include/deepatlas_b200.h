@@ -78,6 +78,12 @@ int da_warp_dice_sums_bwd(const float* prob, const float* field, int add_identit
 int da_softmax_fwd(const float* x, float* y, int N, int C, int64_t V, da_stream_t stream);
 int da_softmax_bwd(const float* y, const float* dy, float* dx, int N, int C, int64_t V, da_stream_t stream);
 
+/* ---- validation: label argmax + per-class overlap counts (models/segmentation.py:188-194, lib/evalMetrics.py:58-68) ----
+ * logits [N,C,V]; truth (nullable) [N,V] labels; counts [N,3,C] int64 = (#argmax==c, #truth==c, #both); pred (nullable)
+ * [N,V] uint8 label map (first maximum wins, as torch.max).  Bit-exact (integer atomics). */
+int da_argmax_counts(const float* logits, const void* truth, int truth_kind, int N, int C, int64_t V, int64_t* counts,
+                     uint8_t* pred, da_stream_t stream);
+
 /* ---- local NCC (VoxelMorphLNCC.forward, lib/loss.py:597-617) --------------------------------------------
  * I,J [N,1,D,H,W]; loss_out: one device float = 1 - mean(cc).  need_grad bit0 = I, bit1 = J; `coef`
  * (da_lncc_coef_bytes) is saved by forward for backward. */

@@ -339,3 +339,24 @@ def joint_loss(seg_sd: SD, reg_sd: SD, batch, n_classes: int, lambdas=None, dtyp
             + lam["ana"] * dice_multiclass(S_w, onehot, C, "Uniform", False, False, 1e-6)
             + lam["sup"] * (dice_multiclass(P_m, S_m.long(), C, "Uniform", False, True, 1e-6)
                             + dice_multiclass(P_t, S_t.long(), C, "Uniform", False, True, 1e-6)))
+
+
+# --------------------------------------------------------------------------------------------
+# evaluation step
+# --------------------------------------------------------------------------------------------
+
+
+def eval_dice_per_class(pred_logits, truths, n_classes: int):
+    """Inner loop of SegmentationExperiment.eval (models/segmentation.py:188-194) with metricEval('dice', ...,
+    num_labels=2) = 1 - scipy.spatial.distance.dice on boolean arrays (lib/evalMetrics.py:58-68), one volume at a time.
+    Returns (N, n_classes-1) float64 and the argmax label map."""
+    import numpy as np
+    import scipy.spatial.distance
+    labels = torch.max(pred_logits, 1)[1]
+    out = np.zeros((pred_logits.shape[0], n_classes - 1))
+    for n in range(pred_logits.shape[0]):
+        for c in range(1, n_classes):
+            a, b = labels[n].numpy().reshape(-1) == c, truths[n].numpy().reshape(-1) == c
+            with np.errstate(invalid="ignore", divide="ignore"):
+                out[n, c - 1] = 1.0 - scipy.spatial.distance.dice(a, b)
+    return torch.from_numpy(out), labels

@@ -322,3 +322,24 @@ def test_warped_dice_fused_vs_oracle(cuda, C, size, dtype):
         p2, f2 = prob.to(cuda).requires_grad_(True), phi.to(cuda).requires_grad_(True)
         crit(da.ops.warp3d(p2, f2), lab.to(cuda)).backward()
         assert rel_err(pg.grad, p2.grad) < TOL and rel_err(fg.grad, f2.grad) < TOL
+
+
+@pytest.mark.parametrize("C,size,dtype", [(4, (9, 10, 11), torch.uint8), (32, (8, 12, 16), torch.int64)])
+def test_eval_argmax_and_dice_bit_exact(cuda, C, size, dtype):
+    """Validation step: label argmax indices and per-class Dice (scipy formula) bit-exact against the oracle, including
+    ties (first maximum wins) and a class absent from both maps (nan, as scipy)."""
+    from deepatlas_b200 import evaluation
+    from oracle import ref_port as P
+    g = _g()
+    logits = torch.randn((2, C) + size, generator=g)
+    logits[:, 2] = logits[:, 1]                      # exact ties between classes 1 and 2 everywhere class 1 would win
+    logits[:, C - 1] = -50.0                         # last class never predicted ...
+    truth = torch.randint(0, C - 1, (2,) + size, generator=g).to(dtype)   # ... and never present
+    counts, pred = evaluation.argmax_counts(logits.to(cuda), truth.to(cuda))
+    ref_dice, ref_labels = P.eval_dice_per_class(logits, truth.long(), C)
+    assert torch.equal(pred.cpu().long(), ref_labels)
+    got = evaluation.dice_per_class(logits.to(cuda), truth.to(cuda)).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(ref_dice)) and bool(torch.isnan(got[:, -1]).all())
+    ok = ~torch.isnan(ref_dice)
+    assert torch.equal(got[ok], ref_dice[ok])
+    assert int(counts[:, 0].sum()) == 2 * logits[0, 0].numel() and int(counts[:, 0, 2].sum()) == 0
