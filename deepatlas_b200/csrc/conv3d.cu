@@ -774,7 +774,7 @@ inline bool tma_disabled() {
 inline bool fwd_tma_ok(const float* x1, const float* x2, const float* out, const ConvGeom& g) {
   const int Cin = g.C1 + g.C2;
   return !force_direct() && !tma_disabled() && g.stride == 1 && g.pad == 1 && Cin >= 3 && (g.Wi & 3) == 0 && g.Wo >= 16 &&
-         (int64_t)g.Do * g.Ho * g.Wo >= 32768 && aligned16(x1) && aligned16(x2) && aligned16(out) &&
+         (int64_t)g.Do * g.Ho * g.Wo >= 8192 && aligned16(x1) && aligned16(x2) && aligned16(out) &&
          (g.C2 == 0 || g.C1 % TMA_CK == 0);
 }
 
