@@ -845,8 +845,11 @@ inline bool umma_enabled() {
 }
 constexpr int64_t UMMA_IMG_BYTES = UmmaCfg::W_BYTES;  // 92160
 inline bool fwd_umma_ok(const ConvGeom& g) {
+  // one launch covers a 16 x 16 channel block: below ~50k voxels a launch no longer amortises its fixed cost and the
+  // tiled FFMA kernel (one launch per layer) wins (measured on UNet's 32^3 levels: 768 launches per layer)
+  if (g_force_direct == 3) return g.stride == 1 && g.pad == 1;  // tests: tensor-core path whatever the size heuristics say
   return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 &&
-         (int64_t)g.Do * g.Ho * g.Wo >= 32768;
+         (int64_t)g.Do * g.Ho * g.Wo >= 65536;
 }
 inline int64_t umma_workspace_bytes(int Cin, int Cout) {
   return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + UM_KC - 1) / UM_KC) * UMMA_IMG_BYTES + 256;
@@ -990,10 +993,10 @@ DA_API int da_umma_debug_read(int64_t* out6) {
 
 // Kernel selection for k3 s1 p1 convolutions: 0 = automatic (tcgen05 3xTF32 forward/dgrad + TMA-staged FFMA weight
 // gradient where they apply), 1 = always the generic direct kernels, 2 = tiled exact-FFMA kernels only (the parity
-// tests cross-check all three).  Also settable through the
+// tests cross-check all of them), 3 = tcgen05 forward/dgrad whenever structurally possible (ignores the size heuristics).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
 DA_API int da_set_conv_impl(int impl) {
-  DA_REQUIRE(impl >= 0 && impl <= 2, "da_set_conv_impl: impl must be 0 (auto), 1 (direct) or 2 (tiled FFMA, no tensor cores)");
+  DA_REQUIRE(impl >= 0 && impl <= 3, "da_set_conv_impl: impl must be 0 (auto), 1 (direct), 2 (tiled FFMA, no tensor cores) or 3 (tensor cores forced)");
   g_force_direct = impl;
   return DA_OK;
 }

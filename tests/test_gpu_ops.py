@@ -190,12 +190,12 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", ["auto", "direct", "ffma"])
+@pytest.mark.parametrize("impl", ["auto", "direct", "ffma", "umma"])
 @pytest.mark.parametrize("slope", [None, 0.0])
 def test_conv3d(cuda, case, impl, slope):
     from deepatlas_b200 import _lib, ops
     C1, C2, Cout, ks, stride, size, transposed = case
-    if impl != "auto" and slope is not None:
+    if impl not in ("auto", "umma") and slope is not None:
         pytest.skip("activation epilogue covered by the auto run")
     g = _g()
     x1 = torch.randn((2, C1) + size, generator=g)
@@ -230,8 +230,10 @@ def test_conv3d(cuda, case, impl, slope):
         mask_box["gpu_pos"] = out.detach().cpu() > 0
         return out
 
+    if impl == "umma" and (ks != 3 or stride != 1):
+        pytest.skip("tensor-core path covers k3 s1 p1")
     ins = [x1] + ([x2] if C2 else []) + [w, b]
-    _lib.call("da_set_conv_impl", {"auto": 0, "direct": 1, "ffma": 2}[impl])
+    _lib.call("da_set_conv_impl", {"auto": 0, "direct": 1, "ffma": 2, "umma": 3}[impl])
     try:
         res = _run_both(gpu, cpu, ins, cuda)
     finally:
