@@ -7,6 +7,7 @@
 // (= four adjacent output voxels -> float4 stores) and four output channels; the weight layout
 // (Cin,Cout,2,2,2) is already [ci][co][pos], so no repack is needed.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace {
 
@@ -218,6 +219,95 @@ __global__ void __launch_bounds__(DW_THREADS) deconv_k2s2_wgrad_kernel(const flo
   }
 }
 
+// TMA-staged tiled variant (W % 4 == 0, 16-byte aligned tensors): a block owns 8 ci x 8 co and walks a region of
+// 1 x 4 x 32 input-voxel tiles; the dY tile [8 co][2][8][64] (32 KB) and the x tile [8 ci][4][32] are box-loaded once and
+// shared by the four warps, warp = (a, b) output-row parity, both c parities in registers: 128 accumulators, 512 FFMA
+// per 24 LDS.128.  dY is read (Cin/8) times from L2 instead of (Cin/4) times through L1.
+constexpr int DT_TY = 4, DT_TX = 32, DT_CI = 8, DT_CO = 8;
+constexpr int DT_SX_BYTES = DT_CI * DT_TY * DT_TX * 4;            // 4096
+constexpr int DT_SD_BYTES = DT_CO * 2 * (2 * DT_TY) * (2 * DT_TX) * 4;  // 32768
+constexpr int DT_STAGE_BYTES = DT_SX_BYTES + DT_SD_BYTES;
+constexpr int DT_SMEM_BYTES = 2 * DT_STAGE_BYTES + 128;
+constexpr int DT_THREADS = 128;
+
+struct DeconvWgArgs {
+  float* partials;
+  int Cin, Cout, N, D, H, W;
+  int tiles_x, tiles_y, tiles_per_region, ntiles, nCoB;
+  int64_t region_stride;
+};
+
+__global__ void __launch_bounds__(DT_THREADS, 2)
+    deconv_k2s2_wgrad_tma_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mdy, DeconvWgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[2];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pa = warp >> 1, pb = warp & 1;  // output parity along z and y handled by this warp
+  const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
+  const int region = blockIdx.y;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&mx);
+    tma_prefetch_desc(&mdy);
+  }
+  __syncthreads();
+  float acc[DT_CI][DT_CO][2];
+#pragma unroll
+  for (int c = 0; c < DT_CI; ++c)
+#pragma unroll
+    for (int o = 0; o < DT_CO; ++o) acc[c][o][0] = acc[c][o][1] = 0.f;
+  const int t0 = region * a.tiles_per_region, t1 = min(a.ntiles, t0 + a.tiles_per_region);
+  auto issue = [&](int t, int s) {
+    int tb = t;
+    const int bx = tb % a.tiles_x; tb /= a.tiles_x;
+    const int by = tb % a.tiles_y; tb /= a.tiles_y;
+    const int z = tb % a.D;
+    const int n = tb / a.D;
+    uint8_t* st = smem + s * DT_STAGE_BYTES;
+    mbar_expect_tx(&full[s], DT_STAGE_BYTES);
+    tma_load_5d(st, &mx, &full[s], bx * DT_TX, by * DT_TY, z, cib * DT_CI, n);
+    tma_load_5d(st + DT_SX_BYTES, &mdy, &full[s], 2 * bx * DT_TX, 2 * by * DT_TY, 2 * z, cob * DT_CO, n);
+  };
+  if (threadIdx.x == 0 && t0 < t1) issue(t0, 0);
+  const int tx4 = lane & 7, ty = lane >> 3;  // one iteration: 4 rows x 8 quads of 4 input voxels
+  for (int t = t0; t < t1; ++t) {
+    const int k = t - t0, s = k & 1;
+    if (threadIdx.x == 0 && t + 1 < t1) issue(t + 1, s ^ 1);
+    mbar_wait(&full[s], (k >> 1) & 1);
+    const float* sx = reinterpret_cast<const float*>(smem + s * DT_STAGE_BYTES);
+    const float* sd = reinterpret_cast<const float*>(smem + s * DT_STAGE_BYTES + DT_SX_BYTES);
+    float4 xv[DT_CI];
+#pragma unroll
+    for (int c = 0; c < DT_CI; ++c) xv[c] = *reinterpret_cast<const float4*>(sx + (c * DT_TY + ty) * DT_TX + tx4 * 4);
+#pragma unroll
+    for (int o = 0; o < DT_CO; ++o) {
+      const float4* dr = reinterpret_cast<const float4*>(sd + ((o * 2 + pa) * (2 * DT_TY) + 2 * ty + pb) * (2 * DT_TX) + tx4 * 8);
+      const float4 d0 = dr[0], d1 = dr[1];  // dY at output x = 8*tx4 .. 8*tx4+7: even = parity 0, odd = parity 1
+#pragma unroll
+      for (int c = 0; c < DT_CI; ++c) {
+        acc[c][o][0] = fmaf(xv[c].x, d0.x, fmaf(xv[c].y, d0.z, fmaf(xv[c].z, d1.x, fmaf(xv[c].w, d1.z, acc[c][o][0]))));
+        acc[c][o][1] = fmaf(xv[c].x, d0.y, fmaf(xv[c].y, d0.w, fmaf(xv[c].z, d1.y, fmaf(xv[c].w, d1.w, acc[c][o][1]))));
+      }
+    }
+    __syncthreads();
+  }
+  // fold the 32 lanes (xor butterfly, fixed order) and write this region's partial sums
+  float* pr = a.partials + (int64_t)region * a.region_stride;
+#pragma unroll
+  for (int c = 0; c < DT_CI; ++c)
+#pragma unroll
+    for (int o = 0; o < DT_CO; ++o)
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        const float v = warp_sum(acc[c][o][pc]);
+        const int ci = cib * DT_CI + c, co = cob * DT_CO + o;
+        if (lane == 0 && ci < a.Cin && co < a.Cout) pr[((int64_t)ci * a.Cout + co) * 8 + (pa * 2 + pb) * 2 + pc] = v;
+      }
+}
+
 __global__ void dc_reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count, float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -269,8 +359,39 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
   DA_REQUIRE(x && dy && grad_weight && workspace, "da_deconv_k2s2_wgrad: null pointer");
   if (workspace_bytes < da_deconv_k2s2_wgrad_workspace_bytes(Cin, Cout)) { da_set_error("da_deconv_k2s2_wgrad: workspace too small"); return DA_ERR_WORKSPACE; }
   const int64_t count = (int64_t)Cin * Cout * 8;
-  const int64_t total_rows = (int64_t)N * D * H * ((W + 31) / 32);
   const int cap = dc_region_cap(count);
+  if ((W & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0 && da_get_encode_tiled() != nullptr) {
+    DeconvWgArgs a;
+    a.partials = (float*)workspace; a.Cin = Cin; a.Cout = Cout; a.N = N; a.D = D; a.H = H; a.W = W;
+    a.tiles_x = (W + DT_TX - 1) / DT_TX; a.tiles_y = (H + DT_TY - 1) / DT_TY;
+    a.ntiles = N * D * a.tiles_x * a.tiles_y;
+    a.nCoB = (Cout + DT_CO - 1) / DT_CO;
+    const int groups = ((Cin + DT_CI - 1) / DT_CI) * a.nCoB;
+    int nregions = (6 * DA_NUM_SMS + groups / 2) / groups;
+    if (nregions > cap) nregions = cap;
+    if (nregions > a.ntiles) nregions = a.ntiles;
+    if (nregions < 1) nregions = 1;
+    a.tiles_per_region = (a.ntiles + nregions - 1) / nregions;
+    nregions = (a.ntiles + a.tiles_per_region - 1) / a.tiles_per_region;
+    a.region_stride = count;
+    CUtensorMap mx, mdy;
+    int r = da_make_volume_map(&mx, x, N, Cin, D, H, W, DT_TX, DT_TY, 1, DT_CI);
+    if (!r) r = da_make_volume_map(&mdy, dy, N, Cout, 2 * D, 2 * H, 2 * W, 2 * DT_TX, 2 * DT_TY, 2, DT_CO);
+    if (r) return r;
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(deconv_k2s2_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+      configured = true;
+    }
+    deconv_k2s2_wgrad_tma_kernel<<<dim3(groups, nregions), DT_THREADS, DT_SMEM_BYTES, stream>>>(mx, mdy, a);
+    int rc = da_check_launch("da_deconv_k2s2_wgrad_tma");
+    if (rc) return rc;
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
+    rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
+    if (rc || !grad_bias) return rc;
+    return da_channel_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, workspace, workspace_bytes, stream);
+  }
+  const int64_t total_rows = (int64_t)N * D * H * ((W + 31) / 32);
   int nregions = (int)(total_rows < cap ? total_rows : cap);
   const int64_t rpr = da_cdiv(total_rows, nregions);
   nregions = (int)da_cdiv(total_rows, rpr);
