@@ -663,6 +663,7 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restr
 
 #include "conv3d_tma.inc.cuh"
 #include "conv3d_umma.inc.cuh"
+#include "conv3d_wgrad_umma.inc.cuh"
 
 // out[i] = sum_r partials[r][i]  (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
@@ -1083,6 +1084,60 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
 
 // Weight gradient (+ optional bias gradient).  grad_weight has the layer's own layout
 // ((Cout,Cin,k^3), or (Cin,Cout,k^3) when transposed).  x2 may be null.
+// tcgen05 weight gradient (conv3d_wgrad_umma_kernel): k3 s1 p1 layers whose volume amortises the per-CTA TMEM read-out
+inline bool wgrad_umma_ok(int N, int D, int H, int W) {
+  if (g_force_direct == 3) return true;
+  const char* e = getenv("DA_WGRAD_UMMA");
+  if (e && strcmp(e, "0") == 0) return false;
+  return umma_enabled() && !force_direct() && W >= 16 && (int64_t)N * D * H * W >= 65536;
+}
+
+int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed, float* grad_weight,
+                   float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, float* partials, int cap, cudaStream_t stream) {
+  const int Cin = C1 + C2;
+  const int64_t count = (int64_t)Cin * Cout * 27;
+  const int tiles_x = (Wi + WU_XT - 1) / WU_XT, tiles_y = (Hi + WU_YT - 1) / WU_YT;
+  const int ntiles = N * Di * tiles_y * tiles_x;
+  const int a_ch = transposed ? Cout : Cin, b_ch = transposed ? Cin : Cout;
+  const int groups = ((a_ch + 15) / 16) * ((b_ch + 15) / 16);
+  int nregions = (2 * DA_NUM_SMS + groups / 2) / groups;
+  if (nregions > cap) nregions = cap;
+  if (nregions > ntiles) nregions = ntiles;
+  if (nregions < 1) nregions = 1;
+  const int tpr = (ntiles + nregions - 1) / nregions;
+  nregions = (ntiles + tpr - 1) / tpr;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WU_SMEM_BYTES);
+    configured = true;
+  }
+  auto launch = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off) -> int {
+    WgUmmaArgs a;
+    a.x = xin; a.dy = gout; a.partials = partials;
+    a.N = N; a.C = C; a.ci_off = ci_off; a.Cin_total = Cin_total_; a.Cout = Cout_; a.co_off = co_off;
+    a.region_stride = count; a.D = Di; a.H = Hi; a.W = Wi;
+    a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_per_region = tpr; a.ntiles = ntiles;
+    a.nCoB = (Cout_ + 15) / 16;
+    dim3 grid(((C + 15) / 16) * a.nCoB, nregions);
+    conv3d_wgrad_umma_kernel<<<grid, WU_THREADS, WU_SMEM_BYTES, stream>>>(a);
+    return da_check_launch("conv3d_wgrad_umma");
+  };
+  int rc;
+  if (!transposed) {
+    rc = launch(x1, C1, 0, Cin, dy, Cout, 0);
+    if (!rc && C2) rc = launch(x2, C2, C1, Cin, dy, Cout, 0);
+  } else {
+    rc = launch(dy, Cout, 0, Cout, x1, C1, 0);
+    if (!rc && C2) rc = launch(dy, Cout, 0, Cout, x2, C2, C1);
+  }
+  if (rc) return rc;
+  reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+  rc = da_check_launch("conv3d_wgrad_umma/reduce");
+  if (!rc && grad_bias)
+    rc = run_channel_sum(dy, N, Cout, (int64_t)Di * Hi * Wi, grad_bias, partials + (int64_t)nregions * count, stream);
+  return rc;
+}
+
 DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
                            float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                            int stride, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
@@ -1107,6 +1162,8 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
     if (nregions < 1) nregions = 1;
     const int tpr = (ntiles + nregions - 1) / nregions;
     nregions = (ntiles + tpr - 1) / tpr;
+    if (wgrad_umma_ok(N, Di, Hi, Wi))
+      return run_wgrad_umma(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, partials, cap, stream);
     float* bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
     static bool configured = false;
     if (!configured) {

@@ -1,0 +1,249 @@
+// Tensor-core (tcgen05, 3xTF32) weight gradient of the k3 s1 p1 convolutions.  Included by conv3d.cu.
+//
+//   dW[co][ci][kz][ky][kx] = sum_q dY[co][q] * X[ci][q + (kz-1, ky-1, kx-1)]
+// as ONE GEMM per (16 ci x 16 co) block whose accumulator never leaves TMEM until the CTA has walked its whole region:
+//   D[(t, ci)][(kz, ky, co)] += sum_k A[(t, ci)][k] * B[(kz, ky, co)][k],      k = (x, ye): 2 x-positions x 4 y-rows per MMA
+//   A[(t, ci)][(x, ye)]      = X [ci][z][y0+ye][x0 - 1 + x + t]                 t = kx
+//   B[(kz,ky,co)][(x, ye)]   = dY[co][z-kz+1][y0+ye-ky+1][x0 + x]
+// * The kx shift costs nothing: the A tile is stored [x-position][ci 16][4 y-rows] (256 B per position), so MMA row
+//   16*t + ci simply lands t positions further (SBO = 128 B, LBO = 256 B alias each other on purpose).  Rows t = 3..7 of
+//   the 128-row MMA compute garbage that is never read.
+// * ky and kz are folded into N = 144: the producers replicate each dY value into the nine (kz, ky) row groups of the
+//   B tile (9 x 16 co rows per x-position); 1.2 KB of shared-memory stores per position against 30 MMA-cycles.
+// * fp32 accuracy from three TF32 MMAs per K step (hi/lo split by the producers), as in conv3d_umma_kernel.
+// * No epilogue per tile: 24 MMAs per 64-position tile, two-stage producer/MMA pipeline, one TMEM read at the end that
+//   writes this CTA's partial sums (fixed-order region reduce afterwards, deterministic).
+// Warp roles: 0 = MMA issue + TMEM allocation, 1..15 = producers (B tasks on threads 0..383, A tasks on 384..479 of the
+// producer set), warps 4 and 5 read the accumulator at the end.
+
+constexpr int WU_XT = 16, WU_YT = 4;             // tile: 16 x-positions x 4 y-rows of one plane
+constexpr int WU_AC = WU_XT + 8;                 // A chunks per stage (x0-1 .. x0+XT+6)
+constexpr int WU_N = 144;                        // (kz, ky, co)
+constexpr int WU_A_BYTES = WU_AC * 256;          // per hi / lo half
+constexpr int WU_BP = WU_N * 16 + 16;             // B pitch per x-position: +16 B so that lanes along x hit different banks
+constexpr int WU_B_BYTES = WU_XT * WU_BP;        // 37120 per half
+constexpr int WU_STAGE_BYTES = 2 * WU_A_BYTES + 2 * WU_B_BYTES;  // 86528
+constexpr int WU_SMEM_BYTES = 2 * WU_STAGE_BYTES + 128;
+constexpr int WU_THREADS = 512, WU_NPROD = 480;
+constexpr int WU_BTASKS = WU_XT * 3 * 16, WU_ATASKS = WU_AC * 16;  // 768, 384
+static_assert(WU_BTASKS == 2 * 384 && WU_ATASKS == 4 * 96, "producer mapping");
+
+struct WgUmmaArgs {
+  const float* x;   // [N][C][D][H][W]   halo side
+  const float* dy;  // [N][Cout][D][H][W]
+  float* partials;  // [region][Cout_total][Cin_total][27]
+  int N, C, ci_off, Cin_total, Cout, co_off;
+  int64_t region_stride;
+  int D, H, W;
+  int tiles_x, tiles_y, tiles_per_region, ntiles, nCoB;
+};
+
+__global__ void __launch_bounds__(WU_THREADS, 1) conv3d_wgrad_umma_kernel(WgUmmaArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[2], empty[2], done;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
+  const int region = blockIdx.y;
+  const int64_t HW = (int64_t)a.H * a.W, V = HW * a.D;
+  const int t0 = region * a.tiles_per_region, t1 = min(a.ntiles, t0 + a.tiles_per_region);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], WU_NPROD); mbar_init(&empty[i], 1); }
+    mbar_init(&done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // =============================== MMA issue ===============================
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WU_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc0 = umma_desc(0, 256, 128), bdesc0 = umma_desc(0, WU_BP, 128);
+    const uint32_t base_s = smem_u32(smem);
+    uint32_t first = 1;
+    for (int t = t0; t < t1; ++t) {
+      const int k = t - t0, s = k & 1;
+      mbar_wait(&full[s], (k >> 1) & 1);
+      tc_fence_after();
+      if (elected) {
+        const uint32_t a_hi = base_s + (uint32_t)s * WU_STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * WU_A_BYTES, b_lo = b_hi + WU_B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < WU_XT / 2; ++ks) {
+          const uint32_t ao = (uint32_t)(2 * ks) * 256, bo = (uint32_t)(2 * ks) * WU_BP;
+          umma_tf32(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, first ? 0u : 1u);
+          first = 0;
+          umma_tf32(tmem, umma_desc_at(adesc0, a_lo + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, 1u);
+          umma_tf32(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_lo + bo), idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elected) umma_commit(&done);
+    __syncwarp();
+  } else if (threadIdx.x < 32 + 384) {
+    // =============================== B producers: (x, co, kz) fixed per (thread, j) ===============================
+    const int tp = threadIdx.x - 32;
+    const float* base[2];
+    int tkz[2], tco[2];
+    bool tok[2];
+    const int tx = tp & 15;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tb = tp + 384 * j;
+      tco[j] = (tb >> 4) & 15; tkz[j] = tb >> 8;
+      tok[j] = cob * 16 + tco[j] < a.Cout;
+      base[j] = a.dy + (int64_t)(cob * 16 + tco[j]) * V + tx;
+    }
+    float v[2][6], vn[2][6];
+    auto gather = [&](int t, float (&o)[2][6]) {
+      int tb = t;
+      const int bx = tb % a.tiles_x; tb /= a.tiles_x;
+      const int by = tb % a.tiles_y; tb /= a.tiles_y;
+      const int z = tb % a.D;
+      const int n = tb / a.D;
+      const int x0 = bx * WU_XT, y0 = by * WU_YT;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int zz = z - tkz[j] + 1;
+        const bool ok = tok[j] && zz >= 0 && zz < a.D && x0 + tx < a.W;
+        const float* p = base[j] + (int64_t)n * a.Cout * V + (int64_t)zz * HW + x0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const int gy = y0 - 1 + r;
+          o[j][r] = (ok && gy >= 0 && gy < a.H) ? __ldg(p + (int64_t)gy * a.W) : 0.f;
+        }
+      }
+    };
+    if (t0 < t1) gather(t0, vn);
+    for (int t = t0; t < t1; ++t) {
+      const int k = t - t0, s = k & 1, use = k >> 1;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) v[j][r] = vn[j][r];
+      if (t + 1 < t1) gather(t + 1, vn);  // next tile's loads fly while this one is split and stored
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      uint8_t* st = smem + s * WU_STAGE_BYTES + 2 * WU_A_BYTES;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {  // dY row y0 + e - ky + 1  =  v[e - ky + 2]
+            const float val = v[j][e - ky + 2];
+            h[e] = __uint_as_float(__float_as_uint(val) & 0xffffe000u);
+            l[e] = val - h[e];
+          }
+          const int off = tx * WU_BP + ((tkz[j] * 3 + ky) * 16 + tco[j]) * 16;
+          *reinterpret_cast<float4*>(st + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(st + WU_B_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+  } else {
+    // =============================== A producers: (xc, ci) fixed per (thread, j) ===============================
+    // lanes 0..7 of every quarter warp hold eight different ci (16 B apart in the tile): conflict-free 16-byte stores
+    const int tp = threadIdx.x - 32 - 384, w = tp >> 5, l5 = tp & 31;
+    const float* base[4];
+    int txc[4], tci[4];
+    bool tok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      tci[j] = (l5 & 7) + 8 * (j & 1);
+      txc[j] = (l5 >> 3) + 4 * (w + 3 * (j >> 1));
+      tok[j] = cib * 16 + tci[j] < a.C && txc[j] < WU_XT + 2;  // chunks beyond feed only the unused rows t >= 3
+      base[j] = a.x + (int64_t)(cib * 16 + tci[j]) * V + txc[j] - 1;
+    }
+    float v[4][4], vn[4][4];
+    auto gather = [&](int t, float (&o)[4][4]) {
+      int tb = t;
+      const int bx = tb % a.tiles_x; tb /= a.tiles_x;
+      const int by = tb % a.tiles_y; tb /= a.tiles_y;
+      const int z = tb % a.D;
+      const int n = tb / a.D;
+      const int x0 = bx * WU_XT, y0 = by * WU_YT;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gx = x0 - 1 + txc[j];
+        const bool ok = tok[j] && gx >= 0 && gx < a.W;
+        const float* p = base[j] + (int64_t)n * a.C * V + (int64_t)z * HW + x0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int gy = y0 + r;
+          o[j][r] = (ok && gy < a.H) ? __ldg(p + (int64_t)gy * a.W) : 0.f;
+        }
+      }
+    };
+    if (t0 < t1) gather(t0, vn);
+    for (int t = t0; t < t1; ++t) {
+      const int k = t - t0, s = k & 1, use = k >> 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[j][r] = vn[j][r];
+      if (t + 1 < t1) gather(t + 1, vn);
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      uint8_t* st = smem + s * WU_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __uint_as_float(__float_as_uint(v[j][e]) & 0xffffe000u);
+          l[e] = v[j][e] - h[e];
+        }
+        const int off = (txc[j] * 16 + tci[j]) * 16;
+        *reinterpret_cast<float4*>(st + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(st + WU_A_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+  }
+
+  // ---- final read of the accumulator: rows 16*t + ci (t = kx < 3), columns (kz*3+ky)*16 + co ----
+  if (warp == 4 || warp == 5) {
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    const int r = (warp - 4) * 32 + lane;  // TMEM lane = accumulator row; warp 4 -> lanes 0..31, warp 5 -> 32..63
+    const int kx = r >> 4, ci = cib * 16 + (r & 15);
+    float* pr = a.partials + (int64_t)region * a.region_stride;
+#pragma unroll 1
+    for (int g = 0; g < 9; ++g) {
+      float v16[16];
+      tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 16), v16);
+      tmem_ld_wait();
+      if (kx < 3 && ci < a.C && t0 < t1) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int co = cob * 16 + c;
+          if (co < a.Cout) pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + g * 3 + kx] = v16[c];
+        }
+      } else if (kx < 3 && ci < a.C) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int co = cob * 16 + c;
+          if (co < a.Cout) pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + g * 3 + kx] = 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+}
