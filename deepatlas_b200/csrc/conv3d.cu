@@ -1106,9 +1106,11 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
   if (nregions < 1) nregions = 1;
   const int tpr = (ntiles + nregions - 1) / nregions;
   nregions = (ntiles + tpr - 1) / tpr;
+  const bool use_tma = !tma_disabled() && (Wi & 3) == 0 && Wi >= 24 && Hi >= 6;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WU_SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_wgrad_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WV_SMEM_BYTES);
     configured = true;
   }
   auto launch = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off) -> int {
@@ -1119,6 +1121,14 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_per_region = tpr; a.ntiles = ntiles;
     a.nCoB = (Cout_ + 15) / 16;
     dim3 grid(((C + 15) / 16) * a.nCoB, nregions);
+    if (use_tma && aligned16(xin) && aligned16(gout)) {
+      CUtensorMap mx, mdy;
+      int r = da_make_volume_map(&mx, xin, N, C, Di, Hi, Wi, 24, 4, 1, 16);
+      if (!r) r = da_make_volume_map(&mdy, gout, N, Cout_, Di, Hi, Wi, 16, 6, 1, 16);
+      if (r) return r;
+      conv3d_wgrad_umma_tma_kernel<<<grid, WU_THREADS, WV_SMEM_BYTES, stream>>>(mx, mdy, a);
+      return da_check_launch("conv3d_wgrad_umma_tma");
+    }
     conv3d_wgrad_umma_kernel<<<grid, WU_THREADS, WU_SMEM_BYTES, stream>>>(a);
     return da_check_launch("conv3d_wgrad_umma");
   };

@@ -247,3 +247,223 @@ __global__ void __launch_bounds__(WU_THREADS, 1) conv3d_wgrad_umma_kernel(WgUmma
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed variant (W % 4 == 0, 16-byte aligned tensors): same GEMM, but the raw tiles arrive through rank-5 tensor maps
+// (zero fill outside the volume and beyond the channel count, so the producers carry no bounds checks and no address
+// arithmetic) and the tiles of a CTA walk along z, so each tile brings ONE new dY plane; the other two are still in
+// the five-slot plane ring.  Warp 0 = MMA issue, warp 1 = TMA issue, warps 2..13 = B producers, 14..15 = A producers.
+//   rawY slot: [16 co][6 rows y0-1..y0+4][16 x]   box {16, 6, 1, 16, 1}
+//   rawX slot: [16 ci][4 rows y0..y0+3][24 x from x0-4]   box {24, 4, 1, 16, 1}   (inner coordinate stays 16-byte aligned)
+constexpr int WV_YS = 5, WV_XS = 3;
+constexpr int WV_RAW_BYTES = 16 * 6 * 16 * 4;  // 6144 for both kinds of slot
+static_assert(16 * 4 * 24 * 4 == WV_RAW_BYTES, "raw slots share one size");
+constexpr int WV_RAW_OFF = 2 * WU_STAGE_BYTES;  // 173056: multiple of 128
+static_assert(WV_RAW_OFF % 128 == 0, "TMA destination alignment");
+constexpr int WV_SMEM_BYTES = WV_RAW_OFF + (WV_YS + WV_XS) * WV_RAW_BYTES + 128;
+constexpr int WV_NPROD = 448;
+
+__global__ void __launch_bounds__(WU_THREADS, 1)
+conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgUmmaArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[2], empty[2], rawfull[3], consumed[3], done;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
+  const int region = blockIdx.y;
+  // tile order: z fastest, then bx, by, n
+  const int t0 = region * a.tiles_per_region, t1 = min(a.ntiles, t0 + a.tiles_per_region);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], WV_NPROD); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&rawfull[i], 1); mbar_init(&consumed[i], WV_NPROD); }
+    mbar_init(&done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  float* rawY = reinterpret_cast<float*>(smem + WV_RAW_OFF);
+  float* rawX = reinterpret_cast<float*>(smem + WV_RAW_OFF + WV_YS * WV_RAW_BYTES);
+
+  if (warp == 0) {
+    // =============================== MMA issue ===============================
+    uint32_t elected;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WU_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc0 = umma_desc(0, 256, 128), bdesc0 = umma_desc(0, WU_BP, 128);
+    const uint32_t base_s = smem_u32(smem);
+    uint32_t first = 1;
+    for (int t = t0; t < t1; ++t) {
+      const int k = t - t0, s = k & 1;
+      mbar_wait(&full[s], (k >> 1) & 1);
+      tc_fence_after();
+      if (elected) {
+        const uint32_t a_hi = base_s + (uint32_t)s * WU_STAGE_BYTES, a_lo = a_hi + WU_A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * WU_A_BYTES, b_lo = b_hi + WU_B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < WU_XT / 2; ++ks) {
+          const uint32_t ao = (uint32_t)(2 * ks) * 256, bo = (uint32_t)(2 * ks) * WU_BP;
+          umma_tf32(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, first ? 0u : 1u);
+          first = 0;
+          umma_tf32(tmem, umma_desc_at(adesc0, a_lo + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, 1u);
+          umma_tf32(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_lo + bo), idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elected) umma_commit(&done);
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== TMA issue ===============================
+    if (lane == 0) {
+      tma_prefetch_desc(&map_x);
+      tma_prefetch_desc(&map_dy);
+      int q = -1;  // sequence number of the newest dY plane in the ring
+      for (int t = t0; t < t1; ++t) {
+        const int k = t - t0;
+        const int z = t % a.D;
+        int col = t / a.D;
+        const int bx = col % a.tiles_x; col /= a.tiles_x;
+        const int by = col % a.tiles_y;
+        const int n = col / a.tiles_y;
+        const int x0 = bx * WU_XT, y0 = by * WU_YT;
+        const bool fresh = (k == 0) || (z == 0);  // new column: all three planes; otherwise only plane z+1
+        // slots about to be overwritten were last read by tile k-1 (fresh) or k-3 (steady state)
+        const int dep = fresh ? k - 1 : k - 3;
+        if (dep >= 0) mbar_wait(&consumed[dep % 3], (dep / 3) & 1);
+        uint64_t* bar = &rawfull[k % 3];
+        mbar_expect_tx(bar, (uint32_t)WV_RAW_BYTES * (fresh ? 4u : 2u));
+        tma_load_5d(rawX + (k % WV_XS) * (WV_RAW_BYTES / 4), &map_x, bar, x0 - 4, y0, z, cib * 16, n);
+        if (fresh) {
+          tma_load_5d(rawY + ((q + 1) % WV_YS) * (WV_RAW_BYTES / 4), &map_dy, bar, x0, y0 - 1, z - 1, cob * 16, n);
+          tma_load_5d(rawY + ((q + 2) % WV_YS) * (WV_RAW_BYTES / 4), &map_dy, bar, x0, y0 - 1, z, cob * 16, n);
+          q += 3;
+        } else {
+          q += 1;
+        }
+        tma_load_5d(rawY + (q % WV_YS) * (WV_RAW_BYTES / 4), &map_dy, bar, x0, y0 - 1, z + 1, cob * 16, n);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 14) {
+    // =============================== B producers: (x, co, kz) fixed per (thread, j) ===============================
+    const int tp = threadIdx.x - 64;
+    const int tx = tp & 15;
+    int tkz[2], tco[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tb = tp + 384 * j;
+      tco[j] = (tb >> 4) & 15; tkz[j] = tb >> 8;
+    }
+    int q = -1, z = t0 % a.D;
+    for (int t = t0; t < t1; ++t) {
+      const int k = t - t0, s = k & 1, use = k >> 1;
+      q += ((k == 0) || (z == 0)) ? 3 : 1;
+      if (++z == a.D) z = 0;
+      mbar_wait(&rawfull[k % 3], (k / 3) & 1);
+      float v[2][6];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float* p = rawY + ((q - tkz[j]) % WV_YS) * (WV_RAW_BYTES / 4) + tco[j] * 96 + tx;  // plane z - kz + 1
+#pragma unroll
+        for (int r = 0; r < 6; ++r) v[j][r] = p[r * 16];
+      }
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      uint8_t* st = smem + s * WU_STAGE_BYTES + 2 * WU_A_BYTES;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {  // dY row y0 + e - ky + 1  =  v[e - ky + 2]
+            const float val = v[j][e - ky + 2];
+            h[e] = __uint_as_float(__float_as_uint(val) & 0xffffe000u);
+            l[e] = val - h[e];
+          }
+          const int off = tx * WU_BP + ((tkz[j] * 3 + ky) * 16 + tco[j]) * 16;
+          *reinterpret_cast<float4*>(st + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(st + WU_B_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+      mbar_arrive(&consumed[k % 3]);
+    }
+  } else {
+    // =============================== A producers: (xc, ci) fixed per (thread, j) ===============================
+    // lanes 0..7 of every quarter warp hold eight different ci (16 B apart in the tile): conflict-free 16-byte stores
+    const int w = warp - 14;
+    int txc[6], tci[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int g = w + 2 * j;  // 12 groups of 32 tasks: (ci half, four chunks)
+      tci[j] = (lane & 7) + 8 * (g & 1);
+      txc[j] = (lane >> 3) + 4 * (g >> 1);
+    }
+    for (int t = t0; t < t1; ++t) {
+      const int k = t - t0, s = k & 1, use = k >> 1;
+      mbar_wait(&rawfull[k % 3], (k / 3) & 1);
+      const float* xs = rawX + (k % WV_XS) * (WV_RAW_BYTES / 4);
+      float v[6][4];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        // chunk xc holds input x = x0 - 1 + xc = raw column xc + 3; chunks past 20 feed only the unused rows t >= 3
+        const bool ok = txc[j] + 3 < 24;
+        const float* p = xs + tci[j] * 96 + txc[j] + 3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[j][r] = ok ? p[r * 24] : 0.f;
+      }
+      if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
+      uint8_t* st = smem + s * WU_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = __uint_as_float(__float_as_uint(v[j][e]) & 0xffffe000u);
+          l[e] = v[j][e] - h[e];
+        }
+        const int off = (txc[j] * 16 + tci[j]) * 16;
+        *reinterpret_cast<float4*>(st + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(st + WU_A_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+      mbar_arrive(&consumed[k % 3]);
+    }
+  }
+
+  // ---- final read of the accumulator: rows 16*t + ci (t = kx < 3), columns (kz*3+ky)*16 + co ----
+  if (warp == 4 || warp == 5) {
+    mbar_wait(&done, 0);
+    tc_fence_after();
+    const int r = (warp - 4) * 32 + lane;
+    const int kx = r >> 4, ci = cib * 16 + (r & 15);
+    float* pr = a.partials + (int64_t)region * a.region_stride;
+#pragma unroll 1
+    for (int g = 0; g < 9; ++g) {
+      float v16[16];
+      tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 16), v16);
+      tmem_ld_wait();
+      if (kx < 3 && ci < a.C) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int co = cob * 16 + c;
+          if (co < a.Cout) pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + g * 3 + kx] = v16[c];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+}
