@@ -873,7 +873,7 @@ int launch_umma(const UmmaArgs& a, cudaStream_t stream) {
     cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
     configured = true;
   }
-  dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N);
+  dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N * a.nco);
   conv3d_umma_kernel<<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
   return da_check_launch("conv3d_umma");
 }
@@ -900,16 +900,28 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, float* 
   a.tiles_x = (g.Wo + UM_TX - 1) / UM_TX; a.tiles_y = (g.Ho + UM_TY - 1) / UM_TY;
   // planes per CTA: enough CTAs for ~4 waves, at least 8 planes to amortise the two-plane pipeline fill
   int zg = g.Do;
-  const int xy = a.tiles_x * a.tiles_y * g.N;
-  while (zg > 8 && (int64_t)xy * ((g.Do + zg - 1) / zg) < 4 * DA_NUM_SMS) zg = (zg + 1) / 2;
-  a.zg = zg;
-  for (int ib = 0; ib < nco; ++ib)
-    for (int ik = 0; ik < nk; ++ik) {
-      a.wimg = wp + (int64_t)(ib * nk + ik) * (UMMA_IMG_BYTES / 4);
-      a.c0 = ik * KC; a.co0 = ib * CB; a.accumulate = ik > 0; a.last = ik == nk - 1;
-      rc = launch_umma(a, stream);
-      if (rc) return rc;
+  const int xy = a.tiles_x * a.tiles_y * g.N * nco;
+  // planes per CTA: minimise waves x (planes per CTA + pipeline fill); one CTA per SM
+  {
+    int64_t best = -1;
+    for (int groups = 1; groups <= g.Do; ++groups) {
+      const int cand = (g.Do + groups - 1) / groups;
+      if (cand < 4 && groups > 1) break;
+      const int64_t ctas = (int64_t)xy * ((g.Do + cand - 1) / cand);
+      const int64_t cost = ((ctas + DA_NUM_SMS - 1) / DA_NUM_SMS) * (cand + 3);
+      if (best < 0 || cost < best) { best = cost; zg = cand; }
     }
+  }
+  a.zg = zg;
+  // the channel chunks accumulate through the output tensor (serial launches); the output-channel blocks are
+  // independent and share each launch (grid.z)
+  a.nco = nco; a.img_stride = (int64_t)nk * (UMMA_IMG_BYTES / 4);
+  for (int ik = 0; ik < nk; ++ik) {
+    a.wimg = wp + (int64_t)ik * (UMMA_IMG_BYTES / 4);
+    a.c0 = ik * KC; a.accumulate = ik > 0; a.last = ik == nk - 1;
+    rc = launch_umma(a, stream);
+    if (rc) return rc;
+  }
   return DA_OK;
 }
 
@@ -948,7 +960,7 @@ inline int repack(const float* src, float* dst, int d0, int d1, int T, int a_is_
 
 inline int cpad(int c) { return (int)pad_to(c, c >= 16 ? 16 : (c > 4 ? 8 : 4)); }
 
-constexpr int WG_MAX_REGIONS = 128;
+constexpr int WG_MAX_REGIONS = 148;
 inline int wg_region_cap(int64_t count) {
   int64_t r = ((int64_t)32 << 20) / (count > 0 ? count : 1);
   if (r > WG_MAX_REGIONS) r = WG_MAX_REGIONS;
@@ -1097,48 +1109,77 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
   const int Cin = C1 + C2;
   const int64_t count = (int64_t)Cin * Cout * 27;
   const int tiles_x = (Wi + WU_XT - 1) / WU_XT, tiles_y = (Hi + WU_YT - 1) / WU_YT;
-  const int ntiles = N * Di * tiles_y * tiles_x;
-  const int a_ch = transposed ? Cout : Cin, b_ch = transposed ? Cin : Cout;
-  const int groups = ((a_ch + 15) / 16) * ((b_ch + 15) / 16);
-  int nregions = (2 * DA_NUM_SMS + groups / 2) / groups;
-  if (nregions > cap) nregions = cap;
-  if (nregions > ntiles) nregions = ntiles;
-  if (nregions < 1) nregions = 1;
-  const int tpr = (ntiles + nregions - 1) / nregions;
-  nregions = (ntiles + tpr - 1) / tpr;
-  const bool use_tma = !tma_disabled() && (Wi & 3) == 0 && Wi >= 24 && Hi >= 6;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WU_SMEM_BYTES);
     cudaFuncSetAttribute(conv3d_wgrad_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WV_SMEM_BYTES);
     configured = true;
   }
-  auto launch = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off) -> int {
-    WgUmmaArgs a;
-    a.x = xin; a.dy = gout; a.partials = partials;
-    a.N = N; a.C = C; a.ci_off = ci_off; a.Cin_total = Cin_total_; a.Cout = Cout_; a.co_off = co_off;
-    a.region_stride = count; a.D = Di; a.H = Hi; a.W = Wi;
-    a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_per_region = tpr; a.ntiles = ntiles;
-    a.nCoB = (Cout_ + 15) / 16;
-    dim3 grid(((C + 15) / 16) * a.nCoB, nregions);
-    if (use_tma && aligned16(xin) && aligned16(gout)) {
-      CUtensorMap mx, mdy;
-      int r = da_make_volume_map(&mx, xin, N, C, Di, Hi, Wi, 24, 4, 1, 16);
-      if (!r) r = da_make_volume_map(&mdy, gout, N, Cout_, Di, Hi, Wi, 16, 6, 1, 16);
-      if (r) return r;
-      conv3d_wgrad_umma_tma_kernel<<<grid, WU_THREADS, WV_SMEM_BYTES, stream>>>(mx, mdy, a);
-      return da_check_launch("conv3d_wgrad_umma_tma");
+  int rc, nregions;
+  const bool use_tma = !tma_disabled() && (Wi & 3) == 0 && Wi >= 24 && Hi >= 6 && aligned16(x1) && aligned16(x2) && aligned16(dy);
+  if (use_tma) {
+    // one launch: halo-side blocks x plain-side blocks x one wave of CTAs.  Work units = (column, z segment) dealt
+    // round-robin, so CTAs that run together walk neighbouring columns in lockstep (DRAM pages, L2 lines shared);
+    // the segment count minimises rounds x (planes per unit + pipeline fill).
+    WgUmmaTmaArgs a;
+    const float* h1 = transposed ? dy : x1; const float* h2 = transposed ? nullptr : x2;
+    const float* p1 = transposed ? x1 : dy; const float* p2 = transposed ? x2 : nullptr;
+    a.H1 = transposed ? Cout : C1; a.H2 = transposed ? 0 : C2;
+    a.P1 = transposed ? C1 : Cout; a.P2 = transposed ? C2 : 0;
+    a.nH1 = (a.H1 + 15) / 16; a.nP1 = (a.P1 + 15) / 16;
+    const int nHB = a.nH1 + (a.H2 + 15) / 16;
+    a.nPB = a.nP1 + (a.P2 + 15) / 16;
+    const int groups = nHB * a.nPB;
+    nregions = DA_NUM_SMS / groups;
+    if (nregions > cap) nregions = cap;
+    if (nregions < 1) nregions = 1;
+    a.ncols = N * tiles_y * tiles_x; a.zlen = Di; a.nunits = a.ncols;
+    int64_t best = -1;
+    for (int segs = 1; segs <= Di; ++segs) {
+      const int cand = (Di + segs - 1) / segs;
+      if (cand < 8 && segs > 1) break;
+      const int64_t units = (int64_t)a.ncols * ((Di + cand - 1) / cand);
+      const int64_t cost = ((units + nregions - 1) / nregions) * (cand + 3);
+      if (best < 0 || cost < best) { best = cost; a.zlen = cand; a.nunits = (int)units; }
     }
-    conv3d_wgrad_umma_kernel<<<grid, WU_THREADS, WU_SMEM_BYTES, stream>>>(a);
-    return da_check_launch("conv3d_wgrad_umma");
-  };
-  int rc;
-  if (!transposed) {
-    rc = launch(x1, C1, 0, Cin, dy, Cout, 0);
-    if (!rc && C2) rc = launch(x2, C2, C1, Cin, dy, Cout, 0);
+    if (nregions > a.nunits) nregions = a.nunits;
+    a.partials = partials; a.region_stride = count; a.D = Di; a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+    CUtensorMap mh1, mh2, mp1, mp2;
+    rc = da_make_volume_map(&mh1, h1, N, a.H1, Di, Hi, Wi, 24, 4, 1, 16);
+    if (!rc) rc = a.H2 ? da_make_volume_map(&mh2, h2, N, a.H2, Di, Hi, Wi, 24, 4, 1, 16) : (mh2 = mh1, 0);
+    if (!rc) rc = da_make_volume_map(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 6, 1, 16);
+    if (!rc) rc = a.P2 ? da_make_volume_map(&mp2, p2, N, a.P2, Di, Hi, Wi, 16, 6, 1, 16) : (mp2 = mp1, 0);
+    if (rc) return rc;
+    conv3d_wgrad_umma_tma_kernel<<<dim3(groups, nregions), WU_THREADS, WV_SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+    rc = da_check_launch("conv3d_wgrad_umma_tma");
   } else {
-    rc = launch(dy, Cout, 0, Cout, x1, C1, 0);
-    if (!rc && C2) rc = launch(dy, Cout, 0, Cout, x2, C2, C1);
+    const int ntiles = N * Di * tiles_y * tiles_x;
+    const int a_ch = transposed ? Cout : Cin, b_ch = transposed ? Cin : Cout;
+    const int groups = ((a_ch + 15) / 16) * ((b_ch + 15) / 16);
+    nregions = (2 * DA_NUM_SMS + groups / 2) / groups;
+    if (nregions > cap) nregions = cap;
+    if (nregions > ntiles) nregions = ntiles;
+    if (nregions < 1) nregions = 1;
+    const int tpr = (ntiles + nregions - 1) / nregions;
+    nregions = (ntiles + tpr - 1) / tpr;
+    auto launch = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off) -> int {
+      WgUmmaArgs a;
+      a.x = xin; a.dy = gout; a.partials = partials;
+      a.N = N; a.C = C; a.ci_off = ci_off; a.Cin_total = Cin_total_; a.Cout = Cout_; a.co_off = co_off;
+      a.region_stride = count; a.D = Di; a.H = Hi; a.W = Wi;
+      a.tiles_x = tiles_x; a.tiles_y = tiles_y; a.tiles_per_region = tpr; a.ntiles = ntiles;
+      a.nCoB = (Cout_ + 15) / 16;
+      dim3 grid(((C + 15) / 16) * a.nCoB, nregions);
+      conv3d_wgrad_umma_kernel<<<grid, WU_THREADS, WU_SMEM_BYTES, stream>>>(a);
+      return da_check_launch("conv3d_wgrad_umma");
+    };
+    if (!transposed) {
+      rc = launch(x1, C1, 0, Cin, dy, Cout, 0);
+      if (!rc && C2) rc = launch(x2, C2, C1, Cin, dy, Cout, 0);
+    } else {
+      rc = launch(dy, Cout, 0, Cout, x1, C1, 0);
+      if (!rc && C2) rc = launch(dy, Cout, 0, Cout, x2, C2, C1);
+    }
   }
   if (rc) return rc;
   reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);

@@ -48,10 +48,11 @@ struct UmmaCfg {
 
 struct UmmaArgs {
   const float* x1; const float* x2; int C1, C2;
-  const float* wimg;          // prepared weight image for this (co block, channel chunk)
+  const float* wimg;          // prepared weight image of (co block 0, this channel chunk); block ib is img_stride floats further
+  int64_t img_stride; int nco; // output-channel blocks of the layer = blockIdx.z % nco
   const float* bias; float* out;
   int N, D, H, W, Cout;
-  int c0, co0;                // first input channel of this chunk, first output channel of this block
+  int c0;                     // first input channel of this chunk
   int accumulate, last;       // add to the existing output; apply bias + activation
   int act; float slope;
   int tiles_x, tiles_y, zg;   // z planes per CTA
@@ -122,7 +123,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
   const int z0 = blockIdx.y * a.zg;
   const int zcount = min(a.zg, a.D - z0);
   const int nsteps = zcount + 2;  // input planes z0-1 .. z0+zcount
-  const int n = blockIdx.z;
+  const int n = blockIdx.z / a.nco, ib = blockIdx.z % a.nco;  // output-channel blocks of one layer share a launch
+  const int co0 = ib * UM_CB;
+  const float* wimg = a.wimg + (int64_t)ib * a.img_stride;
   const int64_t HW = (int64_t)a.H * a.W, V = HW * a.D;
 
   // ---- one-time setup: barriers, weights, zero the ring tails, TMEM (allocated, then zeroed by the epilogue warps) --
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < Cfg::W_FLOATS / 4; i += UM_THREADS)
-    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(a.wimg) + i);
+    reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wimg) + i);
   // rows UM_PLANE .. UM_PFA of every chunk are only read by discarded accumulator rows; zero them once (no NaN patterns)
   for (int i = threadIdx.x; i < 3 * 2 * NCH * (UM_PFA - UM_PLANE); i += UM_THREADS) {
     const int t = i % (UM_PFA - UM_PLANE), c = i / (UM_PFA - UM_PLANE);
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     // full L2 round trip per output channel (measured: 6.2k of the 7.1k cycles of a plane step)
     float bv[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) bv[c] = (a.last && a.bias && a.co0 + c < a.Cout) ? __ldg(a.bias + a.co0 + c) : 0.f;
+    for (int c = 0; c < 16; ++c) bv[c] = (a.last && a.bias && co0 + c < a.Cout) ? __ldg(a.bias + co0 + c) : 0.f;
     const bool do_act = a.last && a.act;
     long long e_wait = 0, e_tmem = 0, e_bar = 0, e_out = 0;
     const long long e_begin = clock64();
@@ -282,11 +285,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       const int ol = pi - 2;                 // output plane completed by this step (local index), if >= 0
       const int blk = (pi + 1) % 3;          // = (pi - 2) mod 3
       const bool live = ol >= 0;             // ol < zcount always (nsteps = zcount + 2)
-      float* op = a.out + ((int64_t)n * a.Cout + a.co0) * V + (int64_t)(z0 + ol) * HW + (int64_t)gy * a.W + gx;
+      float* op = a.out + ((int64_t)n * a.Cout + co0) * V + (int64_t)(z0 + ol) * HW + (int64_t)gy * a.W + gx;
       // the previous chunks' partial output does not depend on this step's MMAs: fetch it before waiting for them
       float old[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) old[c] = (a.accumulate && live && valid && a.co0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
+      for (int c = 0; c < 16; ++c) old[c] = (a.accumulate && live && valid && co0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
       const long long e0 = clock64();
       mbar_wait(&acc_full[mt], pi & 1);
       const long long e1 = clock64();
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
         const float left = __shfl_sync(0xffffffffu, v[0][c], (lane + 31) & 31);
         const float right = __shfl_sync(0xffffffffu, v[2][c], (lane + 1) & 31);
         float r = v[1][c] + left + right + old[c];
-        const int co = a.co0 + c;
+        const int co = co0 + c;
         r += bv[c];
         if (do_act) r = r > 0.f ? r : r * a.slope;
         if (valid && co < a.Cout && !(a.flags & 1)) op[(int64_t)c * V] = r;

@@ -263,17 +263,37 @@ static_assert(WV_RAW_OFF % 128 == 0, "TMA destination alignment");
 constexpr int WV_SMEM_BYTES = WV_RAW_OFF + (WV_YS + WV_XS) * WV_RAW_BYTES + 128;
 constexpr int WV_NPROD = 448;
 
+struct WgUmmaTmaArgs {
+  float* partials;  // [region][P1+P2][H1+H2][27]
+  int64_t region_stride;
+  int H1, H2, P1, P2;   // channels of the halo-side tensors (x, or dy when transposed) and of the plain-side tensors
+  int nH1, nP1, nPB;    // 16-channel blocks of the first halo tensor / first plain tensor, plain blocks in total
+  int D;
+  int tiles_x, tiles_y;
+  int ncols, zlen, nunits;  // work unit = (column, z segment of zlen planes); unit u -> CTA u % gridDim.y
+};
+
 __global__ void __launch_bounds__(WU_THREADS, 1)
-conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy, WgUmmaArgs a) {
+conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant__ CUtensorMap map_h2,
+                             const __grid_constant__ CUtensorMap map_p1, const __grid_constant__ CUtensorMap map_p2, WgUmmaTmaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full[2], empty[2], rawfull[3], consumed[3], done;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cob = blockIdx.x % a.nCoB, cib = blockIdx.x / a.nCoB;
+  // channel blocks: halo side (rows of dW's inner index) and plain side, each possibly split over two tensors (the
+  // concatenation is never materialised); a block never straddles the two
+  int cob = blockIdx.x % a.nPB, cib = blockIdx.x / a.nPB;
+  const bool h2 = cib >= a.nH1, p2 = cob >= a.nP1;
+  if (h2) cib -= a.nH1;
+  if (p2) cob -= a.nP1;
+  const CUtensorMap* map_x = h2 ? &map_h2 : &map_h1;
+  const CUtensorMap* map_dy = p2 ? &map_p2 : &map_p1;
+  const int hC = h2 ? a.H2 : a.H1, pC = p2 ? a.P2 : a.P1;     // channels of the chosen tensors
+  const int hg0 = (h2 ? a.H1 : 0), pg0 = (p2 ? a.P1 : 0);     // their offsets in the concatenated index
   const int region = blockIdx.y;
-  // tile order: z fastest, then bx, by, n
-  const int t0 = region * a.tiles_per_region, t1 = min(a.ntiles, t0 + a.tiles_per_region);
+  // work units (column, z segment) are dealt round-robin: CTAs running together walk neighbouring columns in lockstep
+  const int R = gridDim.y;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&full[i], WV_NPROD); mbar_init(&empty[i], 1); }
@@ -300,8 +320,10 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __
     const uint64_t adesc0 = umma_desc(0, 256, 128), bdesc0 = umma_desc(0, WU_BP, 128);
     const uint32_t base_s = smem_u32(smem);
     uint32_t first = 1;
-    for (int t = t0; t < t1; ++t) {
-      const int k = t - t0, s = k & 1;
+    int ntl = 0;
+    for (int u = region; u < a.nunits; u += R) { const int zb = (u / a.ncols) * a.zlen; ntl += min(a.D, zb + a.zlen) - zb; }
+    for (int k = 0; k < ntl; ++k) {
+      const int s = k & 1;
       mbar_wait(&full[s], (k >> 1) & 1);
       tc_fence_after();
       if (elected) {
@@ -324,32 +346,34 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __
   } else if (warp == 1) {
     // =============================== TMA issue ===============================
     if (lane == 0) {
-      tma_prefetch_desc(&map_x);
-      tma_prefetch_desc(&map_dy);
+      tma_prefetch_desc(map_x);
+      tma_prefetch_desc(map_dy);
       int q = -1;  // sequence number of the newest dY plane in the ring
-      for (int t = t0; t < t1; ++t) {
-        const int k = t - t0;
-        const int z = t % a.D;
-        int col = t / a.D;
+      int k = 0;
+      for (int u = region; u < a.nunits; u += R) {
+        int col = u % a.ncols;
+        const int zb = (u / a.ncols) * a.zlen, ze = min(a.D, zb + a.zlen);
         const int bx = col % a.tiles_x; col /= a.tiles_x;
         const int by = col % a.tiles_y;
         const int n = col / a.tiles_y;
         const int x0 = bx * WU_XT, y0 = by * WU_YT;
-        const bool fresh = (k == 0) || (z == 0);  // new column: all three planes; otherwise only plane z+1
+        for (int z = zb; z < ze; ++z, ++k) {
+        const bool fresh = z == zb;  // new unit: all three planes; otherwise only plane z+1
         // slots about to be overwritten were last read by tile k-1 (fresh) or k-3 (steady state)
         const int dep = fresh ? k - 1 : k - 3;
         if (dep >= 0) mbar_wait(&consumed[dep % 3], (dep / 3) & 1);
         uint64_t* bar = &rawfull[k % 3];
         mbar_expect_tx(bar, (uint32_t)WV_RAW_BYTES * (fresh ? 4u : 2u));
-        tma_load_5d(rawX + (k % WV_XS) * (WV_RAW_BYTES / 4), &map_x, bar, x0 - 4, y0, z, cib * 16, n);
+        tma_load_5d(rawX + (k % WV_XS) * (WV_RAW_BYTES / 4), map_x, bar, x0 - 4, y0, z, cib * 16, n);
         if (fresh) {
-          tma_load_5d(rawY + ((q + 1) % WV_YS) * (WV_RAW_BYTES / 4), &map_dy, bar, x0, y0 - 1, z - 1, cob * 16, n);
-          tma_load_5d(rawY + ((q + 2) % WV_YS) * (WV_RAW_BYTES / 4), &map_dy, bar, x0, y0 - 1, z, cob * 16, n);
+          tma_load_5d(rawY + ((q + 1) % WV_YS) * (WV_RAW_BYTES / 4), map_dy, bar, x0, y0 - 1, z - 1, cob * 16, n);
+          tma_load_5d(rawY + ((q + 2) % WV_YS) * (WV_RAW_BYTES / 4), map_dy, bar, x0, y0 - 1, z, cob * 16, n);
           q += 3;
         } else {
           q += 1;
         }
-        tma_load_5d(rawY + (q % WV_YS) * (WV_RAW_BYTES / 4), &map_dy, bar, x0, y0 - 1, z + 1, cob * 16, n);
+        tma_load_5d(rawY + (q % WV_YS) * (WV_RAW_BYTES / 4), map_dy, bar, x0, y0 - 1, z + 1, cob * 16, n);
+        }
       }
     }
     __syncwarp();
@@ -363,11 +387,12 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __
       const int tb = tp + 384 * j;
       tco[j] = (tb >> 4) & 15; tkz[j] = tb >> 8;
     }
-    int q = -1, z = t0 % a.D;
-    for (int t = t0; t < t1; ++t) {
-      const int k = t - t0, s = k & 1, use = k >> 1;
-      q += ((k == 0) || (z == 0)) ? 3 : 1;
-      if (++z == a.D) z = 0;
+    int q = -1, k = 0;
+    for (int u = region; u < a.nunits; u += R) {
+      const int zb = (u / a.ncols) * a.zlen, ze = min(a.D, zb + a.zlen);
+      for (int z = zb; z < ze; ++z, ++k) {
+      const int s = k & 1, use = k >> 1;
+      q += (z == zb) ? 3 : 1;
       mbar_wait(&rawfull[k % 3], (k / 3) & 1);
       float v[2][6];
 #pragma unroll
@@ -397,6 +422,7 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __
       fence_proxy_async();
       mbar_arrive(&full[s]);
       mbar_arrive(&consumed[k % 3]);
+      }
     }
   } else {
     // =============================== A producers: (xc, ci) fixed per (thread, j) ===============================
@@ -409,8 +435,10 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __
       tci[j] = (lane & 7) + 8 * (g & 1);
       txc[j] = (lane >> 3) + 4 * (g >> 1);
     }
-    for (int t = t0; t < t1; ++t) {
-      const int k = t - t0, s = k & 1, use = k >> 1;
+    int ntl = 0;
+    for (int u = region; u < a.nunits; u += R) { const int zb = (u / a.ncols) * a.zlen; ntl += min(a.D, zb + a.zlen) - zb; }
+    for (int k = 0; k < ntl; ++k) {
+      const int s = k & 1, use = k >> 1;
       mbar_wait(&rawfull[k % 3], (k / 3) & 1);
       const float* xs = rawX + (k % WV_XS) * (WV_RAW_BYTES / 4);
       float v[6][4];
@@ -454,11 +482,11 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __
       float v16[16];
       tmem_ld16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 16), v16);
       tmem_ld_wait();
-      if (kx < 3 && ci < a.C) {
+      if (kx < 3 && ci < hC) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int co = cob * 16 + c;
-          if (co < a.Cout) pr[((int64_t)(a.co_off + co) * a.Cin_total + a.ci_off + ci) * 27 + g * 3 + kx] = v16[c];
+          if (co < pC) pr[((int64_t)(pg0 + co) * (a.H1 + a.H2) + hg0 + ci) * 27 + g * 3 + kx] = v16[c];
         }
       }
     }
