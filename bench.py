@@ -226,7 +226,7 @@ def run_ours(args):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
-        def wgrad():   # largest share of the step (ncu launch list, profiles/r01_launches_tcgen05.csv): the FFMA weight gradient
+        def wgrad():   # tcgen05 weight gradient (second largest share of the step)
             _lib.call("da_conv3d_wgrad", P(x1), 32, P(x2), 16, P(dy), 0, P(gw), P(gb), 1, SIZE[0], SIZE[1], SIZE[2], 16, 3, 1, 1, P(wsw), nbw, st)
 
         def fwd():     # tcgen05 3xTF32 forward (three 16-channel chunks accumulate)
@@ -248,28 +248,33 @@ def run_ours(args):
         k_bytes = 4.0 * (48 * V + 16 * V + 16 * 48 * 27)        # read X (both sources) + dY, write dW
         f_bytes = 4.0 * (48 * V + 16 * V + 16 * 48 * 27)        # read X, W, write Y
         k_flop = 2.0 * 27 * 48 * 16 * V
-        ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # TFLOP/s: SMs x FP32 lanes x 2 x max SM clock (nominal, not measured)
         tf32_peak = None
         try:
             tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
         except Exception:
             tf32_peak = 1590.0 / 2.0
         del x1, x2, w, dy, gw, gb, wsw
-        roofline = {"bound": "hbm", "kernel": "conv3d_wgrad_tma_kernel (decBlock2.0 weight gradient, cat(32,16) x dY16 @160x192x160; 31% of the step)",
-                    "achieved": k_bytes / (wg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": k_bytes / (wg_ms * 1e-3) / 1e9 / peak, "traffic": 1.292e9,
-                    "traffic_source": "ncu --set full, profiles/r01_ncu_c_wgrad_tma_12warps.csv (dram read 1286.5 MB + write 5.6 MB per launch)",
-                    "peak_source": peak_src, "launch_ms": wg_ms, "algorithmic_bytes_per_launch": k_bytes,
-                    "fp32_tflops": k_flop / (wg_ms * 1e-3) / 1e12, "fp32_frac_of_ffma_peak": k_flop / (wg_ms * 1e-3) / 1e12 / ffma_peak,
-                    "note": "exact-fp32 FFMA kernel: bound by the FP32 pipe, not HBM (DESIGN.md 3); the HBM fraction is reported as the contract asks",
+        # dominant kernel of the step (profiles/r01_launches_step_tcgen05_wgrad.csv: conv3d_umma_kernel 28 %, conv3d_wgrad_umma_tma_kernel 22 %)
+        roofline = {"bound": "tensor", "kernel": "conv3d_umma_kernel x3 channel-chunk launches (decBlock2.0 forward cat(32,16) -> 16 @160x192x160; tcgen05 kind::tf32, 3xTF32 split)",
+                    "achieved": 3.0 * k_flop / (fw_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": 3.0 * k_flop / (fw_ms * 1e-3) / 1e12 / tf32_peak,
+                    "useful_fp32_equivalent_tflops": k_flop / (fw_ms * 1e-3) / 1e12,
+                    "traffic": 3 * 595.0e6,
+                    "traffic_source": "ncu --set full, profiles/r01_ncu_c_conv_umma_tcgen05.csv: dram 318 MB read + 277 MB write per chunk launch, three launches per layer",
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 runs at half the bf16 rate); achieved counts the three TF32 MMAs per fp32 product",
+                    "launch_ms": fw_ms, "algorithmic_flop_per_launch": k_flop, "algorithmic_bytes_per_launch": f_bytes,
+                    "hbm_achieved_gbs": f_bytes / (fw_ms * 1e-3) / 1e9, "hbm_frac": f_bytes / (fw_ms * 1e-3) / 1e9 / peak, "hbm_peak": peak, "hbm_peak_source": peak_src,
                     "step": {"algorithmic_bytes": ALGO_BYTES_STEP, "achieved": ALGO_BYTES_STEP / (ms * 1e-3) / 1e9,
                              "frac": ALGO_BYTES_STEP / (ms * 1e-3) / 1e9 / peak}}
-        roofline_tensor = {"bound": "tensor", "kernel": "conv3d_umma_kernel x3 chunks (decBlock2.0 forward, tcgen05 kind::tf32, 3xTF32 split; 22% of the step)",
-                           "achieved": 3.0 * k_flop / (fw_ms * 1e-3) / 1e12, "useful_fp32_equivalent": k_flop / (fw_ms * 1e-3) / 1e12,
-                           "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * k_flop / (fw_ms * 1e-3) / 1e12 / tf32_peak,
-                           "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 runs at half the bf16 rate)",
-                           "launch_ms": fw_ms, "hbm_achieved_gbs": f_bytes / (fw_ms * 1e-3) / 1e9, "hbm_frac": f_bytes / (fw_ms * 1e-3) / 1e9 / peak,
-                           "ncu": "profiles/r01_ncu_c_conv_umma_tcgen05.csv: tensor pipe active 50 %, dram 318 MB read + 277 MB write per chunk launch"}
+        roofline_wgrad = {"bound": "tensor", "kernel": "conv3d_wgrad_umma_tma_kernel (decBlock2.0 weight gradient, cat(32,16) x dY16 @160x192x160; tcgen05 3xTF32, one launch) + region reduce + bias sum",
+                          "achieved": 3.0 * k_flop / (wg_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                          "frac": 3.0 * k_flop / (wg_ms * 1e-3) / 1e12 / tf32_peak,
+                          "useful_fp32_equivalent_tflops": k_flop / (wg_ms * 1e-3) / 1e12,
+                          "traffic": 1.3485e9,
+                          "traffic_source": "ncu --set full, profiles/r01_ncu_d_wgrad_umma_tma.csv (dram read 1343.9 MB + write 4.6 MB; tensor pipe active 79 %)",
+                          "launch_ms": wg_ms, "algorithmic_bytes_per_launch": k_bytes,
+                          "hbm_achieved_gbs": k_bytes / (wg_ms * 1e-3) / 1e9, "hbm_frac": k_bytes / (wg_ms * 1e-3) / 1e9 / peak,
+                          "note": "128-row MMAs carry 48 useful rows (kx = 0..2 x 16 ci): the tensor pipe is 79 % busy while the useful fp32-equivalent rate is what the step sees"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -288,7 +293,7 @@ def run_ours(args):
                            "l2_policy": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": 2.0 * world / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tensor, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_wgrad": roofline_wgrad, "cpu_baseline": cpu,
                 "loss": last}
         print(json.dumps(line), flush=True)
     if world > 1:

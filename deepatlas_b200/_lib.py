@@ -29,10 +29,10 @@ SIGNATURES = {
     "da_dice_workspace_bytes": ("iil", "size"),
     "da_dice_sums_fwd": ("ppiiiilppls", "rc"),
     "da_dice_sums_bwd": ("ppiiiilppppps", "rc"),
-    "da_warp_dice_fwd_workspace_bytes": ("iil", "size"),
+    "da_warp_dice_fwd_workspace_bytes": ("iill", "size"),
     "da_warp_dice_bwd_workspace_bytes": ("il", "size"),
-    "da_warp_dice_sums_fwd": ("ppipiiiiiiiiippls", "rc"),
-    "da_warp_dice_sums_bwd": ("ppipippiiiiiiiipppls", "rc"),
+    "da_warp_dice_sums_fwd": ("ppipiiiiiiiiipppls", "rc"),
+    "da_warp_dice_sums_bwd": ("ppipipppiiiiiiiipppls", "rc"),
     "da_softmax_fwd": ("ppiils", "rc"),
     "da_softmax_bwd": ("pppiils", "rc"),
     "da_argmax_counts": ("ppiiilpps", "rc"),

@@ -153,7 +153,7 @@ class WarpedDiceSumsFunction(torch.autograd.Function):
     term of the joint step; see csrc/warp_dice.cu for the structure of the backward."""
 
     @staticmethod
-    def forward(ctx, prob, phi, labels, add_identity: bool):
+    def forward(ctx, prob, phi, labels, add_identity: bool, deterministic: bool = False):
         prob, phi = _f32(prob, "prob"), _f32(phi, "phi")
         N, C, D, H, W = prob.shape
         if phi.dim() != 5 or phi.shape[0] != N or phi.shape[1] != 3:
@@ -167,17 +167,19 @@ class WarpedDiceSumsFunction(torch.autograd.Function):
         if labels.numel() != N * Do * Ho * Wo:
             raise ValueError("warped_dice_sums: labels must have N*Do*Ho*Wo elements")
         sums = torch.empty((N, 3, C), dtype=torch.float32, device=prob.device)
-        nb = _lib.size("da_warp_dice_fwd_workspace_bytes", N, C, Do * Ho * Wo)
+        nb = _lib.size("da_warp_dice_fwd_workspace_bytes", N, C, Do * Ho * Wo, D * H * W)
         ws = _ws(nb, prob.device)
+        # Wsum: the scattered trilinear weights; produced here, consumed again by the backward
+        wsum = None if deterministic else torch.empty((N, D, H, W), dtype=torch.float32, device=prob.device)
         _lib.call("da_warp_dice_sums_fwd", _p(prob), _p(phi), int(add_identity), _p(labels), _KIND[labels.dtype], N, C,
-                  D, H, W, Do, Ho, Wo, _p(sums), _p(ws), nb, _stream())
-        ctx.save_for_backward(prob, phi, labels)
+                  D, H, W, Do, Ho, Wo, _p(sums), _p(wsum), _p(ws), nb, _stream())
+        ctx.save_for_backward(prob, phi, labels, wsum)
         ctx.add_identity = bool(add_identity)
         return sums
 
     @staticmethod
     def backward(ctx, g):
-        prob, phi, labels = ctx.saved_tensors
+        prob, phi, labels, wsum = ctx.saved_tensors
         N, C, D, H, W = prob.shape
         Do, Ho, Wo = phi.shape[2:]
         g = _f32(g, "grad_sums")
@@ -185,16 +187,17 @@ class WarpedDiceSumsFunction(torch.autograd.Function):
         g_prob = torch.empty_like(prob) if ctx.needs_input_grad[0] else None
         g_phi = torch.empty_like(phi) if ctx.needs_input_grad[1] else None
         if g_prob is None and g_phi is None:
-            return None, None, None, None
-        nb = _lib.size("da_warp_dice_bwd_workspace_bytes", N, D * H * W) if g_prob is not None else 0
-        ws = _ws(nb, prob.device) if g_prob is not None else None
+            return None, None, None, None, None
+        nb = _lib.size("da_warp_dice_bwd_workspace_bytes", N, D * H * W)
+        ws = _ws(nb, prob.device)
         _lib.call("da_warp_dice_sums_bwd", _p(prob), _p(phi), int(ctx.add_identity), _p(labels), _KIND[labels.dtype],
-                  _p(gS), _p(gI), N, C, D, H, W, Do, Ho, Wo, _p(g_prob), _p(g_phi), _p(ws), nb, _stream())
-        return g_prob, g_phi, None, None
+                  _p(gS), _p(gI), _p(wsum), N, C, D, H, W, Do, Ho, Wo, _p(g_prob), _p(g_phi), _p(ws), nb, _stream())
+        return g_prob, g_phi, None, None, None
 
 
-def warped_dice_sums(prob, phi, labels, add_identity=False):
-    return WarpedDiceSumsFunction.apply(prob, phi, labels, add_identity)
+def warped_dice_sums(prob, phi, labels, add_identity=False, deterministic=False):
+    """deterministic=True: gather kernel with a fixed summation order for S (about 5x slower forward)."""
+    return WarpedDiceSumsFunction.apply(prob, phi, labels, add_identity, deterministic)
 
 
 class SoftmaxFunction(torch.autograd.Function):

@@ -63,16 +63,19 @@ int da_dice_sums_bwd(const float* source, const void* target, int target_kind, i
 /* ---- warped Dice sums: the anatomy term dice(grid_sample(P, phi), onehot(S_t)) of the joint step, fused ------
  * (F.grid_sample as at voxel_morph.py:90-91 + DiceLossMultiClass label-target sums, lib/loss.py:433-450,472).
  * prob [N,C,D,H,W]; field [N,3,Do,Ho,Wo]; labels [N,Do,Ho,Wo] (kind 0 uint8, 1 int64, 3 int32); sums [N,3,C].
- * The warped map is never materialised; backward scatters 16 scalars per voxel (see csrc/warp_dice.cu). */
-int64_t da_warp_dice_fwd_workspace_bytes(int N, int C, int64_t Vo);
+ * The warped map is never materialised.  wsum (nullable, [N,D,H,W]) selects the scatter formulation: S_c = <P[c], Wsum>
+ * with Wsum the trilinear weights scattered once (8 atomics + 8 gathers per voxel instead of 8*C gathers); the
+ * forward leaves Wsum there and the backward takes it as wsum_fwd (null = recompute).  wsum = null runs the gather
+ * kernel (fixed summation order).  Backward: 8 atomics + 16 gathers per voxel + dense passes (csrc/warp_dice.cu). */
+int64_t da_warp_dice_fwd_workspace_bytes(int N, int C, int64_t Vo, int64_t Vs);
 int64_t da_warp_dice_bwd_workspace_bytes(int N, int64_t Vs);
 int da_warp_dice_sums_fwd(const float* prob, const float* field, int add_identity, const void* labels, int label_kind,
-                          int N, int C, int D, int H, int W, int Do, int Ho, int Wo, float* sums, void* workspace,
-                          int64_t workspace_bytes, da_stream_t stream);
+                          int N, int C, int D, int H, int W, int Do, int Ho, int Wo, float* sums, float* wsum,
+                          void* workspace, int64_t workspace_bytes, da_stream_t stream);
 int da_warp_dice_sums_bwd(const float* prob, const float* field, int add_identity, const void* labels, int label_kind,
-                          const float* gS, const float* gI, int N, int C, int D, int H, int W, int Do, int Ho, int Wo,
-                          float* grad_prob, float* grad_field, void* workspace, int64_t workspace_bytes,
-                          da_stream_t stream);
+                          const float* gS, const float* gI, const float* wsum_fwd, int N, int C, int D, int H, int W,
+                          int Do, int Ho, int Wo, float* grad_prob, float* grad_field, void* workspace,
+                          int64_t workspace_bytes, da_stream_t stream);
 
 /* channel softmax (F.softmax(dim=1)) materialised for the anatomy branch, where probabilities are warped */
 int da_softmax_fwd(const float* x, float* y, int N, int C, int64_t V, da_stream_t stream);

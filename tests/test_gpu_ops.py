@@ -325,6 +325,19 @@ def test_warped_dice_fused_vs_oracle(cuda, C, size, dtype):
         p2, f2 = prob.to(cuda).requires_grad_(True), phi.to(cuda).requires_grad_(True)
         crit(da.ops.warp3d(p2, f2), lab.to(cuda)).backward()
         assert rel_err(pg.grad, p2.grad) < TOL and rel_err(fg.grad, f2.grad) < TOL
+    # the scatter formulation (default) and the gather kernel (fixed summation order) give the same sums; the
+    # label-driven sums T and I do not depend on the formulation at all
+    s_scatter = da.ops.warped_dice_sums(prob.to(cuda), phi.to(cuda), lab.to(cuda))
+    s_gather = da.ops.warped_dice_sums(prob.to(cuda), phi.to(cuda), lab.to(cuda), deterministic=True)
+    assert rel_err(s_scatter[:, 0], s_gather[:, 0]) < 1e-5
+    assert torch.equal(s_scatter[:, 1], s_gather[:, 1])
+    assert rel_err(s_scatter[:, 2], s_gather[:, 2]) < 1e-5
+    # out-of-range labels (ignored by the one-hot) and a field that leaves the volume: zero padding on both paths
+    lab2 = lab.long().clone(); lab2[:, 0] = C + 3
+    far = phi * 1.6
+    a = da.ops.warped_dice_sums(prob.to(cuda), far.to(cuda), lab2.to(cuda))
+    b = da.ops.warped_dice_sums(prob.to(cuda), far.to(cuda), lab2.to(cuda), deterministic=True)
+    assert rel_err(a, b) < 1e-5
 
 
 @pytest.mark.parametrize("C,size,dtype", [(4, (9, 10, 11), torch.uint8), (32, (8, 12, 16), torch.int64)])
