@@ -25,9 +25,10 @@ constexpr int UM_TX = 40, UM_TY = 6, UM_PX = UM_TX + 2;  // (a 128-byte aligned 
 constexpr int UM_PLANE = (UM_TY + 2) * UM_PX;  // 336 positions staged per plane
 constexpr int UM_PFA = 344;                    // allocated positions per channel chunk (>= 2*128 + 2*PX)
 constexpr int UM_MT = 2;                       // M tiles per plane (2*128 >= TY*PX = 252)
-constexpr int UM_NPROD = 224;                  // producer threads (7 warps): 512 threads in total -> 128 registers each
-constexpr int UM_NEPI = 256;                   // epilogue threads: warp w handles M tile w/4, TMEM lane quadrant w%4
-constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-7 epilogue, 8 MMA issue, 9.. producers
+constexpr int UM_NPROD = 224;                  // producer threads (7 warps)
+constexpr int UM_NEPI = 512;                   // epilogue threads: warp w handles TMEM lane quadrant w%4, M tile (w/4)%2, output-channel half w/8
+constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-15 epilogue, 16 MMA issue, 17.. producers (768 threads, 85 registers)
+constexpr int UM_MMA_WARP = UM_NEPI / 32;
 constexpr int UM_CB = 16, UM_KC = 16;          // output channels per launch, input channels per launch
 constexpr int UM_NB = 3 * UM_CB;               // columns of one accumulator block: (kx, co)
 constexpr int UM_N = 3 * UM_NB;                // MMA N: three blocks = three output planes in flight
@@ -94,6 +95,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -141,7 +154,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     const int t = i % (UM_PFA - UM_PLANE), c = i / (UM_PFA - UM_PLANE);
     reinterpret_cast<float4*>(ring)[c * UM_PFA + UM_PLANE + t] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (warp == 8) {
+  if (warp == UM_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= 9) {
+  if (warp > UM_MMA_WARP) {
     // =============================== producers ===============================
     // thread = one 4-channel chunk (grp) x UM_PPT fixed in-plane positions: everything but the plane offset is loop invariant
     constexpr int TPG = UM_NPROD / NCH;          // 56 threads per channel chunk
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
       mbar_arrive(&plane_full[slot]);
     }
-  } else if (warp == 8) {
+  } else if (warp == UM_MMA_WARP) {
     // =============================== MMA issue ===============================
     uint32_t elected;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
@@ -266,8 +279,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     }
   } else {
     // =============================== epilogue ===============================
-    static_assert(UM_MT == 2 && UM_NEPI == 256, "one epilogue warp per (M tile, lane quadrant)");
-    const int w = warp & 3, mt = warp >> 2, wg = warp;  // wg = mt*4 + w: rows [32*wg, 32*wg + 32) of the 256-row range
+    static_assert(UM_MT == 2 && UM_NEPI == 512 && UM_CB == 16, "one epilogue warp per (M tile, lane quadrant, channel half)");
+    // two warps share every 32-row group and split its 16 output channels: the epilogue is latency bound per warp
+    // (dependent TMEM load -> shuffle -> store chains), so twice the warps halve its share of the plane step
+    const int w = warp & 3, mt = (warp >> 2) & 1, wg = warp & 7, ch0 = (warp >> 3) * 8;  // rows [32*wg, 32*wg + 32)
     const int fc = UM_PX + wg * 32 + lane;
     const int hy = fc / UM_PX, hx = fc - hy * UM_PX;
     const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
@@ -275,9 +290,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     const uint32_t trow = tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)mt * N;
     // bias in registers: a load inside the store loop cannot be hoisted past the stores (possible aliasing) and costs a
     // full L2 round trip per output channel (measured: 6.2k of the 7.1k cycles of a plane step)
-    float bv[16];
+    float bv[8];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) bv[c] = (a.last && a.bias && co0 + c < a.Cout) ? __ldg(a.bias + co0 + c) : 0.f;
+    for (int c = 0; c < 8; ++c) bv[c] = (a.last && a.bias && co0 + ch0 + c < a.Cout) ? __ldg(a.bias + co0 + ch0 + c) : 0.f;
     const bool do_act = a.last && a.act;
     long long e_wait = 0, e_tmem = 0, e_bar = 0, e_out = 0;
     const long long e_begin = clock64();
@@ -285,23 +300,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       const int ol = pi - 2;                 // output plane completed by this step (local index), if >= 0
       const int blk = (pi + 1) % 3;          // = (pi - 2) mod 3
       const bool live = ol >= 0;             // ol < zcount always (nsteps = zcount + 2)
-      float* op = a.out + ((int64_t)n * a.Cout + co0) * V + (int64_t)(z0 + ol) * HW + (int64_t)gy * a.W + gx;
+      float* op = a.out + ((int64_t)n * a.Cout + co0 + ch0) * V + (int64_t)(z0 + ol) * HW + (int64_t)gy * a.W + gx;
       // the previous chunks' partial output does not depend on this step's MMAs: fetch it before waiting for them
-      float old[16];
+      float old[8];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) old[c] = (a.accumulate && live && valid && co0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
+      for (int c = 0; c < 8; ++c) old[c] = (a.accumulate && live && valid && co0 + ch0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
       const long long e0 = clock64();
       mbar_wait(&acc_full[mt], pi & 1);
       const long long e1 = clock64();
       tc_fence_after();
-      float v[3][16];
+      float v[3][8];
       if (live) {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) tmem_ld16(trow + (uint32_t)(blk * NB + kx * UM_CB), v[kx]);
+        for (int kx = 0; kx < 3; ++kx) tmem_ld8(trow + (uint32_t)(blk * NB + kx * UM_CB + ch0), v[kx]);
         tmem_ld_wait();
       }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) tmem_st16_zero(trow + (uint32_t)(blk * NB + kx * UM_CB));
+      for (int kx = 0; kx < 3; ++kx) tmem_st8_zero(trow + (uint32_t)(blk * NB + kx * UM_CB + ch0));
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[mt]);  // block read and cleared: the next step may accumulate into it
@@ -311,11 +326,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       const int eb = pi & 1;
       if (lane == 31) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) edge_s[eb][wg][0][c] = v[0][c];
+        for (int c = 0; c < 8; ++c) edge_s[eb][wg][0][ch0 + c] = v[0][c];
       }
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) edge_s[eb][wg][1][c] = v[2][c];
+        for (int c = 0; c < 8; ++c) edge_s[eb][wg][1][ch0 + c] = v[2][c];
       }
       const long long e2 = clock64();
       named_bar_sync(1, UM_NEPI);
@@ -325,19 +340,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       // wrap around first replaces the value it sends by the neighbouring warp's edge row (its own was published above).
       if (lane == 31) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[0][c] = (wg > 0) ? edge_s[eb][wg - 1][0][c] : 0.f;
+        for (int c = 0; c < 8; ++c) v[0][c] = (wg > 0) ? edge_s[eb][wg - 1][0][ch0 + c] : 0.f;
       }
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) v[2][c] = (wg < 7) ? edge_s[eb][wg + 1][1][c] : 0.f;
+        for (int c = 0; c < 8; ++c) v[2][c] = (wg < 7) ? edge_s[eb][wg + 1][1][ch0 + c] : 0.f;
       }
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < 8; ++c) {
         const float left = __shfl_sync(0xffffffffu, v[0][c], (lane + 31) & 31);
         const float right = __shfl_sync(0xffffffffu, v[2][c], (lane + 1) & 31);
         float r = v[1][c] + left + right + old[c];
-        const int co = co0 + c;
+        const int co = co0 + ch0 + c;
         r += bv[c];
         if (do_act) r = r > 0.f ? r : r * a.slope;
         if (valid && co < a.Cout && !(a.flags & 1)) op[(int64_t)c * V] = r;
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
+  if (warp == UM_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(Cfg::TMEM_COLS) : "memory");
 }
 
 // Weight image of one (16-output-channel block, 16-input-channel chunk):
