@@ -51,6 +51,7 @@ SIGNATURES = {
     "da_umma_debug_read": ("p", "rc"),
     "da_set_conv_impl": ("i", "rc"),
     "da_conv3d_pack_bytes": ("iii", "size"),
+    "da_conv3d_dgrad_workspace_bytes": ("iiiiiiii", "size"),
     "da_conv3d_wgrad_workspace_bytes": ("iii", "size"),
     "da_conv3d_fwd": ("pipipippiiiiiiiiifpls", "rc"),
     "da_conv3d_dgrad": ("ppipiiiiiiiiiiipls", "rc"),

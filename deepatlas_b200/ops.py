@@ -356,7 +356,7 @@ class Conv3dFunction(torch.autograd.Function):
             _lib.call("da_act_bwd", _p(dy), _p(out), float(slope), dy.numel(), _p(g), st)
             dy = g
         dx1 = dx2 = dw = db = None
-        nb = _lib.size("da_conv3d_pack_bytes", Cin, Cout, ks)
+        nb = _lib.size("da_conv3d_dgrad_workspace_bytes", N, Cin, Cout, Di, Hi, Wi, ks, stride)
         ws = _ws(nb, dy.device)
         if ctx.needs_input_grad[0]:
             dx1 = torch.empty_like(x1)

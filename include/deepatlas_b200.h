@@ -119,6 +119,7 @@ int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, int H, 
 int da_umma_debug_read(int64_t* out11); /* debug: cycle counters of the tensor-core conv's MMA warps (DA_UMMA_DEBUG=1) */
 int da_set_conv_impl(int impl); /* 0 = auto (tcgen05 3xTF32 fwd/dgrad, TMA FFMA wgrad), 1 = generic direct kernels, 2 = tiled FFMA only, 3 = tcgen05 forced */
 int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks);
+int64_t da_conv3d_dgrad_workspace_bytes(int N, int Cin, int Cout, int Di, int Hi, int Wi, int ks, int stride); /* >= pack_bytes; stride 2 adds the zero-inserted dy that lets the tcgen05 path run */
 int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks);
 int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed,
                   const float* bias, float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride,
