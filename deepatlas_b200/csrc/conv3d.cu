@@ -761,6 +761,79 @@ int launch_direct(const float* x1, const float* x2, const float* wp, const float
   return da_check_launch("conv3d_direct");
 }
 
+// 1x1x1 convolution, streaming: thread = four consecutive voxels (one float4 per input channel) x CO output channels
+// held in registers; the (small) weight block sits in shared memory and is read by broadcast.  HBM bound: the input is
+// read once per CO block (L2 serves the repeats), the output written once.  w(o, i) = weight[o*so + i*si] covers the
+// forward (so = Cin, si = 1) and the data gradient (so = 1, si = Cin_total, pointer advanced by ci_off).
+constexpr int K1_MAXC = 128;
+template <int CO>
+__global__ void __launch_bounds__(256, 2) conv1x1_stream_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int C1, int C2,
+                                                             const float* __restrict__ weight, int so, int si,
+                                                             const float* __restrict__ bias, float* __restrict__ out, int Cout,
+                                                             int64_t V4, int act, float slope) {
+  __shared__ __align__(16) float sw[K1_MAXC * CO];  // [ci][co]
+  const int Cin = C1 + C2, co0 = blockIdx.y * CO, n = blockIdx.z;
+  for (int i = threadIdx.x; i < Cin * CO; i += 256) {
+    const int ci = i / CO, c = i - ci * CO;
+    sw[i] = co0 + c < Cout ? weight[(int64_t)(co0 + c) * so + (int64_t)ci * si] : 0.f;
+  }
+  __syncthreads();
+  const int64_t i4 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i4 >= V4) return;
+  float4 acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    const float b = (bias && co0 + c < Cout) ? bias[co0 + c] : 0.f;
+    acc[c] = make_float4(b, b, b, b);
+  }
+  const float4* p1 = reinterpret_cast<const float4*>(x1) + (int64_t)n * C1 * V4 + i4;
+  const float4* p2 = x2 ? reinterpret_cast<const float4*>(x2) + (int64_t)n * C2 * V4 + i4 : nullptr;
+#pragma unroll 4
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float4 v = ci < C1 ? __ldcs(p1 + (int64_t)ci * V4) : __ldcs(p2 + (int64_t)(ci - C1) * V4);
+    const float4* w4 = reinterpret_cast<const float4*>(sw + ci * CO);
+#pragma unroll
+    for (int q = 0; q < CO / 4; ++q) {
+      const float4 w = w4[q];
+      acc[4 * q + 0].x = fmaf(w.x, v.x, acc[4 * q + 0].x); acc[4 * q + 0].y = fmaf(w.x, v.y, acc[4 * q + 0].y);
+      acc[4 * q + 0].z = fmaf(w.x, v.z, acc[4 * q + 0].z); acc[4 * q + 0].w = fmaf(w.x, v.w, acc[4 * q + 0].w);
+      acc[4 * q + 1].x = fmaf(w.y, v.x, acc[4 * q + 1].x); acc[4 * q + 1].y = fmaf(w.y, v.y, acc[4 * q + 1].y);
+      acc[4 * q + 1].z = fmaf(w.y, v.z, acc[4 * q + 1].z); acc[4 * q + 1].w = fmaf(w.y, v.w, acc[4 * q + 1].w);
+      acc[4 * q + 2].x = fmaf(w.z, v.x, acc[4 * q + 2].x); acc[4 * q + 2].y = fmaf(w.z, v.y, acc[4 * q + 2].y);
+      acc[4 * q + 2].z = fmaf(w.z, v.z, acc[4 * q + 2].z); acc[4 * q + 2].w = fmaf(w.z, v.w, acc[4 * q + 2].w);
+      acc[4 * q + 3].x = fmaf(w.w, v.x, acc[4 * q + 3].x); acc[4 * q + 3].y = fmaf(w.w, v.y, acc[4 * q + 3].y);
+      acc[4 * q + 3].z = fmaf(w.w, v.z, acc[4 * q + 3].z); acc[4 * q + 3].w = fmaf(w.w, v.w, acc[4 * q + 3].w);
+    }
+  }
+  float4* po = reinterpret_cast<float4*>(out) + ((int64_t)n * Cout + co0) * V4 + i4;
+#pragma unroll
+  for (int c = 0; c < CO; ++c) {
+    if (co0 + c >= Cout) break;
+    float4 r = acc[c];
+    if (act) {
+      r.x = r.x > 0.f ? r.x : r.x * slope; r.y = r.y > 0.f ? r.y : r.y * slope;
+      r.z = r.z > 0.f ? r.z : r.z * slope; r.w = r.w > 0.f ? r.w : r.w * slope;
+    }
+    __stcs(po + (int64_t)c * V4, r);
+  }
+}
+
+// returns -1 if the streaming kernel does not apply (caller falls back to the direct kernel)
+inline int run_conv1x1_stream(const float* x1, const float* x2, int C1, int C2, const float* weight, int so, int si, const float* bias,
+                              float* out, int N, int Cout, int64_t V, int act, float slope, cudaStream_t stream) {
+  if ((V & 3) != 0 || C1 + C2 > K1_MAXC || V < 4096) return -1;
+  if ((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) & 15) != 0) return -1;
+  const int64_t V4 = V / 4;
+  if (Cout > 8) {
+    dim3 grid((unsigned)da_cdiv(V4, 256), (Cout + 15) / 16, N);
+    conv1x1_stream_kernel<16><<<grid, 256, 0, stream>>>(x1, x2, C1, C2, weight, so, si, bias, out, Cout, V4, act, slope);
+  } else {
+    dim3 grid((unsigned)da_cdiv(V4, 256), (Cout + 7) / 8, N);
+    conv1x1_stream_kernel<8><<<grid, 256, 0, stream>>>(x1, x2, C1, C2, weight, so, si, bias, out, Cout, V4, act, slope);
+  }
+  return da_check_launch("conv1x1_stream");
+}
+
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 int g_force_no_tma = -1;
 inline bool tma_disabled() {
@@ -1049,6 +1122,10 @@ DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const
   ConvGeom g{N, C1, C2, Di, Hi, Wi, conv_out(Di, ks, stride, pad), conv_out(Hi, ks, stride, pad), conv_out(Wi, ks, stride, pad),
              Cout, cpad(Cout), stride, pad, act, slope};
   float* wp = (float*)workspace;
+  if (ks == 1 && stride == 1 && pad == 0 && !transposed && !force_direct()) {
+    const int rc1 = run_conv1x1_stream(x1, x2, C1, C2, weight, Cin, 1, bias, out, N, Cout, (int64_t)Di * Hi * Wi, act, slope, stream);
+    if (rc1 >= 0) return rc1;
+  }
   if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
     return transposed ? run_conv_umma(x1, x2, weight, wp, bias, out, g, Cout, 1, 1, 0, stream)
                       : run_conv_umma(x1, x2, weight, wp, bias, out, g, Cin, 0, 0, 0, stream);
@@ -1102,6 +1179,10 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
     // dgrad = conv of dy (Cout channels) with [co][flip tap][ci]; for a transposed layer: no flip, dims swapped
     ConvGeom g{N, Cout, 0, Do, Ho, Wo, Di, Hi, Wi, Cdx, Cp, 1, ks == 3 ? 1 : 0, 0, 0.f};
     DA_REQUIRE(ks == 1 || pad == 1, "da_conv3d_dgrad: k3 needs pad 1");
+    if (ks == 1 && pad == 0 && !transposed && !force_direct()) {
+      const int rc1 = run_conv1x1_stream(dy, nullptr, Cout, 0, weight + ci_off, 1, Cin_total, nullptr, dx, N, Cdx, (int64_t)Di * Hi * Wi, 0, 0.f, stream);
+      if (rc1 >= 0) return rc1;
+    }
     if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
       return transposed ? run_conv_umma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, 0, 0, ci_off, stream)
                         : run_conv_umma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);

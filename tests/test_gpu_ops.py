@@ -177,7 +177,9 @@ CONV_CASES = [
     (16, 0, 32, 3, 2, (20, 24, 40), False),     # stride 2 through the TMA-staged tiled weight gradient (W % 8 == 0)
     (6, 0, 12, 3, 2, (10, 18, 72), False),      # stride 2, ragged channel groups, two x tiles
     (16, 0, 7, 1, 1, (8, 9, 10), False),        # 1x1 head
-    (16, 0, 32, 1, 1, (16, 20, 24), False),     # 1x1 head, 32 classes (streaming k1 weight-gradient kernel)
+    (16, 0, 32, 1, 1, (16, 20, 24), False),     # 1x1 head, 32 classes (streaming k1 kernels, 16-channel blocks)
+    (8, 8, 5, 1, 1, (16, 20, 24), False),       # 1x1 streaming kernel, two sources, 8-channel block partly filled
+    (40, 0, 24, 1, 1, (12, 16, 32), False),     # 1x1 streaming kernel, second channel block partly filled
     (24, 8, 16, 3, 1, (8, 8, 8), True),         # ConvTranspose3d k3 s1 p1, two sources
     (16, 0, 8, 3, 1, (32, 32, 32), True),       # ConvTranspose3d through the tiled kernel
     (6, 0, 16, 3, 1, (32, 32, 32), False),      # TMA path, last channel chunk partial (zero-filled by the TMA unit)
