@@ -895,7 +895,11 @@ int run_conv_tma(const float* x1, const float* x2, const float* weight, float* w
                  int d0, int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
   const int Cin = g.C1 + g.C2;
   const int cin_pad = (Cin + TMA_CK - 1) / TMA_CK * TMA_CK;
-  const int CO = (g.Cop % 16 == 0) ? 16 : (g.Cop % 8 == 0 ? 8 : 4);
+  int CO = (g.Cop % 16 == 0) ? 16 : (g.Cop % 8 == 0 ? 8 : 4);
+  {  // small volumes (the 20x24x20 level): 8-channel blocks double the CTA count when 16-channel blocks leave SMs idle
+    const int64_t tiles = (int64_t)((g.Wo + TX - 1) / TX) * ((g.Ho + TY - 1) / TY) * ((g.Do + TZ - 1) / TZ) * g.N;
+    if (CO == 16 && tiles * (g.Cop / 16) < DA_NUM_SMS) CO = 8;
+  }
   const int64_t total = (int64_t)cin_pad * 27 * g.Cop;
   int blocks = (int)da_cdiv(total, 256);
   if (blocks > 4096) blocks = 4096;
@@ -957,12 +961,8 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, float* 
   const int Cin = g.C1 + g.C2;
   constexpr int CB = UM_CB, KC = UM_KC;
   const int nco = (g.Cout + CB - 1) / CB, nk = (Cin + KC - 1) / KC;
-  for (int ib = 0; ib < nco; ++ib)
-    for (int ik = 0; ik < nk; ++ik) {
-      float* img = wp + (int64_t)(ib * nk + ik) * (UMMA_IMG_BYTES / 4);
-      umma_prep_weights_kernel<<<45, 256, 0, stream>>>(weight, img, d1, a_is_dim0, flip, Cin, ik * KC, g.Cout, b_off, ib * CB);
-    }
-  int rc = da_check_launch("umma_prep_weights", nco * nk);
+  umma_prep_weights_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, wp, d1, a_is_dim0, flip, Cin, KC, g.Cout, b_off, CB);
+  int rc = da_check_launch("umma_prep_weights");
   if (rc) return rc;
   UmmaArgs a;
   a.dbg = umma_dbg_buffer();

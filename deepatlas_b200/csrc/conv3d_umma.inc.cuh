@@ -376,7 +376,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 //   [hi|lo][ky][ci/4][row = t*48 + kx*16 + co][4 floats],  t = 0..4 <-> kz = 2,1,0,2,1.
 // Source indexing as repack_weights_kernel (a = this conv's input channel, b = its output channel).
 __global__ void umma_prep_weights_kernel(const float* __restrict__ src, float* __restrict__ dst, int d1, int a_is_dim0, int flip,
-                                         int A, int c0, int B, int b_off, int co0) {
+                                         int A, int kc, int B, int b_off, int cb) {
+  // grid (blocks, channel chunks, output-channel blocks): all images of a layer in one launch, image (ib, ik) at
+  // dst + (ib * nk + ik) * W_FLOATS
+  const int c0 = blockIdx.y * kc, co0 = blockIdx.z * cb;
+  dst += (int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * UmmaCfg::W_FLOATS;
   const int total = UmmaCfg::W_FLOATS;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 3;

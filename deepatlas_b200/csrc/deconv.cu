@@ -83,12 +83,16 @@ __global__ void __launch_bounds__(DC_THREADS) deconv_k2s2_fwd_kernel(const float
   }
 }
 
-// dX[ci][v] = sum_co sum_pos dY[co][2v+pos] * W[ci][co][pos];  grid (pairs/128, ceil(Cin/4), N)
+// dX[ci][v] = sum_co sum_pos dY[co][2v+pos] * W[ci][co][pos];  grid (pairs/128, ceil(Cin/CI), N).
+// dY (8x the voxels of dX) is read once per CI-block of input channels: CI = 16 keeps the re-reads of a tensor that does
+// not fit L2 at Cin/16 (the first version used 4 channels per block and was DRAM bound on the repeats).
+template <int CI>
 __global__ void __launch_bounds__(DC_THREADS) deconv_k2s2_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                                        float* __restrict__ dx, int Cin, int Cout, int D, int H,
                                                                        int W) {
-  __shared__ __align__(16) float sw[DC_CC * 32];  // [co_local][ci 4][pos 8]
-  const int n = blockIdx.z, ci0 = blockIdx.y * 4;
+  constexpr int CC = 16;                             // output channels staged per chunk
+  __shared__ __align__(16) float sw[CC * CI * 8];    // [co_local][ci][pos 8]
+  const int n = blockIdx.z, ci0 = blockIdx.y * CI;
   const int W2 = (W + 1) / 2;
   const int64_t pairs = (int64_t)D * H * W2, V = (int64_t)D * H * W;
   const int64_t p = (int64_t)blockIdx.x * DC_THREADS + threadIdx.x;
@@ -98,12 +102,14 @@ __global__ void __launch_bounds__(DC_THREADS) deconv_k2s2_dgrad_kernel(const flo
   const bool two = x0 + 1 < W;
   const int Ho = 2 * H, Wo = 2 * W;
   const int64_t Vo = 8 * V;
-  float acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  for (int c0 = 0; c0 < Cout; c0 += DC_CC) {
-    const int cc = min(DC_CC, Cout - c0);
+  float acc[2][CI];
+#pragma unroll
+  for (int c = 0; c < CI; ++c) acc[0][c] = acc[1][c] = 0.f;
+  for (int c0 = 0; c0 < Cout; c0 += CC) {
+    const int cc = min(CC, Cout - c0);
     __syncthreads();
-    for (int i = threadIdx.x; i < cc * 32; i += DC_THREADS) {
-      const int cl = i / 32, r = i % 32, ci = ci0 + r / 8;
+    for (int i = threadIdx.x; i < cc * CI * 8; i += DC_THREADS) {
+      const int cl = i / (CI * 8), r = i % (CI * 8), ci = ci0 + r / 8;
       sw[i] = ci < Cin ? w[((int64_t)ci * Cout + c0 + cl) * 8 + (r % 8)] : 0.f;
     }
     __syncthreads();
@@ -122,20 +128,25 @@ __global__ void __launch_bounds__(DC_THREADS) deconv_k2s2_dgrad_kernel(const flo
           g[1][ab * 2] = two ? q[2] : 0.f; g[1][ab * 2 + 1] = two ? q[3] : 0.f;
         }
       }
-      const float* ws = sw + cl * 32;
+      const float4* ws = reinterpret_cast<const float4*>(sw + cl * CI * 8);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          acc[0][c] = fmaf(g[0][k], ws[c * 8 + k], acc[0][c]);
-          acc[1][c] = fmaf(g[1][k], ws[c * 8 + k], acc[1][c]);
-        }
+      for (int c = 0; c < CI; ++c) {
+        const float4 wa = ws[2 * c], wb = ws[2 * c + 1];
+        acc[0][c] = fmaf(g[0][0], wa.x, acc[0][c]); acc[1][c] = fmaf(g[1][0], wa.x, acc[1][c]);
+        acc[0][c] = fmaf(g[0][1], wa.y, acc[0][c]); acc[1][c] = fmaf(g[1][1], wa.y, acc[1][c]);
+        acc[0][c] = fmaf(g[0][2], wa.z, acc[0][c]); acc[1][c] = fmaf(g[1][2], wa.z, acc[1][c]);
+        acc[0][c] = fmaf(g[0][3], wa.w, acc[0][c]); acc[1][c] = fmaf(g[1][3], wa.w, acc[1][c]);
+        acc[0][c] = fmaf(g[0][4], wb.x, acc[0][c]); acc[1][c] = fmaf(g[1][4], wb.x, acc[1][c]);
+        acc[0][c] = fmaf(g[0][5], wb.y, acc[0][c]); acc[1][c] = fmaf(g[1][5], wb.y, acc[1][c]);
+        acc[0][c] = fmaf(g[0][6], wb.z, acc[0][c]); acc[1][c] = fmaf(g[1][6], wb.z, acc[1][c]);
+        acc[0][c] = fmaf(g[0][7], wb.w, acc[0][c]); acc[1][c] = fmaf(g[1][7], wb.w, acc[1][c]);
+      }
     }
   }
   if (!live) return;
   const int64_t vin = ((int64_t)z * H + y) * W + x0;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < CI; ++c) {
     const int ci = ci0 + c;
     if (ci >= Cin) break;
     float* o = dx + ((int64_t)n * Cin + ci) * V + vin;
@@ -349,8 +360,15 @@ DA_API int da_deconv_k2s2_dgrad(const float* dy, const float* weight, float* dx,
                                 cudaStream_t stream) {
   DA_REQUIRE(dy && weight && dx, "da_deconv_k2s2_dgrad: null pointer");
   const int64_t pairs = (int64_t)D * H * ((W + 1) / 2);
-  dim3 grid((unsigned)da_cdiv(pairs, DC_THREADS), (Cin + 3) / 4, N);
-  deconv_k2s2_dgrad_kernel<<<grid, DC_THREADS, 0, stream>>>(dy, weight, dx, Cin, Cout, D, H, W);
+  // few channels per block only where that is needed to fill the GPU (small volumes)
+  const int64_t nbx = da_cdiv(pairs, DC_THREADS);
+  if (Cin > 8 && nbx * ((Cin + 15) / 16) * N >= DA_NUM_SMS) {
+    dim3 grid((unsigned)nbx, (Cin + 15) / 16, N);
+    deconv_k2s2_dgrad_kernel<16><<<grid, DC_THREADS, 0, stream>>>(dy, weight, dx, Cin, Cout, D, H, W);
+  } else {
+    dim3 grid((unsigned)nbx, (Cin + 3) / 4, N);
+    deconv_k2s2_dgrad_kernel<4><<<grid, DC_THREADS, 0, stream>>>(dy, weight, dx, Cin, Cout, D, H, W);
+  }
   return da_check_launch("da_deconv_k2s2_dgrad");
 }
 
