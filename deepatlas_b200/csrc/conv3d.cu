@@ -1244,6 +1244,7 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     configured = true;
   }
   int rc, nregions;
+  float* bias_partials = nullptr;  // set when the kernel folds the bias gradient in
   const bool use_tma = !tma_disabled() && (Wi & 3) == 0 && Wi >= 24 && Hi >= 6 && aligned16(x1) && aligned16(x2) && aligned16(dy);
   if (use_tma) {
     // one launch: halo-side blocks x plain-side blocks x one wave of CTAs.  Work units = (column, z segment) dealt
@@ -1272,6 +1273,8 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     }
     if (nregions > a.nunits) nregions = a.nunits;
     a.partials = partials; a.region_stride = count; a.D = Di; a.tiles_x = tiles_x; a.tiles_y = tiles_y;
+    bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
+    a.bias_partials = bias_partials;
     CUtensorMap mh1, mh2, mp1, mp2;
     rc = da_make_volume_map(&mh1, h1, N, a.H1, Di, Hi, Wi, 24, 4, 1, 16);
     if (!rc) rc = a.H2 ? da_make_volume_map(&mh2, h2, N, a.H2, Di, Hi, Wi, 24, 4, 1, 16) : (mh2 = mh1, 0);
@@ -1312,8 +1315,14 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
   if (rc) return rc;
   reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
   rc = da_check_launch("conv3d_wgrad_umma/reduce");
-  if (!rc && grad_bias)
-    rc = run_channel_sum(dy, N, Cout, (int64_t)Di * Hi * Wi, grad_bias, partials + (int64_t)nregions * count, stream);
+  if (!rc && grad_bias) {
+    if (bias_partials) {
+      reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, nregions, Cout, grad_bias);
+      rc = da_check_launch("conv3d_wgrad_umma/bias-reduce");
+    } else {
+      rc = run_channel_sum(dy, N, Cout, (int64_t)Di * Hi * Wi, grad_bias, partials + (int64_t)nregions * count, stream);
+    }
+  }
   return rc;
 }
 

@@ -271,6 +271,7 @@ struct WgUmmaTmaArgs {
   int D;
   int tiles_x, tiles_y;
   int ncols, zlen, nunits;  // work unit = (column, z segment of zlen planes); unit u -> CTA u % gridDim.y
+  float* bias_partials;     // nullable: [region][P1+P2] sums of the plain-side tensor (= bias gradient when that is dY)
 };
 
 __global__ void __launch_bounds__(WU_THREADS, 1)
@@ -388,6 +389,7 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
       tco[j] = (tb >> 4) & 15; tkz[j] = tb >> 8;
     }
     int q = -1, k = 0;
+    float bsum = 0.f;  // bias gradient: the kz = 1 task holds every dY value of the tile exactly once (rows 1..4)
     for (int u = region; u < a.nunits; u += R) {
       const int zb = (u / a.ncols) * a.zlen, ze = min(a.D, zb + a.zlen);
       for (int z = zb; z < ze; ++z, ++k) {
@@ -400,6 +402,7 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
         const float* p = rawY + ((q - tkz[j]) % WV_YS) * (WV_RAW_BYTES / 4) + tco[j] * 96 + tx;  // plane z - kz + 1
 #pragma unroll
         for (int r = 0; r < 6; ++r) v[j][r] = p[r * 16];
+        if (tkz[j] == 1) bsum += (v[j][1] + v[j][2]) + (v[j][3] + v[j][4]);
       }
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
       uint8_t* st = smem + s * WU_STAGE_BYTES + 2 * WU_A_BYTES;
@@ -423,6 +426,14 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
       mbar_arrive(&full[s]);
       mbar_arrive(&consumed[k % 3]);
       }
+    }
+    if (a.bias_partials && !h2 && cib == 0) {
+      // the 16 x-lanes of one channel sit in one half warp; threads 128..255 of the producer set hold no kz = 1 task
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+      const int co = (tp < 128) ? tco[1] : tco[0];
+      if (tx == 0 && (tp < 128 || tp >= 256) && cob * 16 + co < pC)
+        a.bias_partials[(int64_t)region * (a.P1 + a.P2) + pg0 + cob * 16 + co] = bsum;
     }
   } else {
     // =============================== A producers: (xc, ci) fixed per (thread, j) ===============================
