@@ -73,6 +73,23 @@ SIGNATURES = {
     "da_deconv_k2s2_fwd": ("ppppiiiiiis", "rc"),
     "da_deconv_k2s2_dgrad": ("pppiiiiiis", "rc"),
     "da_deconv_k2s2_wgrad": ("ppppiiiiiipls", "rc"),
+    # remaining registry losses
+    "da_pair_moments_workspace_bytes": ("i", "size"),
+    "da_pair_moments_fwd": ("ppilppls", "rc"),
+    "da_affine2": ("pppilps", "rc"),
+    "da_gradient_loss_workspace_bytes": ("ii", "size"),
+    "da_gradient_loss_fwd": ("piiiiiippls", "rc"),
+    "da_gradient_loss_bwd": ("ppiiiiiips", "rc"),
+    "da_xent_workspace_bytes": ("i", "size"),
+    "da_xent_fwd": ("ppiiiilpfilppls", "rc"),
+    "da_xent_bwd": ("ppiiiilpfilppps", "rc"),
+    # UNet_generator variants, input stage
+    "da_upsample_trilinear2_fwd": ("ppliiis", "rc"),
+    "da_upsample_trilinear2_bwd": ("ppliiis", "rc"),
+    "da_add_bcast": ("ppiiilps", "rc"),
+    "da_channel_reduce": ("piilps", "rc"),
+    "da_crop_clip_f32": ("ppliiiiiiiiiffs", "rc"),
+    "da_crop_u8": ("ppliiiiiiiiis", "rc"),
 }
 
 _lib = None

@@ -1,8 +1,10 @@
-"""Host-side mirror of the reference's loss registry entries on the hot path (lib/loss.py).
+"""Host-side mirror of the reference's loss registry (lib/loss.py:739-750), all ten entries.
 
 Same class names, constructor arguments, ``forward`` signatures and error behaviour as
-``DiceLossMultiClass`` (lib/loss.py:397-476), ``VoxelMorphLNCC`` (:589-617) and ``BendingEnergyLoss``
-(:674-730).  The full-volume arithmetic runs in the CUDA library; only the closing formulas on the
+``DiceLossMultiClass`` (lib/loss.py:397-476), ``VoxelMorphLNCC`` (:589-617), ``BendingEnergyLoss``
+(:674-730) -- the hot path -- and ``NormalizedCrossCorrelationLoss`` (:485-501), ``gradientLoss`` (:625-671),
+``L2Loss`` (:733-736), ``FocalLoss`` (:120-186), ``SoftCrossEntropy`` (:96-117), ``nn.MSELoss`` and
+``nn.CrossEntropyLoss``.  The full-volume arithmetic runs in the CUDA library; only the closing formulas on the
 handful of per-class / per-term sums are evaluated with torch ops (on device, no host sync).
 """
 from __future__ import annotations
@@ -118,10 +120,152 @@ class BendingEnergyLoss(nn.Module):
         return (sums * self._coef(input.shape, input.device)[None]).sum()
 
 
+class NormalizedCrossCorrelationLoss(nn.Module):
+    """1 - NCC (lib/loss.py:485-501): per sample cov(a,b) / (std(a) std(b)) over all voxels, mean over the batch."""
+
+    def forward(self, input, target):
+        m = ops.pair_moments(input.reshape(input.shape[0], -1), target.reshape(target.shape[0], -1))
+        V = float(input[0].numel())
+        ncc = (m[:, 8] / V) / (torch.sqrt(m[:, 6] / V) * torch.sqrt(m[:, 7] / V))
+        return 1 - ncc.mean()
+
+
+class MSELoss(nn.Module):
+    """nn.MSELoss (registry 'mse', lib/loss.py:742) and the reference's own MSELoss (lib/loss.py:504-509)."""
+
+    def __init__(self, size_average=None, reduce=None, reduction="mean"):
+        super().__init__()
+        if size_average is not None or reduce is not None:
+            reduction = "mean" if (size_average is None or size_average) and (reduce is None or reduce) else (
+                "sum" if reduce is None or reduce else "none")
+        if reduction not in ("mean", "sum"):
+            raise NotImplementedError("deepatlas_b200: MSELoss is built for reduction 'mean' / 'sum'")
+        self.reduction = reduction
+
+    def forward(self, input, target):
+        if input.shape != target.shape:
+            raise RuntimeError(f"The size of tensor a {tuple(input.shape)} must match the size of tensor b "
+                               f"{tuple(target.shape)}")
+        total = ops.pair_moments(input.reshape(1, -1), target.reshape(1, -1))[0, 5]
+        return total / input.numel() if self.reduction == "mean" else total
+
+
+class L2Loss(nn.Module):
+    """lib/loss.py:733-736: mean of squares."""
+
+    def forward(self, input):
+        return ops.pair_moments(input.reshape(1, -1))[0, 2] / input.numel()
+
+
+class gradientLoss(nn.Module):
+    """Spatial-gradient regulariser of a displacement field (lib/loss.py:625-671), including the reference's
+    `+` in the H and W differences (lib/loss.py:657,659) and its per-CHANNEL scale factors (:663-665)."""
+
+    def __init__(self, norm="L2", spacing=(1, 1, 1), normalize=True):
+        super().__init__()
+        self.norm = norm
+        self.spacing = torch.tensor(spacing).float()
+        self.normalize = normalize
+        if self.normalize:
+            self.spacing = self.spacing / self.spacing.min()
+
+    def forward(self, input):
+        N, C, D, H, W = input.shape
+        sums = ops.gradient_sums(input, l1=self.norm != "L2")                     # (N, C, 3)
+        counts = torch.tensor([(D - 2) * H * W, D * (H - 2) * W, D * H * (W - 2)], dtype=torch.float32)
+        sp = self.spacing
+        if self.norm == "L2":
+            dims = torch.tensor([D, H, W], dtype=torch.float32)
+            if self.normalize:
+                dims = dims / dims.min()
+            # (dx**2).mean(2) * (spatial_dims * spacing / spacing[k])**2 broadcasts the 3-vector over channels
+            scale = torch.stack([(dims * sp / sp[k]) ** 2 for k in range(3)], dim=1)  # (channel, term)
+            if C != 3:
+                raise RuntimeError(f"The size of tensor a ({C}) must match the size of tensor b (3) at non-singleton "
+                                   "dimension 1")
+            coef = scale / counts[None, :] / (N * C)
+        else:
+            coef = (1.0 / counts / (N * C))[None, :].expand(C, 3)
+        return (sums * coef.to(input.device)[None]).sum() / 3.0
+
+
+class CrossEntropyLoss(nn.Module):
+    """nn.CrossEntropyLoss (registry 'cross_entropy', lib/loss.py:748) for (N,C,D,H,W) scores and class-index
+    targets (N,D,H,W): per-class ``weight``, ``ignore_index`` and reduction 'mean' / 'sum'."""
+
+    def __init__(self, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction="mean",
+                 label_smoothing=0.0):
+        super().__init__()
+        if size_average is not None or reduce is not None:
+            reduction = "mean" if (size_average is None or size_average) and (reduce is None or reduce) else (
+                "sum" if reduce is None or reduce else "none")
+        if reduction not in ("mean", "sum") or label_smoothing != 0.0:
+            raise NotImplementedError("deepatlas_b200: CrossEntropyLoss is built for reduction 'mean' / 'sum' without "
+                                      "label smoothing")
+        self.register_buffer("weight", weight)
+        self.ignore_index, self.reduction, self.label_smoothing = ignore_index, reduction, label_smoothing
+
+    def forward(self, input, target):
+        if target.is_floating_point():   # class probabilities: -sum_c t_c log_softmax(x)_c, mean over N * voxels
+            if self.weight is not None:
+                raise NotImplementedError("deepatlas_b200: probability targets with class weights")
+            s = ops.xent_sums(input, target, 2)
+            return s[0] / s[1] if self.reduction == "mean" else s[0]
+        s = ops.xent_sums(input, target, 0, class_weight=self.weight, ignore_index=self.ignore_index)
+        return s[0] / s[1] if self.reduction == "mean" else s[0]
+
+
+class FocalLoss(nn.Module):
+    """lib/loss.py:120-186.  ``probs = F.nll_loss(P, targets)`` is -P[target] there, so the modulating factor is
+    (1 + P[target])**gamma; reproduced as is (parity with the reference, not with the paper)."""
+
+    def __init__(self, class_num, alpha=None, gamma=2, size_average=True, soft_max=True):
+        super().__init__()
+        self.alpha = torch.ones(class_num, 1) if alpha is None else alpha
+        self.gamma, self.class_num, self.size_average, self.soft_max = gamma, class_num, size_average, soft_max
+
+    def forward(self, inputs, targets):
+        if inputs.dim() != 5:
+            raise NotImplementedError("deepatlas_b200: FocalLoss is built for (B,C,X,Y,Z) inputs")
+        if inputs.is_cuda and not self.alpha.is_cuda:
+            self.alpha = self.alpha.cuda()
+        s = ops.xent_sums(inputs, targets, 1, class_weight=self.alpha.float().reshape(-1), gamma=float(self.gamma),
+                          focal_softmax=bool(self.soft_max))
+        return s[0] / s[1] if self.size_average else s[0]
+
+
+class SoftCrossEntropy(nn.Module):
+    """lib/loss.py:96-117 for class-wise probability targets (B,C,D,M,N).  With a label-mask target the reference
+    multiplies the raw label VALUES into the log-probabilities (it uses ``target``, not the one-hot it just built,
+    lib/loss.py:114-116, and negates a uint8): that path is not reproduced.  ``softmax=False`` clamps the
+    prediction at 1e-8 (in place in the reference; here the argument is left untouched)."""
+
+    def __init__(self, n_class=None, weight_type="Simple", no_bg=False, softmax=False):
+        super().__init__()
+        self.weight_type, self.n_class, self.no_bg, self.softmax = weight_type, n_class, no_bg, softmax
+
+    def forward(self, pred, target):
+        shape = list(pred.shape)
+        if len(target.shape) == len(shape) - 1:
+            raise NotImplementedError("deepatlas_b200: SoftCrossEntropy with a label-mask target (see class docstring)")
+        if target.shape[1] != shape[1]:
+            raise ValueError("Incorrect size of target tensor: {}, should be {} or []".format(
+                target.shape, shape, shape[:1] + [1, ] + shape[2:]))
+        s = ops.xent_sums(pred, target, 2 if self.softmax else 3)
+        return s[0] / s[1]
+
+
 loss_dict = {
+    "ncc": NormalizedCrossCorrelationLoss,
     "lncc": VoxelMorphLNCC,
+    "mse": MSELoss,
+    "gradient": gradientLoss,
     "bendingEnergy": BendingEnergyLoss,
     "dice": DiceLossMultiClass,
+    "L2": L2Loss,
+    "focal": FocalLoss,
+    "cross_entropy": CrossEntropyLoss,
+    "soft_cross_entropy": SoftCrossEntropy,
 }
 
 

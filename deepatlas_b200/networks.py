@@ -144,12 +144,24 @@ class _MaxPool2(nn.MaxPool3d):
         return ops.maxpool2(x)
 
 
+class _ConvK2S2(nn.Conv3d):
+    """The strided down-sampler of maxpool=False (unets.py:231): Conv3d kernel 2, stride 2, no padding."""
+
+    def forward(self, x):
+        return ops.conv_k2s2(x, self.weight, self.bias)
+
+
+class _UpsampleTrilinear2(nn.Upsample):
+    """nn.Upsample(scale_factor=2, mode='trilinear') of upsample=True (unets.py:236)."""
+
+    def forward(self, x):
+        return ops.upsample_trilinear2(x)
+
+
 def UNet_generator(encoders, decoders, act="ReLU", upsample=False, maxpool=True, res=False):
-    """Class factory mirroring lib/network_factory/unets.py:182-280 (maxpool / deconv / non-residual
-    configuration, which is what the registry's 'UNet_light' uses)."""
-    if upsample or not maxpool or res:
-        raise NotImplementedError("deepatlas_b200: UNet_generator variants upsample=True / maxpool=False / res=True "
-                                  "are outside the built hot path (SURVEY.md 8(f) row 3)")
+    """Class factory mirroring lib/network_factory/unets.py:182-280, all variants: ``upsample=True`` (trilinear x2
+    instead of the k2 s2 deconvolution), ``maxpool=False`` (k2 s2 convolution instead of max-pooling) and
+    ``res=True`` (``enc(x) + x`` / ``dec(cat) + x`` with torch's channel broadcasting)."""
 
     class UNetTemplate(nn.Module):
         def __init__(self, in_channel, n_classes, bias=False, BN=False):
@@ -168,11 +180,16 @@ def UNet_generator(encoders, decoders, act="ReLU", upsample=False, maxpool=True,
                 self.encoders.append(nn.Sequential(*[convBlock(enc[k], enc[k + 1], bias=bias, batchnorm=BN, act=act)
                                                      for k in range(len(enc) - 1)]))
                 if i < len(encoders) - 1:
-                    self.down_samplers.append(_MaxPool2(2))
+                    self.down_samplers.append(_MaxPool2(2) if self.maxpool else
+                                              _ConvK2S2(enc[-1], encoders[i + 1][0], kernel_size=2, stride=2, padding=0,
+                                                        bias=bias))
             n_inner = len(enc) - 1  # the reference re-uses the last encoder tuple's length (unets.py:247)
             for i, dec in enumerate(decoders):
-                self.up_samplers.append(deconvBlock(encoders[-1][-1] if i == 0 else decoders[i - 1][-1], dec[0],
-                                                    kernel_size=2, stride=2, bias=bias, batchnorm=BN, act=act))
+                if self.upsample:
+                    self.up_samplers.append(_UpsampleTrilinear2(scale_factor=2, mode="trilinear"))
+                else:
+                    self.up_samplers.append(deconvBlock(encoders[-1][-1] if i == 0 else decoders[i - 1][-1], dec[0],
+                                                        kernel_size=2, stride=2, bias=bias, batchnorm=BN, act=act))
                 dec = (encoders[-(i + 2)][-1] + dec[0],) + tuple(dec[1:])
                 blocks = [convBlock(dec[k], dec[k + 1], kernel_size=3, stride=1, padding=1, bias=bias, batchnorm=BN,
                                     act=act) for k in range(n_inner)]
@@ -186,16 +203,20 @@ def UNet_generator(encoders, decoders, act="ReLU", upsample=False, maxpool=True,
         def forward(self, x):
             skips = []
             for i, enc in enumerate(self.encoders):
+                y = x
                 for blk in enc:
-                    x = blk(x)
+                    y = blk(y)
+                x = ops.add(y, x) if self.res else y                      # unets.py:264
                 if i < self.levels - 1:
                     skips.append(x)
                     x = self.down_samplers[i](x)
             for j, dec in enumerate(self.decoders):
                 x = self.up_samplers[j](x)
                 skip = skips.pop()
+                y = x
                 for k, blk in enumerate(dec):
-                    x = blk(x, skip) if k == 0 else blk(x)  # first conv reads cat(x, skip) as two sources
+                    y = blk(y, skip) if k == 0 else blk(y)  # first conv reads cat(x, skip) as two sources
+                x = ops.add(y, x) if self.res else y                      # unets.py:275
             return x
 
     return UNetTemplate
@@ -269,6 +290,44 @@ class convBlockVM(nn.Module):
         if self.residual:
             y = y + y  # the reference's `x += x` (modules.py:59-60), kept
         return y
+
+
+class deconvBlockVM(nn.Module):
+    """Mirror of modules.deconvBlock (lib/network_factory/modules.py:65-86): attributes ``deconv`` / ``bn``;
+    ConvTranspose3d (k2 s2, or k3 s1 p1) -> [bn] -> activation -> optional ``x += input``."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, bias=False,
+                 batchnorm=False, residual=False, act=nn.ReLU):
+        super().__init__()
+        if (kernel_size, stride, padding, output_padding) == (2, 2, 0, 0):
+            self._kind = "deconv"
+        elif (kernel_size, stride, padding, output_padding) == (3, 1, 1, 0):
+            self._kind = "convT3"
+        else:
+            raise NotImplementedError(
+                f"deepatlas_b200: ConvTranspose3d k{kernel_size} s{stride} p{padding} is not on the hot path")
+        self.deconv = nn.ConvTranspose3d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
+                                         output_padding=output_padding, bias=bias)
+        self.bn = nn.BatchNorm3d(out_channels) if batchnorm else None
+        if isinstance(act, str):
+            act = _ACT[act][0]
+        self.nonlinear = act
+        self.residual = residual
+        self._slope = 0.01 if act is nn.LeakyReLU else 0.0
+
+    def forward(self, input):
+        fused = self._slope if self.bn is None else None
+        if self._kind == "convT3":
+            x = ops.conv3d(input, self.deconv.weight, self.deconv.bias, transposed=True, stride=1, pad=1, slope=fused)
+        else:
+            x = ops.deconv_k2s2(input, self.deconv.weight, self.deconv.bias)
+            if fused is not None:
+                x = _LeakyFunction.apply(x, fused)
+        if self.bn is not None:
+            x = _bn_apply(self.bn, x, self._slope)
+        if self.residual:
+            x = ops.add(x, input)
+        return x
 
 
 class VoxelMorphCVPR2018(nn.Module):

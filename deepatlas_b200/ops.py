@@ -524,3 +524,299 @@ class DeconvK2S2Function(torch.autograd.Function):
 
 def deconv_k2s2(x, weight, bias=None):
     return DeconvK2S2Function.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Conv3d kernel 2 stride 2 (maxpool=False down-sampler, lib/network_factory/unets.py:231): the adjoint of
+# the k2 s2 deconvolution, so its three passes are the deconvolution's three kernels with roles swapped.
+# ------------------------------------------------------------------------------------------------------
+class ConvK2S2Function(torch.autograd.Function):
+    """y = conv3d(x, weight (Cout,Cin,2,2,2), stride 2, padding 0) + bias; even extents only."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, weight = _f32(x, "x"), _f32(weight, "weight")
+        bias = _f32(bias, "bias") if bias is not None else None
+        N, Cin, D, H, W = x.shape
+        if weight.shape[1] != Cin or tuple(weight.shape[2:]) != (2, 2, 2):
+            raise ValueError(f"conv_k2s2: weight must be (Cout,{Cin},2,2,2), got {tuple(weight.shape)}")
+        if D % 2 or H % 2 or W % 2:
+            raise RuntimeError("deepatlas_b200: conv k2 s2 is built for even extents")
+        Cout = weight.shape[0]
+        st = _stream()
+        y = torch.empty((N, Cout, D // 2, H // 2, W // 2), dtype=torch.float32, device=x.device)
+        # deconv data gradient with (Cin_deconv, Cout_deconv) = (Cout, Cin): y[co] = sum x[ci, 2z+a, ..] w[co, ci, a, ..]
+        _lib.call("da_deconv_k2s2_dgrad", _p(x), _p(weight), _p(y), N, Cout, Cin, D // 2, H // 2, W // 2, st)
+        if bias is not None:  # y = (y - 0) * 1 + bias through the normalisation kernel, in place
+            zero = torch.zeros(Cout, device=x.device)
+            one = torch.ones(Cout, device=x.device)
+            _lib.call("da_bn_act_fwd", _p(y), _p(zero), _p(one), None, _p(bias), N, Cout, y[0, 0].numel(), 0, 0.0, _p(y), st)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _f32(dy, "grad_out")
+        N, Cin, D, H, W = x.shape
+        Cout = weight.shape[0]
+        st = _stream()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _lib.call("da_deconv_k2s2_fwd", _p(dy), _p(weight), None, _p(dx), N, Cout, Cin, D // 2, H // 2, W // 2, st)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            nb = _lib.size("da_deconv_k2s2_wgrad_workspace_bytes", Cout, Cin)
+            ws = _ws(nb, dy.device)
+            _lib.call("da_deconv_k2s2_wgrad", _p(dy), _p(x), _p(dw), None, N, Cout, Cin, D // 2, H // 2, W // 2, _p(ws), nb, st)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty((Cout,), dtype=torch.float32, device=dy.device)
+            nb = _lib.size("da_channel_sum_workspace_bytes", Cout)
+            ws = _ws(nb, dy.device)
+            _lib.call("da_channel_sum", _p(dy), N, Cout, dy[0, 0].numel(), _p(db), _p(ws), nb, st)
+        return dx, dw, db
+
+
+def conv_k2s2(x, weight, bias=None):
+    return ConvK2S2Function.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------------
+# trilinear x2 up-sampling, residual add  (lib/network_factory/unets.py:236,264,275)
+# ------------------------------------------------------------------------------------------------------
+class UpsampleTrilinear2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32(x, "x")
+        N, C, D, H, W = x.shape
+        y = torch.empty((N, C, 2 * D, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        _lib.call("da_upsample_trilinear2_fwd", _p(x), _p(y), N * C, D, H, W, _stream())
+        ctx.shape = (N, C, D, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, D, H, W = ctx.shape
+        dy = _f32(dy, "grad_out")
+        dx = torch.empty((N, C, D, H, W), dtype=torch.float32, device=dy.device)
+        _lib.call("da_upsample_trilinear2_bwd", _p(dy), _p(dx), N * C, D, H, W, _stream())
+        return dx
+
+
+def upsample_trilinear2(x):
+    return UpsampleTrilinear2Function.apply(x)
+
+
+class AddFunction(torch.autograd.Function):
+    """a + b for a [N,Ca,...] and b [N,Cb,...] with Cb == Ca or Cb == 1 (channel broadcast, as torch's `+`)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32(a, "a"), _f32(b, "b")
+        if a.dim() != b.dim() or a.shape[0] != b.shape[0] or tuple(a.shape[2:]) != tuple(b.shape[2:]) or \
+                b.shape[1] not in (a.shape[1], 1):
+            raise RuntimeError(f"The size of tensor a {tuple(a.shape)} must match the size of tensor b "
+                               f"{tuple(b.shape)} (equal, or b with a single channel)")
+        N, Ca = a.shape[:2]
+        V = a[0, 0].numel()
+        out = torch.empty_like(a)
+        _lib.call("da_add_bcast", _p(a), _p(b), N, Ca, b.shape[1], V, _p(out), _stream())
+        ctx.cfg = (N, Ca, b.shape[1], V, tuple(b.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, Ca, Cb, V, bshape = ctx.cfg
+        ga = g if ctx.needs_input_grad[0] else None
+        gb = None
+        if ctx.needs_input_grad[1]:
+            if Cb == Ca:
+                gb = g
+            else:
+                g = _f32(g, "grad_out")
+                gb = torch.empty(bshape, dtype=torch.float32, device=g.device)
+                _lib.call("da_channel_reduce", _p(g), N, Ca, V, _p(gb), _stream())
+        return ga, gb
+
+
+def add(a, b):
+    """``a + b`` of the residual variants; the operand with fewer channels is broadcast."""
+    if b.shape[1] > a.shape[1]:
+        a, b = b, a
+    return AddFunction.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------------
+# remaining registry losses  (lib/loss.py:96-186, 485-501, 625-671, 733-736)
+# ------------------------------------------------------------------------------------------------------
+class PairMomentsFunction(torch.autograd.Function):
+    """m[N,9] = (sum a, sum b, sum a^2, sum b^2, sum ab, sum (a-b)^2, sum (a-ma)^2, sum (b-mb)^2, sum (a-ma)(b-mb))
+    per sample; b may be None.  The backward is one affine pass per input."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = _f32(a, "input")
+        if b is not None:
+            b = _f32(b, "target")
+            if b.shape != a.shape:
+                raise RuntimeError(f"The size of tensor a {tuple(a.shape)} must match the size of tensor b {tuple(b.shape)}")
+        N = a.shape[0]
+        V = a[0].numel()
+        out = torch.empty((N, 9), dtype=torch.float32, device=a.device)
+        nb = _lib.size("da_pair_moments_workspace_bytes", N)
+        ws = _ws(nb, a.device)
+        _lib.call("da_pair_moments_fwd", _p(a), _p(b), N, V, _p(out), _p(ws), nb, _stream())
+        ctx.save_for_backward(a, b, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, m = ctx.saved_tensors
+        N = a.shape[0]
+        V = a[0].numel()
+        coef_a, coef_b = pair_moment_coefs(g.float(), m, V)
+        st = _stream()
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = torch.empty_like(a)
+            _lib.call("da_affine2", _p(a), _p(b), _p(coef_a), N, V, _p(ga), st)
+        if b is not None and ctx.needs_input_grad[1]:
+            gb = torch.empty_like(b)
+            _lib.call("da_affine2", _p(b), _p(a), _p(coef_b), N, V, _p(gb), st)
+        return ga, gb
+
+
+def pair_moment_coefs(g, m, V):
+    """Per-sample coefficients of the affine gradients of the nine moments: grad_a = ca[:,0]*a + ca[:,1]*b + ca[:,2] and
+    grad_b = cb[:,0]*b + cb[:,1]*a + cb[:,2], for upstream gradients g [N,9] and moments m [N,9].
+    d/da_i: Sa 1 | Saa 2a | Sab b | Sdd 2(a-b) | cAA 2(a-ma) | cAB (b-mb); symmetrically for b."""
+    ma, mb = m[:, 0] / V, m[:, 1] / V
+    ca = torch.stack([2 * g[:, 2] + 2 * g[:, 5] + 2 * g[:, 6],
+                      g[:, 4] - 2 * g[:, 5] + g[:, 8],
+                      g[:, 0] - 2 * g[:, 6] * ma - g[:, 8] * mb], dim=1).contiguous()
+    cb = torch.stack([2 * g[:, 3] + 2 * g[:, 5] + 2 * g[:, 7],
+                      g[:, 4] - 2 * g[:, 5] + g[:, 8],
+                      g[:, 1] - 2 * g[:, 7] * mb - g[:, 8] * ma], dim=1).contiguous()
+    return ca, cb
+
+
+def pair_moments(a, b=None):
+    return PairMomentsFunction.apply(a, b)
+
+
+class GradientSumsFunction(torch.autograd.Function):
+    """sums[N,C,3] of gradientLoss (lib/loss.py:655-659): f(u[d+2]-u[d]), f(u[h+2]+u[h]), f(u[w+2]+u[w])."""
+
+    @staticmethod
+    def forward(ctx, u, l1: bool):
+        u = _f32(u, "input")
+        if u.dim() != 5:
+            raise ValueError(f"gradient loss: input must be (N,C,D,H,W), got {tuple(u.shape)}")
+        N, C, D, H, W = u.shape
+        sums = torch.empty((N, C, 3), dtype=torch.float32, device=u.device)
+        nb = _lib.size("da_gradient_loss_workspace_bytes", N, C)
+        ws = _ws(nb, u.device)
+        _lib.call("da_gradient_loss_fwd", _p(u), N, C, D, H, W, int(l1), _p(sums), _p(ws), nb, _stream())
+        ctx.save_for_backward(u)
+        ctx.l1 = bool(l1)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        N, C, D, H, W = u.shape
+        g = _f32(g, "grad_sums")
+        gu = torch.empty_like(u)
+        _lib.call("da_gradient_loss_bwd", _p(u), _p(g), N, C, D, H, W, int(ctx.l1), _p(gu), _stream())
+        return gu, None
+
+
+def gradient_sums(u, l1=False):
+    return GradientSumsFunction.apply(u, l1)
+
+
+class XentFunction(torch.autograd.Function):
+    """out2 = (sum of per-voxel terms, sum of weights) of the channel log-softmax losses; mode 0 cross entropy,
+    1 focal, 2 soft cross entropy (log_softmax), 3 soft cross entropy (log of clamped probabilities)."""
+
+    @staticmethod
+    def forward(ctx, x, target, mode: int, class_weight, gamma: float, focal_softmax: bool, ignore_index: int):
+        x = _f32(x, "input")
+        N, C = x.shape[:2]
+        V = x[0, 0].numel()
+        if not target.is_cuda:
+            raise RuntimeError("deepatlas_b200: 'target' must be a CUDA tensor")
+        if mode >= 2:
+            target = _f32(target, "target")
+            if target.shape != x.shape:
+                raise ValueError("soft cross entropy: target must have the shape of the prediction")
+            kind = 2
+        else:
+            if target.is_floating_point():
+                raise RuntimeError("deepatlas_b200: class-index target expected (integer dtype)")
+            if target.dtype not in _KIND:
+                target = target.long()
+            target = target.contiguous()
+            if target.numel() != N * V:
+                raise ValueError("Expected target of N*D*H*W class indices")
+            kind = _KIND[target.dtype]
+        cw = _f32(class_weight, "class weight").reshape(-1) if class_weight is not None else None
+        if cw is not None and cw.numel() != C:
+            raise ValueError("class weight must have one entry per class")
+        out2 = torch.empty((2,), dtype=torch.float32, device=x.device)
+        nb = _lib.size("da_xent_workspace_bytes", N)
+        ws = _ws(nb, x.device)
+        _lib.call("da_xent_fwd", _p(x), _p(target), kind, mode, N, C, V, _p(cw), float(gamma), int(focal_softmax),
+                  int(ignore_index), _p(out2), _p(ws), nb, _stream())
+        ctx.save_for_backward(x, target, cw)
+        ctx.cfg = (kind, mode, float(gamma), int(focal_softmax), int(ignore_index))
+        return out2
+
+    @staticmethod
+    def backward(ctx, g):
+        x, target, cw = ctx.saved_tensors
+        kind, mode, gamma, fsm, ign = ctx.cfg
+        N, C = x.shape[:2]
+        V = x[0, 0].numel()
+        gscale = g[0:1].float().contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gt = torch.empty_like(target) if (mode >= 2 and ctx.needs_input_grad[1]) else None
+        if gx is None and gt is None:
+            return (None,) * 7
+        if mode < 2 and gx is None:
+            return (None,) * 7
+        _lib.call("da_xent_bwd", _p(x), _p(target), kind, mode, N, C, V, _p(cw), gamma, fsm, ign, _p(gscale), _p(gx), _p(gt),
+                  _stream())
+        return gx, gt, None, None, None, None, None
+
+
+def xent_sums(x, target, mode, class_weight=None, gamma=0.0, focal_softmax=True, ignore_index=-100):
+    return XentFunction.apply(x, target, mode, class_weight, gamma, focal_softmax, ignore_index)
+
+
+# ------------------------------------------------------------------------------------------------------
+# device-side input stage  (lib/transforms.py:79-80, 124-158)
+# ------------------------------------------------------------------------------------------------------
+def crop_clip(image, lo_corner, size, clip=(0.0, 1.0)):
+    """image [..., D, H, W] fp32 on the device -> clip(image[..., z0:z0+Do, y0:y0+Ho, x0:x0+Wo], *clip)."""
+    image = _f32(image, "image")
+    D, H, W = image.shape[-3:]
+    NC = image.numel() // (D * H * W)
+    out = torch.empty(tuple(image.shape[:-3]) + tuple(size), dtype=torch.float32, device=image.device)
+    _lib.call("da_crop_clip_f32", _p(image), _p(out), NC, D, H, W, *[int(v) for v in lo_corner], *[int(v) for v in size],
+              float(clip[0]), float(clip[1]), _stream())
+    return out
+
+
+def crop_labels(labels, lo_corner, size):
+    """uint8 label map [..., D, H, W] on the device -> the cropped window, still uint8 (read directly by the losses)."""
+    if not labels.is_cuda or labels.dtype != torch.uint8:
+        raise RuntimeError("deepatlas_b200: 'labels' must be a CUDA uint8 tensor")
+    labels = labels.contiguous()
+    D, H, W = labels.shape[-3:]
+    NC = labels.numel() // (D * H * W)
+    out = torch.empty(tuple(labels.shape[:-3]) + tuple(size), dtype=torch.uint8, device=labels.device)
+    _lib.call("da_crop_u8", _p(labels), _p(out), NC, D, H, W, *[int(v) for v in lo_corner], *[int(v) for v in size], _stream())
+    return out

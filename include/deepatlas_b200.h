@@ -169,6 +169,55 @@ int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_weight, fl
                          int Cin, int Cout, int D, int H, int W, void* workspace, int64_t workspace_bytes,
                          da_stream_t stream);
 
+/* ---- remaining entries of the loss registry (lib/loss.py:739-750) ------------------
+ * pair moments: replaces the ATen passes of NormalizedCrossCorrelationLoss (lib/loss.py:494-501), nn.MSELoss
+ * ('mse') and L2Loss (lib/loss.py:733-736).  a, b [N,V] (b nullable); out [N,9] per sample =
+ * (sum a, sum b, sum a^2, sum b^2, sum a*b, sum (a-b)^2, sum (a-ma)^2, sum (b-mb)^2, sum (a-ma)(b-mb)), accumulated
+ * in fp64.  The gradient of any function of those moments is affine in (a, b, 1): da_affine2 with per-sample
+ * coefficients coef [N,3] on the device. */
+int64_t da_pair_moments_workspace_bytes(int N);
+int da_pair_moments_fwd(const float* a, const float* b, int N, int64_t V, float* out, void* workspace,
+                        int64_t workspace_bytes, da_stream_t stream);
+int da_affine2(const float* a, const float* b, const float* coef, int N, int64_t V, float* out, da_stream_t stream);
+
+/* gradientLoss (lib/loss.py:625-671): u [N,C,D,H,W]; sums [N,C,3] = sum f(u[d+2]-u[d]), sum f(u[h+2]+u[h]),
+ * sum f(u[w+2]+u[w]) (the reference adds along H and W -- kept); f = square (norm_l1 0) or abs (1). */
+int64_t da_gradient_loss_workspace_bytes(int N, int C);
+int da_gradient_loss_fwd(const float* u, int N, int C, int D, int H, int W, int norm_l1, float* sums, void* workspace,
+                         int64_t workspace_bytes, da_stream_t stream);
+int da_gradient_loss_bwd(const float* u, const float* grad_sums, int N, int C, int D, int H, int W, int norm_l1,
+                         float* grad_u, da_stream_t stream);
+
+/* channel log-softmax terms: nn.CrossEntropyLoss (mode 0; registry 'cross_entropy', lib/loss.py:748), FocalLoss
+ * (mode 1; lib/loss.py:149-186, including probs = nll_loss(P) = -P[t]), SoftCrossEntropy with softmax (mode 2,
+ * lib/loss.py:114) and without (mode 3, lib/loss.py:116).  x [N,C,V]; target: labels [N,V] (kind 0 uint8, 1 int64,
+ * 3 int32) in modes 0-1, fp32 [N,C,V] (kind 2) in modes 2-3; class_weight (nullable, [C]) = CrossEntropyLoss weight /
+ * FocalLoss alpha; out2 [2] = (sum of terms, sum of weights (mode 0) or voxel count).  Backward: grad_scale is a DEVICE
+ * scalar d loss / d out2[0]; grad_target (nullable) only in the soft modes. */
+int64_t da_xent_workspace_bytes(int N);
+int da_xent_fwd(const float* x, const void* target, int target_kind, int mode, int N, int C, int64_t V,
+                const float* class_weight, float gamma, int focal_softmax, int64_t ignore_index, float* out2,
+                void* workspace, int64_t workspace_bytes, da_stream_t stream);
+int da_xent_bwd(const float* x, const void* target, int target_kind, int mode, int N, int C, int64_t V,
+                const float* class_weight, float gamma, int focal_softmax, int64_t ignore_index,
+                const float* grad_scale, float* grad_x, float* grad_target, da_stream_t stream);
+
+/* ---- UNet_generator variants (lib/network_factory/unets.py:230-241,264,275) ------------
+ * nn.Upsample(scale_factor=2, mode='trilinear') (align_corners=False): x [NC,D,H,W] -> y [NC,2D,2H,2W]. */
+int da_upsample_trilinear2_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, da_stream_t stream);
+int da_upsample_trilinear2_bwd(const float* dy, float* dx, int64_t NC, int D, int H, int W, da_stream_t stream);
+/* residual add `enc(x) + x`: out [N,Ca,V] = a + b, b [N,Cb,V] with Cb == Ca or 1 (broadcast); and the gradient of the
+ * broadcast operand, out [N,1,V] = sum over channels of g [N,C,V]. */
+int da_add_bcast(const float* a, const float* b, int N, int Ca, int Cb, int64_t V, float* out, da_stream_t stream);
+int da_channel_reduce(const float* g, int N, int C, int64_t V, float* out, da_stream_t stream);
+
+/* ---- device-side input stage (lib/transforms.py:79-80 clip to [0,1], :124-158 CropTensor)
+ * src [NC,D,H,W] -> dst [NC,Do,Ho,Wo] = src[z0:z0+Do, y0:y0+Ho, x0:x0+Wo] (fp32 clipped to [lo,hi]; uint8 labels). */
+int da_crop_clip_f32(const float* src, float* dst, int64_t NC, int D, int H, int W, int z0, int y0, int x0, int Do,
+                     int Ho, int Wo, float lo, float hi, da_stream_t stream);
+int da_crop_u8(const uint8_t* src, uint8_t* dst, int64_t NC, int D, int H, int W, int z0, int y0, int x0, int Do,
+               int Ho, int Wo, da_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,21 +173,97 @@ def golden_nets(ref):
     return out, meta
 
 
+def golden_extra(ref):
+    """the remaining registry losses and the UNet_generator variants, from the real modules."""
+    out = {}
+    g = _g(SEED + 1)
+    size = (7, 8, 9)
+    a = torch.rand((2, 1) + size, generator=g, requires_grad=True)
+    b = torch.rand((2, 1) + size, generator=g, requires_grad=True)
+    out.update(pair_a=_np(a), pair_b=_np(b))
+    for name, crit, args in (("ncc", ref.get_loss_function("ncc")(), (a, b)), ("mse", ref.get_loss_function("mse")(), (a, b)),
+                             ("L2", ref.get_loss_function("L2")(), (a,))):
+        a.grad = b.grad = None
+        loss = crit(*args)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_ga"] = _np(loss), _np(a.grad)
+        if len(args) == 2:
+            out[f"{name}_gb"] = _np(b.grad)
+    u = (torch.randn((2, 3, 8, 9, 10), generator=g) * 0.1).requires_grad_(True)
+    out["grad_u"] = _np(u)
+    for norm in ("L2", "L1"):
+        for k, sp in enumerate(((1, 1, 1), (1.0, 1.5, 2.0))):
+            u.grad = None
+            loss = ref.get_loss_function("gradient")(norm=norm, spacing=sp)(u)
+            loss.backward()
+            out[f"grad_{norm}_{k}_loss"], out[f"grad_{norm}_{k}_g"] = _np(loss), _np(u.grad)
+            out[f"grad_spacing_{k}"] = np.asarray(sp, np.float32)
+    C, xs = 5, (6, 7, 8)
+    x = torch.randn((2, C) + xs, generator=g, requires_grad=True)
+    t = torch.randint(0, C, (2,) + xs, generator=g)
+    soft = torch.softmax(torch.randn((2, C) + xs, generator=g), 1).requires_grad_(True)
+    w = torch.rand(C, generator=g) + 0.5
+    alpha = torch.rand(C, 1, generator=g) + 0.5
+    out.update(xent_x=_np(x), xent_t=_np(t).astype(np.uint8), xent_soft=_np(soft), xent_w=_np(w), xent_alpha=_np(alpha))
+    cases = {
+        "ce": lambda xi: ref.get_loss_function("cross_entropy")()(xi, t),
+        "ce_w": lambda xi: ref.get_loss_function("cross_entropy")(weight=w)(xi, t),
+        "focal": lambda xi: ref.get_loss_function("focal")(C)(xi, t),
+        "focal_a": lambda xi: ref.get_loss_function("focal")(C, alpha=alpha, gamma=1.5, size_average=False)(xi, t),
+        "focal_nosm": lambda xi: ref.get_loss_function("focal")(C, soft_max=False)(torch.softmax(xi, 1), t),
+        "sce_sm": lambda xi: ref.get_loss_function("soft_cross_entropy")(softmax=True)(xi, soft),
+        "sce": lambda xi: ref.get_loss_function("soft_cross_entropy")(softmax=False)(torch.softmax(xi, 1) * 1.0, soft),  # clamp_ is in place there
+    }
+    for name, fn in cases.items():
+        x.grad = soft.grad = None
+        loss = fn(x)
+        loss.backward()
+        out[f"{name}_loss"], out[f"{name}_gx"] = _np(loss), _np(x.grad)
+        if soft.grad is not None:
+            out[f"{name}_gt"] = _np(soft.grad)
+    # UNet_generator variants (lib/network_factory/unets.py:230-241,264,275)
+    variants = {"strided": (dict(maxpool=False), [(4, 8), (8, 8, 16)], [(8, 8, 8)], 3),
+                "upsample": (dict(upsample=True), [(4, 8), (8, 8, 16)], [(16, 8, 8)], 3),
+                "res": (dict(res=True), [(8, 8), (8, 8)], [(8, 8)], 8),
+                "all": (dict(maxpool=False, upsample=True, res=True), [(8, 8), (8, 8)], [(8, 8)], 8)}
+    xin = torch.rand((1, 1, 8, 12, 8), generator=g)
+    out["var_x"] = _np(xin)
+    for name, (kw, enc, dec, ncls) in variants.items():
+        torch.manual_seed(SEED)
+        net = ref.network_factory.unets.UNet_generator(enc, dec, act="LeakyReLU", **kw)(1, ncls, bias=True, BN=True)
+        net.weights_init()
+        net.train()
+        for k, v in net.state_dict().items():
+            out[f"var_{name}_sd/{k}"] = _np(v)
+        y = net(xin)
+        cot = torch.randn(y.shape, generator=g)
+        (y * cot).sum().backward()
+        out[f"var_{name}_y"], out[f"var_{name}_cot"] = _np(y), _np(cot)
+        for k, p_ in net.named_parameters():
+            out[f"var_{name}_grad/{k}"] = _np(p_.grad)
+    return out
+
+
 def main():
     if not ref_import.available():
         raise SystemExit("reference tree not found at %s" % ref_import.REFERENCE_ROOT)
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     ref = ref_import.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--extra-only" in sys.argv:   # leaves ops.npz / nets.npz / meta.json as committed
+        np.savez_compressed(os.path.join(OUT, "extra.npz"), **golden_extra(ref))
+        print("extra.npz", os.path.getsize(os.path.join(OUT, "extra.npz")), "bytes")
+        return
     ops = golden_ops(ref)
     nets, meta = golden_nets(ref)
+    np.savez_compressed(os.path.join(OUT, "extra.npz"), **golden_extra(ref))
     np.savez_compressed(os.path.join(OUT, "ops.npz"), **ops)
     np.savez_compressed(os.path.join(OUT, "nets.npz"), **nets)
     meta.update(torch=torch.__version__, numpy=np.__version__, seed=SEED, reference_root=ref_import.REFERENCE_ROOT,
                 generated_by="oracle/make_golden.py", dtype="float32 (CPU)")
     with open(os.path.join(OUT, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, sort_keys=True)
-    for n in ("ops.npz", "nets.npz", "meta.json"):
+    for n in ("ops.npz", "nets.npz", "extra.npz", "meta.json"):
         print(n, os.path.getsize(os.path.join(OUT, n)), "bytes")
 
 

@@ -87,26 +87,38 @@ UNET_LIGHT_CFG = dict(  # lib/network_factory/__init__.py:12-15
 
 def unet_generator_forward(x, sd: SD, in_channel: int, bn: bool, cfg=UNET_LIGHT_CFG, training=True,
                            stats_out=None):
-    """UNetTemplate.forward with maxpool=True, upsample=False, res=False
-    (lib/network_factory/unets.py:259-278; construction :222-252)."""
+    """UNetTemplate.forward (lib/network_factory/unets.py:259-278; construction :222-252) for every
+    variant: cfg['maxpool'] (default True; False = Conv3d k2 s2 down-samplers, :231), cfg['upsample']
+    (default False; True = nn.Upsample(scale_factor=2, mode='trilinear'), :236) and cfg['res']
+    (default False; True = ``enc(x) + x`` / ``dec(cat) + x``, :264,275)."""
     encs, decs, act = cfg["encoders"], cfg["decoders"], cfg["act"]
+    maxpool, upsample, res = cfg.get("maxpool", True), cfg.get("upsample", False), cfg.get("res", False)
     skips = []
     for i, enc in enumerate(encs):
         chans = ((in_channel,) + tuple(enc)) if i == 0 else tuple(enc)
+        y = x
         for k in range(len(chans) - 1):
-            x = unet_conv_block(x, sd, f"encoders.{i}.{k}", bn, act, training, stats_out)
+            y = unet_conv_block(y, sd, f"encoders.{i}.{k}", bn, act, training, stats_out)
+        x = (y + x) if res else y
         if i < len(encs) - 1:
             skips.append(x)
-            x = F.max_pool3d(x, 2)
+            if maxpool:
+                x = F.max_pool3d(x, 2)
+            else:
+                x = F.conv3d(x, sd[f"down_samplers.{i}.weight"], sd.get(f"down_samplers.{i}.bias"), stride=2)
     n_inner = len(tuple(encs[-1])) - 1  # unets.py:247 re-uses the encoder loop variable
     for j, dec in enumerate(decs):
-        x = unet_deconv_block(x, sd, f"up_samplers.{j}", bn, act, 2, 2, 0, training, stats_out)
-        x = torch.cat((x, skips.pop()), dim=1)
+        if upsample:
+            x = F.interpolate(x, scale_factor=2, mode="trilinear")
+        else:
+            x = unet_deconv_block(x, sd, f"up_samplers.{j}", bn, act, 2, 2, 0, training, stats_out)
+        y = torch.cat((x, skips.pop()), dim=1)
         for k in range(n_inner):
-            x = unet_conv_block(x, sd, f"decoders.decBlock{j}.{k}", bn, act, training, stats_out)
+            y = unet_conv_block(y, sd, f"decoders.decBlock{j}.{k}", bn, act, training, stats_out)
         if j == len(decs) - 1:
             p = f"decoders.decBlock{j}.{n_inner}"
-            x = F.conv3d(x, sd[p + ".weight"], sd.get(p + ".bias"))
+            y = F.conv3d(y, sd[p + ".weight"], sd.get(p + ".bias"))
+        x = (y + x) if res else y
     return x
 
 
@@ -255,6 +267,96 @@ def bending_energy(u, spacing=(1.0, 1.0, 1.0), normalize=True):
              - u[:, :, :-2, 1:-1, 2:]) * (dims * sp / (sp[2] * sp[0])) ** 2
     return (ddx.mean() + ddy.mean() + ddz.mean() + 2 * dxdy.mean() + 2 * dydz.mean()
             + 2 * dxdz.mean()) / 9.0
+
+
+def ncc_loss(a, b):
+    """NormalizedCrossCorrelationLoss.forward (lib/loss.py:493-501)."""
+    a = a.reshape(a.shape[0], -1)
+    b = b.reshape(b.shape[0], -1)
+    am = a - torch.mean(a, 1, keepdim=True)
+    bm = b - torch.mean(b, 1, keepdim=True)
+    ncc = (am * bm).mean(1) / (torch.sqrt((am ** 2).mean(1)) * torch.sqrt((bm ** 2).mean(1)))
+    return 1 - ncc.mean()
+
+
+def mse_loss(a, b):
+    """nn.MSELoss() (registry 'mse', lib/loss.py:742) == lib/loss.py:504-509."""
+    return ((a - b) ** 2).mean()
+
+
+def l2_loss(a):
+    """L2Loss.forward (lib/loss.py:733-736)."""
+    return (a ** 2).mean()
+
+
+def gradient_loss(u, norm="L2", spacing=(1.0, 1.0, 1.0), normalize=True):
+    """gradientLoss.forward (lib/loss.py:636-671), with the `+` of the H and W differences (:657,659) and the
+    per-channel scale (:663-665) as they are."""
+    sp = torch.tensor(spacing, dtype=torch.float32)
+    if normalize:
+        sp = sp / sp.min()
+    sp = sp.to(u.dtype)
+    dims = torch.tensor(u.shape[2:], dtype=torch.float32)
+    if normalize:
+        dims = dims / dims.min()
+    dims = dims.to(u.dtype)
+    B, C = u.shape[:2]
+    dx = torch.abs(u[:, :, 2:, :, :] - u[:, :, :-2, :, :]).reshape(B, C, -1)
+    dy = torch.abs(u[:, :, :, 2:, :] + u[:, :, :, :-2, :]).reshape(B, C, -1)
+    dz = torch.abs(u[:, :, :, :, 2:] + u[:, :, :, :, :-2]).reshape(B, C, -1)
+    if norm == "L2":
+        dx = (dx ** 2).mean(2) * (dims * sp / sp[0]) ** 2
+        dy = (dy ** 2).mean(2) * (dims * sp / sp[1]) ** 2
+        dz = (dz ** 2).mean(2) * (dims * sp / sp[2]) ** 2
+    return (dx.mean() + dy.mean() + dz.mean()) / 3.0
+
+
+def focal_loss(inputs, targets, alpha=None, gamma=2, size_average=True, soft_max=True):
+    """FocalLoss.forward (lib/loss.py:149-186).  ``F.nll_loss(P, t)`` returns -P[t], hence (1 + P[t])**gamma."""
+    C = inputs.shape[1]
+    x = inputs.permute(0, 2, 3, 4, 1).contiguous().view(-1, C)
+    t = targets.reshape(-1).long()
+    P = F.softmax(x, dim=1) if soft_max else x
+    a = torch.ones(C, 1, dtype=inputs.dtype) if alpha is None else alpha.to(inputs.dtype)
+    a = a[t].view(-1)
+    log_p = -F.cross_entropy(x, t, reduction="none")
+    probs = F.nll_loss(P, t, reduction="none")
+    batch_loss = -a * (torch.pow((1 - probs), gamma)) * log_p
+    return batch_loss.mean() if size_average else batch_loss.sum()
+
+
+def cross_entropy(x, t, weight=None, ignore_index=-100, reduction="mean"):
+    """nn.CrossEntropyLoss (registry 'cross_entropy', lib/loss.py:748)."""
+    return F.cross_entropy(x, t if t.is_floating_point() else t.long(), weight=weight, ignore_index=ignore_index,
+                           reduction=reduction)
+
+
+def soft_cross_entropy(pred, target, softmax=False):
+    """SoftCrossEntropy.forward (lib/loss.py:112-116) for a class-probability target of the shape of pred.
+    (The reference clamps ``pred`` in place when softmax is False; the value is the same.)"""
+    if softmax:
+        return torch.mean(torch.sum(-target * F.log_softmax(pred, 1), 1))
+    return torch.mean(torch.sum(-target * torch.log(pred.clamp(min=1e-8)), 1))
+
+
+def upsample_trilinear2_closed_form(x):
+    """nn.Upsample(scale_factor=2, mode='trilinear') written out (align_corners=False, scale 1/2):
+    src = max(0.5*(dst+0.5)-0.5, 0), i0 = floor(src), i1 = min(i0+1, n-1), weights (1-frac, frac) per axis."""
+    def axis(n):
+        dst = torch.arange(2 * n, dtype=torch.float64)
+        src = (0.5 * (dst + 0.5) - 0.5).clamp(min=0)
+        i0 = src.floor().long()
+        i1 = (i0 + 1).clamp(max=n - 1)
+        l1 = (src - i0).to(x.dtype)
+        return i0, i1, 1 - l1, l1
+    D, H, W = x.shape[2:]
+    out = x
+    for dim, n in ((2, D), (3, H), (4, W)):
+        i0, i1, l0, l1 = axis(n)
+        shape = [1] * 5
+        shape[dim] = -1
+        out = out.index_select(dim, i0) * l0.view(shape) + out.index_select(dim, i1) * l1.view(shape)
+    return out
 
 
 # --------------------------------------------------------------------------------------------

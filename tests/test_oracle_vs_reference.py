@@ -132,3 +132,95 @@ def test_registry_seams(ref):
     finally:
         ref.network_dic.clear(); ref.network_dic.update(keep_n)
         ref.loss_dict.clear(); ref.loss_dict.update(keep_l)
+
+
+# ---- the remaining registry losses and the UNet_generator variants ------------------
+def test_port_remaining_losses(ref):
+    g = _g()
+    a, b = torch.rand((2, 1, 7, 8, 9), generator=g), torch.rand((2, 1, 7, 8, 9), generator=g)
+    assert torch.equal(P.ncc_loss(a, b), ref.get_loss_function("ncc")()(a, b))
+    assert torch.equal(P.mse_loss(a, b), ref.get_loss_function("mse")()(a, b))
+    assert torch.equal(P.mse_loss(a, b), ref.loss.MSELoss()(a, b))
+    assert torch.equal(P.l2_loss(a), ref.get_loss_function("L2")()(a))
+    u = torch.randn((2, 3, 8, 9, 10), generator=g) * 0.1
+    for norm in ("L2", "L1"):
+        for sp in ((1, 1, 1), (1.0, 1.5, 2.0)):
+            assert torch.equal(P.gradient_loss(u, norm, sp), ref.get_loss_function("gradient")(norm=norm, spacing=sp)(u))
+    C = 5
+    x = torch.randn((2, C, 6, 7, 8), generator=g)
+    t = torch.randint(0, C, (2, 6, 7, 8), generator=g)
+    soft = torch.softmax(torch.randn((2, C, 6, 7, 8), generator=g), 1)
+    w = torch.rand(C, generator=g) + 0.5
+    assert torch.equal(P.cross_entropy(x, t), ref.get_loss_function("cross_entropy")()(x, t))
+    assert torch.equal(P.cross_entropy(x, t, weight=w), ref.get_loss_function("cross_entropy")(weight=w)(x, t))
+    for soft_max in (True, False):
+        for size_average in (True, False):
+            xin = x if soft_max else torch.softmax(x, 1)
+            crit = ref.get_loss_function("focal")(C, gamma=2, size_average=size_average, soft_max=soft_max)
+            assert torch.equal(P.focal_loss(xin, t, None, 2, size_average, soft_max), crit(xin, t))
+    alpha = (torch.rand(C, 1, generator=g) + 0.5)
+    assert torch.equal(P.focal_loss(x, t, alpha, 1.5), ref.get_loss_function("focal")(C, alpha=alpha, gamma=1.5)(x, t))
+    assert torch.equal(P.soft_cross_entropy(x, soft, True), ref.get_loss_function("soft_cross_entropy")(softmax=True)(x, soft))
+    p = torch.softmax(x, 1)
+    p[0, 0, 0, 0, :3] = 0.0     # exercises the 1e-8 clamp
+    assert torch.equal(P.soft_cross_entropy(p, soft, False),
+                       ref.get_loss_function("soft_cross_entropy")(softmax=False)(p.clone(), soft))
+
+
+def test_mirror_registry_is_complete(ref):
+    """Every name of the reference's loss registry resolves in the mirror, with the reference's constructor
+    argument names (lib/loss.py:739-750)."""
+    import inspect
+
+    import deepatlas_b200 as da
+    assert set(da.loss_dict) == set(ref.loss_dict)
+    for name in ("ncc", "gradient", "L2", "focal", "soft_cross_entropy", "dice", "lncc", "bendingEnergy"):
+        rp = list(inspect.signature(ref.loss_dict[name].__init__).parameters)
+        mp = list(inspect.signature(da.loss_dict[name].__init__).parameters)
+        norm = lambda q: ["self"] if q == ["self", "args", "kwargs"] else q   # nn.Module's default __init__  # noqa: E731
+        assert norm(rp) == norm(mp), name
+    with pytest.raises(KeyError):
+        da.get_loss_function("nope")
+
+
+VARIANTS = [dict(maxpool=False), dict(upsample=True), dict(res=True), dict(maxpool=False, upsample=True, res=True)]
+
+
+def _variant_cfg(kw):
+    if kw.get("res"):      # channel counts the reference's `+` accepts: equal, or a single input channel
+        enc, dec = [(8, 8), (8, 8)], [(8, 8)]
+    elif kw.get("upsample"):
+        enc, dec = [(4, 8), (8, 8, 16)], [(16, 8, 8)]
+    else:
+        enc, dec = [(4, 8), (8, 8, 16)], [(8, 8, 8)]
+    return enc, dec
+
+
+@pytest.mark.parametrize("kw", VARIANTS)
+def test_port_and_mirror_unet_generator_variants(ref, kw):
+    import deepatlas_b200 as da
+    from deepatlas_b200 import networks as M
+    enc, dec = _variant_cfg(kw)
+    n_classes = 8 if kw.get("res") else 3
+    torch.manual_seed(230)
+    net = ref.network_factory.unets.UNet_generator(enc, dec, act="LeakyReLU", **kw)(1, n_classes, bias=True, BN=True)
+    net.weights_init()
+    net.train()
+    torch.manual_seed(230)
+    mir = M.UNet_generator(enc, dec, act="LeakyReLU", **kw)(1, n_classes, bias=True, BN=True)
+    mir.weights_init()
+    rs, ms = net.state_dict(), mir.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+    x = torch.rand((1, 1, 8, 12, 8), generator=_g())
+    sd = {k: v.clone() for k, v in rs.items()}
+    cfg = dict(encoders=enc, decoders=dec, act="LeakyReLU", **kw)
+    assert torch.equal(P.unet_generator_forward(x, sd, 1, True, cfg=cfg), net(x))
+    assert da is not None
+
+
+def test_port_upsample_closed_form():
+    x = torch.rand((1, 2, 3, 4, 5), generator=_g(), dtype=torch.float64)
+    ref_out = torch.nn.Upsample(scale_factor=2, mode="trilinear")(x)
+    assert float((P.upsample_trilinear2_closed_form(x) - ref_out).abs().max()) < 1e-14
