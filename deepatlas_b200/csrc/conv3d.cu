@@ -947,11 +947,20 @@ inline unsigned long long* umma_dbg_buffer() {
 int launch_umma(const UmmaArgs& a, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(conv3d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
     configured = true;
   }
   dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N * a.nco);
-  conv3d_umma_kernel<<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+  if (a.dbg) {
+    if (a.accumulate) conv3d_umma_kernel<true, true><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+    else conv3d_umma_kernel<true, false><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+  } else {
+    if (a.accumulate) conv3d_umma_kernel<false, true><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+    else conv3d_umma_kernel<false, false><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+  }
   return da_check_launch("conv3d_umma");
 }
 

@@ -24,10 +24,12 @@
 constexpr int UM_TX = 40, UM_TY = 6, UM_PX = UM_TX + 2;  // (a 128-byte aligned pitch of 48 was measured: no gain)
 constexpr int UM_PLANE = (UM_TY + 2) * UM_PX;  // 336 positions staged per plane
 constexpr int UM_PFA = 344;                    // allocated positions per channel chunk (>= 2*128 + 2*PX)
-constexpr int UM_MT = 2;                       // M tiles per plane (2*128 >= TY*PX = 252)
-constexpr int UM_NPROD = 224;                  // producer threads (7 warps)
+constexpr int UM_MT = 2;                       // M tiles per plane
+constexpr int UM_MSTEP = 126;                  // the two M tiles overlap by two rows: each folds kx on its own (rows 1..126)
+constexpr int UM_NPROD = 96;                   // producer threads (3 warps): 20 warps in all = 5 per SM sub-partition, which leaves 96
+                                               // registers per thread (6 per sub-partition cap them at 80 and the epilogue spills)
 constexpr int UM_NEPI = 512;                   // epilogue threads: warp w handles TMEM lane quadrant w%4, M tile (w/4)%2, output-channel half w/8
-constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-15 epilogue, 16 MMA issue, 17.. producers (768 threads, 85 registers)
+constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-15 epilogue, 16 MMA issue, 17-19 producers (640 threads)
 constexpr int UM_MMA_WARP = UM_NEPI / 32;
 constexpr int UM_CB = 16, UM_KC = 16;          // output channels per launch, input channels per launch
 constexpr int UM_NB = 3 * UM_CB;               // columns of one accumulator block: (kx, co)
@@ -35,7 +37,7 @@ constexpr int UM_N = 3 * UM_NB;                // MMA N: three blocks = three ou
 constexpr int UM_NCH = UM_KC / 4;
 constexpr int UM_WROWS = 5 * UM_NB;            // weight rows: kz blocks in the order 2,1,0,2,1 (any cyclic rotation is contiguous)
 static_assert(UM_MT * 128 + 2 * UM_PX <= UM_PFA, "shifted A rows must stay inside the slot");
-static_assert(UM_MT * 128 >= UM_TY * UM_PX, "M tiles must cover the output rows");
+static_assert(UM_MT * UM_MSTEP >= UM_TY * UM_PX, "M tiles must cover the output rows");
 
 struct UmmaCfg {
   static constexpr int SLOT_FLOATS = 2 * UM_NCH * UM_PFA * 4;        // hi + lo
@@ -118,6 +120,7 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
+template <bool DBG, bool ACC>   // cycle counters (DA_UMMA_DEBUG=1); a.accumulate (further input-channel chunks)
 __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) {
   using Cfg = UmmaCfg;
   constexpr int N = UM_N, NCH = UM_NCH, NB = UM_NB;
@@ -175,9 +178,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 
   if (warp > UM_MMA_WARP) {
     // =============================== producers ===============================
-    // thread = one 4-channel chunk (grp) x UM_PPT fixed in-plane positions: everything but the plane offset is loop invariant
-    constexpr int TPG = UM_NPROD / NCH;          // 56 threads per channel chunk
-    constexpr int PPT = UM_PLANE / TPG;          // 6 positions per thread
+    // thread = one 4-channel chunk (grp) x PPT fixed in-plane positions: everything but the plane offset is loop
+    // invariant, and all 4*PPT loads of a plane are in flight together (one memory latency per plane)
+    constexpr int TPG = UM_NPROD / NCH;          // 24 threads per channel chunk
+    constexpr int PPT = UM_PLANE / TPG;          // 14 positions per thread
     static_assert(TPG * NCH == UM_NPROD && PPT * TPG == UM_PLANE, "producer mapping must tile the plane exactly");
     const int tp = threadIdx.x - (UM_NEPI + 32);
     const int grp = tp / TPG, ti = tp - grp * TPG;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       const int f = ti + TPG * b;
       const int hy = f / UM_PX, hx = f - hy * UM_PX;
       const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
-      oxy[b] = (hx < UM_TX + 2 && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? gy * a.W + gx : -1;
+      oxy[b] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? gy * a.W + gx : -1;
     }
     for (int pi = 0; pi < nsteps; ++pi) {
       const int slot = pi % 3, use = pi / 3;
@@ -234,25 +238,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     constexpr uint32_t A_LBO = UM_PFA * 16, B_LBO = UM_WROWS * 16;
     const uint64_t adesc0 = umma_desc(0, A_LBO, 128), bdesc0 = umma_desc(0, B_LBO, 128);
     long long t_acc = 0, t_plane = 0, t_issue = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = DBG ? clock64() : 0;
     for (int pi = 0; pi < nsteps; ++pi) {
-      const long long t0 = clock64();
+      const long long t0 = DBG ? clock64() : 0;
       mbar_wait(&plane_full[pi % 3], (pi / 3) & 1);
-      const long long t1 = clock64();
+      const long long t1 = DBG ? clock64() : 0;
       t_plane += t1 - t0;
       const uint32_t slot_s = ring_s + (uint32_t)(pi % 3) * (Cfg::SLOT_FLOATS * 4);
       const uint32_t brot = sw_s + (uint32_t)(2 - pi % 3) * (NB * 16);  // block b of this step holds kz = (pi - b) mod 3
 #pragma unroll 1
       for (int mt = 0; mt < UM_MT; ++mt) {
-        const long long t2 = clock64();
+        const long long t2 = DBG ? clock64() : 0;
         if (pi > 0) mbar_wait(&acc_empty[mt], (pi - 1) & 1);  // the epilogue has read + zeroed the block finished by step pi-1
-        t_acc += clock64() - t2;
+        if (DBG) t_acc += clock64() - t2;
         tc_fence_after();
         if (elected) {
           const uint32_t dcol = tmem + (uint32_t)mt * N;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint32_t arow = slot_s + (uint32_t)(mt * 128 + ky * UM_PX) * 16;  // (PX + mt*128) + (ky-1)*PX
+            const uint32_t arow = slot_s + (uint32_t)(mt * UM_MSTEP + ky * UM_PX) * 16;  // (PX + mt*MSTEP) + (ky-1)*PX
             const uint32_t wt = brot + (uint32_t)(ky * NCH * UM_WROWS) * 16;
 #pragma unroll
             for (int j2 = 0; j2 < UM_KC / 8; ++j2) {
@@ -270,9 +274,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
         }
         __syncwarp();
       }
-      t_issue += clock64() - t1;
+      if (DBG) t_issue += clock64() - t1;
     }
-    if (a.dbg && lane == 0) {
+    if (DBG && a.dbg && lane == 0) {
       atomicAdd(a.dbg + 0, (unsigned long long)t_acc); atomicAdd(a.dbg + 1, (unsigned long long)t_plane);
       atomicAdd(a.dbg + 2, (unsigned long long)t_issue); atomicAdd(a.dbg + 3, (unsigned long long)(clock64() - t_begin));
       atomicAdd(a.dbg + 4, (unsigned long long)nsteps); atomicAdd(a.dbg + 5, 1ull);
@@ -282,11 +286,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     static_assert(UM_MT == 2 && UM_NEPI == 512 && UM_CB == 16, "one epilogue warp per (M tile, lane quadrant, channel half)");
     // two warps share every 32-row group and split its 16 output channels: the epilogue is latency bound per warp
     // (dependent TMEM load -> shuffle -> store chains), so twice the warps halve its share of the plane step
-    const int w = warp & 3, mt = (warp >> 2) & 1, wg = warp & 7, ch0 = (warp >> 3) * 8;  // rows [32*wg, 32*wg + 32)
-    const int fc = UM_PX + wg * 32 + lane;
+    // M tile mt covers plane rows [PX + mt*MSTEP, +128) and produces the outputs of its rows 1..126: the kx fold never
+    // crosses an M tile, so the two tiles' epilogues run independently (a CTA-wide barrier here cost 1k of 4.7k cycles)
+    const int w = warp & 3, mt = (warp >> 2) & 1, wg = warp & 7, ch0 = (warp >> 3) * 8;
+    const int lrow = w * 32 + lane;                      // row within the M tile
+    const int fc = UM_PX + mt * UM_MSTEP + lrow;
     const int hy = fc / UM_PX, hx = fc - hy * UM_PX;
     const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
-    const bool valid = hx >= 1 && hx <= UM_TX && hy <= UM_TY && gy < a.H && gx < a.W;
+    const bool valid = lrow >= 1 && lrow <= UM_MSTEP && hx >= 1 && hx <= UM_TX && hy <= UM_TY && gy < a.H && gx < a.W;
     const uint32_t trow = tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)mt * N;
     // bias in registers: a load inside the store loop cannot be hoisted past the stores (possible aliasing) and costs a
     // full L2 round trip per output channel (measured: 6.2k of the 7.1k cycles of a plane step)
@@ -294,21 +301,60 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 #pragma unroll
     for (int c = 0; c < 8; ++c) bv[c] = (a.last && a.bias && co0 + ch0 + c < a.Cout) ? __ldg(a.bias + co0 + ch0 + c) : 0.f;
     const bool do_act = a.last && a.act;
+    // The kx fold needs row f-1 (tap 0) and f+1 (tap 2).  Inside a warp they come by shuffle; the two rows at the warp's
+    // ends need the neighbouring warp's edge values, which travel through shared memory.  A store -> barrier -> load
+    // chain inside the step cost 1k of its 4.7k cycles (shared memory is saturated by the MMA operand fetch, every round
+    // trip is several hundred cycles), so the two edge lanes DEFER their rows by one step: they keep the partial sum in
+    // `pend`, and finish it at the next step, when the neighbour's values have long been published.
+    const bool edge_lo = lane == 0 && w > 0, edge_hi = lane == 31 && w < 3;   // rows that wait for a neighbouring warp
+    const bool edge_lane = lane == 0 || lane == 31;
+    float pend[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pend[c] = 0.f;
     long long e_wait = 0, e_tmem = 0, e_bar = 0, e_out = 0;
-    const long long e_begin = clock64();
+    const long long e_begin = DBG ? clock64() : 0;
+    float* const obase = a.out + ((int64_t)n * a.Cout + co0 + ch0) * V + (int64_t)gy * a.W + gx;
+    const int nb = edge_lo ? wg - 1 : wg + 1, side = edge_lo ? 0 : 1;   // indices, not pointers: keeps LDS addressing
+    float e[8];
+    // fetch the neighbouring warp's edge values of step `pstep` (issued early, consumed by store_edges after the TMEM phase)
+    auto fetch_edges = [&](int pstep) {
+      const long long b0 = DBG ? clock64() : 0;
+      named_bar_sync(1 + mt, UM_NEPI / UM_MT);           // every warp of this M tile has published that step's edges
+      if (DBG) e_bar += clock64() - b0;
+      if (edge_lo || edge_hi) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) e[c] = edge_s[pstep & 1][nb][side][ch0 + c];
+      }
+    };
+    auto store_edges = [&](float* opp) {
+      if (edge_lo || edge_hi) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float r = pend[c];
+          if (do_act) r = r > 0.f ? r : r * a.slope;
+          if (valid && co0 + ch0 + c < a.Cout) opp[(int64_t)c * V] = r;
+        }
+      }
+      __syncwarp();
+    };
     for (int pi = 0; pi < nsteps; ++pi) {
       const int ol = pi - 2;                 // output plane completed by this step (local index), if >= 0
       const int blk = (pi + 1) % 3;          // = (pi - 2) mod 3
       const bool live = ol >= 0;             // ol < zcount always (nsteps = zcount + 2)
-      float* op = a.out + ((int64_t)n * a.Cout + co0 + ch0) * V + (int64_t)(z0 + ol) * HW + (int64_t)gy * a.W + gx;
+      float* op = obase + (int64_t)(z0 + ol) * HW;
+      if (ol > 0) fetch_edges(pi - 1);       // the previous plane's edge rows: their neighbours' values are a step old
       // the previous chunks' partial output does not depend on this step's MMAs: fetch it before waiting for them
       float old[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) old[c] = (a.accumulate && live && valid && co0 + ch0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
-      const long long e0 = clock64();
+      for (int c = 0; c < 8; ++c) old[c] = (ACC && live && valid && co0 + ch0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
+      const long long e0 = DBG ? clock64() : 0;
       mbar_wait(&acc_full[mt], pi & 1);
-      const long long e1 = clock64();
+      const long long e1 = DBG ? clock64() : 0;
       tc_fence_after();
+      if (ol > 0 && (edge_lo || edge_hi)) {   // the edge values had the whole wait to arrive; folding them in here frees e[]
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pend[c] += e[c];
+      }
       float v[3][8];
       if (live) {
 #pragma unroll
@@ -320,47 +366,40 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&acc_empty[mt]);  // block read and cleared: the next step may accumulate into it
-      e_wait += e1 - e0; e_tmem += clock64() - e1;
+      if (DBG) { e_wait += e1 - e0; e_tmem += clock64() - e1; }
       if (!live) continue;          // uniform over the CTA
-      // kx fold needs row f-1 (tap 0) and f+1 (tap 2): neighbours by shuffle, warp edges through shared memory
-      const int eb = pi & 1;
+      const long long e3 = DBG ? clock64() : 0;
+      if (ol > 0) store_edges(op - HW);
       if (lane == 31) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) edge_s[eb][wg][0][ch0 + c] = v[0][c];
+        for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][0][ch0 + c] = v[0][c];
       }
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) edge_s[eb][wg][1][ch0 + c] = v[2][c];
-      }
-      const long long e2 = clock64();
-      named_bar_sync(1, UM_NEPI);
-      const long long e3 = clock64();
-      e_bar += e3 - e2;
-      // Branch-free fold: tap-0 values travel one lane up, tap-2 values one lane down, as ROTATIONS; the lane that would
-      // wrap around first replaces the value it sends by the neighbouring warp's edge row (its own was published above).
-      if (lane == 31) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[0][c] = (wg > 0) ? edge_s[eb][wg - 1][0][ch0 + c] : 0.f;
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[2][c] = (wg < 7) ? edge_s[eb][wg + 1][1][ch0 + c] : 0.f;
+        for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][1][ch0 + c] = v[2][c];
       }
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float left = __shfl_sync(0xffffffffu, v[0][c], (lane + 31) & 31);
-        const float right = __shfl_sync(0xffffffffu, v[2][c], (lane + 1) & 31);
-        float r = v[1][c] + left + right + old[c];
-        const int co = co0 + ch0 + c;
-        r += bv[c];
+        float left = __shfl_sync(0xffffffffu, v[0][c], (lane + 31) & 31);
+        float right = __shfl_sync(0xffffffffu, v[2][c], (lane + 1) & 31);
+        if (lane == 0) left = 0.f;      // wrapped around: the true neighbour lives in another warp (added by store_edges)
+        if (lane == 31) right = 0.f;
+        float r = v[1][c] + left + right + old[c] + bv[c];
+        pend[c] = r;
         if (do_act) r = r > 0.f ? r : r * a.slope;
-        if (valid && co < a.Cout && !(a.flags & 1)) op[(int64_t)c * V] = r;
+        if (valid && !edge_lane && co0 + ch0 + c < a.Cout && !(a.flags & 1)) op[(int64_t)c * V] = r;
         if ((a.flags & 1) && r == 1.2345e33f) op[(int64_t)c * V] = r;  // debug: keep the dependency, drop the store
       }
-      e_out += clock64() - e3;
+      if (DBG) e_out += clock64() - e3;
     }
-    if (a.dbg && threadIdx.x == 0) {
+    fetch_edges(nsteps - 1);
+    if (edge_lo || edge_hi) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) pend[c] += e[c];
+    }
+    store_edges(obase + (int64_t)(z0 + nsteps - 3) * HW);
+    if (DBG && a.dbg && threadIdx.x == 0) {
       atomicAdd(a.dbg + 9, (unsigned long long)e_bar); atomicAdd(a.dbg + 10, (unsigned long long)e_out);
       atomicAdd(a.dbg + 6, (unsigned long long)e_wait); atomicAdd(a.dbg + 7, (unsigned long long)e_tmem);
       atomicAdd(a.dbg + 8, (unsigned long long)(clock64() - e_begin));

@@ -16,24 +16,41 @@ constexpr int BN_SPLITS = 32;  // blocks per channel for the statistics passes
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) { return (act && z <= 0.f) ? z * slope : z; }
 __device__ __forceinline__ float act_grad(float z, int act, float slope) { return (act && z <= 0.f) ? slope : 1.f; }
 
-// partials [C][BN_SPLITS][2] (sum, sumsq) in fp64
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t V,
+// partials [C][BN_SPLITS][2] (sum, sumsq) in fp64.  vec: V % 4 == 0 and 16-byte aligned base -> 16-byte loads, four
+// independent ones in flight per thread (a scalar one-load-per-iteration loop left half of the HBM bandwidth unused)
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t V, int vec,
                                                               double* __restrict__ partials) {
   __shared__ double red[BN_THREADS / 32];
   const int c = blockIdx.x, s = blockIdx.y;
-  const int64_t chunk = da_cdiv(V, BN_SPLITS);
   double a1 = 0, a2 = 0;
   for (int n = 0; n < N; ++n) {
     const float* p = x + ((int64_t)n * C + c) * V;
-    const int64_t lo = (int64_t)s * chunk, hi = min(V, lo + chunk);
-    float f1 = 0.f, f2 = 0.f;
-    int k = 0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
-      const float v = p[i];
-      f1 += v; f2 = fmaf(v, v, f2);
-      if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+    if (vec) {
+      const int64_t V4 = V >> 2, chunk = da_cdiv(V4, BN_SPLITS);
+      const int64_t lo = (int64_t)s * chunk, hi = min(V4, lo + chunk);
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      float f1 = 0.f, f2 = 0.f;
+      int k = 0;
+#pragma unroll 4
+      for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
+        const float4 v = __ldg(p4 + i);
+        f1 += (v.x + v.y) + (v.z + v.w);
+        f2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, f2))));
+        if (++k == 8) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+      }
+      a1 += (double)f1; a2 += (double)f2;
+    } else {
+      const int64_t chunk = da_cdiv(V, BN_SPLITS);
+      const int64_t lo = (int64_t)s * chunk, hi = min(V, lo + chunk);
+      float f1 = 0.f, f2 = 0.f;
+      int k = 0;
+      for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
+        const float v = p[i];
+        f1 += v; f2 = fmaf(v, v, f2);
+        if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+      }
+      a1 += (double)f1; a2 += (double)f2;
     }
-    a1 += (double)f1; a2 += (double)f2;
   }
   const double b1 = block_sum<double, BN_THREADS / 32>(a1, red);
   const double b2 = block_sum<double, BN_THREADS / 32>(a2, red);
@@ -95,25 +112,45 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const float* __restrict
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                   const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                  int N, int C, int64_t V, int act, float slope,
+                                                                  int N, int C, int64_t V, int act, float slope, int vec,
                                                                   double* __restrict__ partials) {
   __shared__ double red[BN_THREADS / 32];
   const int c = blockIdx.x, s = blockIdx.y;
   const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-  const int64_t chunk = da_cdiv(V, BN_SPLITS);
   double a1 = 0, a2 = 0;
   for (int n = 0; n < N; ++n) {
     const int64_t base = ((int64_t)n * C + c) * V;
-    const int64_t lo = (int64_t)s * chunk, hi = min(V, lo + chunk);
-    float f1 = 0.f, f2 = 0.f;
-    int k = 0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
-      const float xh = (x[base + i] - mu) * is;
-      const float g = dy[base + i] * act_grad(xh * ga + be, act, slope);
-      f1 += g; f2 = fmaf(g, xh, f2);
-      if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+    if (vec) {
+      const int64_t V4 = V >> 2, chunk = da_cdiv(V4, BN_SPLITS);
+      const int64_t lo = (int64_t)s * chunk, hi = min(V4, lo + chunk);
+      const float4* x4 = reinterpret_cast<const float4*>(x + base);
+      const float4* d4 = reinterpret_cast<const float4*>(dy + base);
+      float f1 = 0.f, f2 = 0.f;
+      int k = 0;
+#pragma unroll 2
+      for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
+        const float4 xv = __ldg(x4 + i), dv = __ldg(d4 + i);
+        const float xh0 = (xv.x - mu) * is, xh1 = (xv.y - mu) * is, xh2 = (xv.z - mu) * is, xh3 = (xv.w - mu) * is;
+        const float g0 = dv.x * act_grad(xh0 * ga + be, act, slope), g1 = dv.y * act_grad(xh1 * ga + be, act, slope);
+        const float g2 = dv.z * act_grad(xh2 * ga + be, act, slope), g3 = dv.w * act_grad(xh3 * ga + be, act, slope);
+        f1 += (g0 + g1) + (g2 + g3);
+        f2 = fmaf(g0, xh0, fmaf(g1, xh1, fmaf(g2, xh2, fmaf(g3, xh3, f2))));
+        if (++k == 8) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+      }
+      a1 += (double)f1; a2 += (double)f2;
+    } else {
+      const int64_t chunk = da_cdiv(V, BN_SPLITS);
+      const int64_t lo = (int64_t)s * chunk, hi = min(V, lo + chunk);
+      float f1 = 0.f, f2 = 0.f;
+      int k = 0;
+      for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
+        const float xh = (x[base + i] - mu) * is;
+        const float g = dy[base + i] * act_grad(xh * ga + be, act, slope);
+        f1 += g; f2 = fmaf(g, xh, f2);
+        if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
+      }
+      a1 += (double)f1; a2 += (double)f2;
     }
-    a1 += (double)f1; a2 += (double)f2;
   }
   const double b1 = block_sum<double, BN_THREADS / 32>(a1, red);
   const double b2 = block_sum<double, BN_THREADS / 32>(a2, red);
@@ -143,12 +180,29 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ s12, int C, int64_t V, float invM,
-                                                         int training, int act, float slope, float* __restrict__ dx) {
+                                                         int training, int act, float slope, int vec, float* __restrict__ dx) {
   const int c = blockIdx.y, n = blockIdx.z;
   const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
   const float m1 = training ? s12[2 * c] * invM : 0.f, m2 = training ? s12[2 * c + 1] * invM : 0.f;
   const float k = ga * is;
   const int64_t base = ((int64_t)n * C + c) * V;
+  if (vec) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + base);
+    const float4* d4 = reinterpret_cast<const float4*>(dy + base);
+    float4* o4 = reinterpret_cast<float4*>(dx + base);
+#pragma unroll 2
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < (V >> 2); i += (int64_t)gridDim.x * 256) {
+      const float4 xv = __ldg(x4 + i), dv = __ldg(d4 + i);
+      float4 o;
+      float xh, g;
+      xh = (xv.x - mu) * is; g = dv.x * act_grad(xh * ga + be, act, slope); o.x = k * (g - m1 - xh * m2);
+      xh = (xv.y - mu) * is; g = dv.y * act_grad(xh * ga + be, act, slope); o.y = k * (g - m1 - xh * m2);
+      xh = (xv.z - mu) * is; g = dv.z * act_grad(xh * ga + be, act, slope); o.z = k * (g - m1 - xh * m2);
+      xh = (xv.w - mu) * is; g = dv.w * act_grad(xh * ga + be, act, slope); o.w = k * (g - m1 - xh * m2);
+      o4[i] = o;
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < V; i += (int64_t)gridDim.x * 256) {
     const float xh = (x[base + i] - mu) * is;
     const float g = dy[base + i] * act_grad(xh * ga + be, act, slope);
@@ -158,7 +212,19 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const float* __restrict
 
 // dx = dy * (y > 0 ? 1 : slope)
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float slope,
-                                                      int64_t total, float* __restrict__ dx) {
+                                                      int64_t total, int vec, float* __restrict__ dx) {
+  if (vec) {
+    const float4* d4 = reinterpret_cast<const float4*>(dy);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    float4* o4 = reinterpret_cast<float4*>(dx);
+#pragma unroll 2
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < (total >> 2); i += (int64_t)gridDim.x * 256) {
+      const float4 d = __ldg(d4 + i), v = __ldg(y4 + i);
+      o4[i] = make_float4(v.x > 0.f ? d.x : d.x * slope, v.y > 0.f ? d.y : d.y * slope, v.z > 0.f ? d.z : d.z * slope,
+                          v.w > 0.f ? d.w : d.w * slope);
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256)
     dx[i] = y[i] > 0.f ? dy[i] : dy[i] * slope;
 }
@@ -262,6 +328,8 @@ __global__ void __launch_bounds__(256) upsample_nearest_bwd_kernel(const float* 
   }
 }
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 inline int ew_grid(int64_t total, int per_block = 256) {
   int64_t b = da_cdiv(total, per_block);
   const int64_t cap = (int64_t)DA_NUM_SMS * 16;
@@ -280,7 +348,7 @@ DA_API int da_bn_stats(const float* x, int N, int C, int64_t V, float eps, float
   DA_REQUIRE(x && mean && invstd && workspace, "da_bn_stats: null pointer");
   if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_stats: workspace too small"); return DA_ERR_WORKSPACE; }
   dim3 grid(C, BN_SPLITS);
-  bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, (double*)workspace);
+  bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, ((V & 3) == 0 && aligned16(x)) ? 1 : 0, (double*)workspace);
   bn_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean,
                                                         invstd, running_mean, running_var);
   return da_check_launch("da_bn_stats", 2);
@@ -303,17 +371,19 @@ DA_API int da_bn_act_bwd(const float* dy, const float* x, const float* mean, con
   double* partials = (double*)workspace;
   float* s12 = (float*)(partials + (int64_t)C * BN_SPLITS * 2);
   dim3 g1(C, BN_SPLITS);
-  bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, partials);
+  const int vec = ((V & 3) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) ? 1 : 0;
+  bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, vec, partials);
   bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(partials, C, dgamma, dbeta, s12);
   dim3 g2(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
   bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)(1.0 / ((double)N * (double)V)),
-                                            training, act, slope, dx);
+                                            training, act, slope, vec, dx);
   return da_check_launch("da_bn_act_bwd", 3);
 }
 
 DA_API int da_act_bwd(const float* dy, const float* y, float slope, int64_t total, float* dx, cudaStream_t stream) {
   DA_REQUIRE(dy && y && dx, "da_act_bwd: null pointer");
-  act_bwd_kernel<<<ew_grid(total), 256, 0, stream>>>(dy, y, slope, total, dx);
+  const int vec = ((total & 3) == 0 && aligned16(dy) && aligned16(y) && aligned16(dx)) ? 1 : 0;
+  act_bwd_kernel<<<ew_grid(vec ? total / 4 : total), 256, 0, stream>>>(dy, y, slope, total, vec, dx);
   return da_check_launch("da_act_bwd");
 }
 
