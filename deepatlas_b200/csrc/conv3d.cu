@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(256, 2) conv1x1_stream_kernel(const float* __r
   }
   const float4* p1 = reinterpret_cast<const float4*>(x1) + (int64_t)n * C1 * V4 + i4;
   const float4* p2 = x2 ? reinterpret_cast<const float4*>(x2) + (int64_t)n * C2 * V4 + i4 : nullptr;
-#pragma unroll 4
+#pragma unroll 8
   for (int ci = 0; ci < Cin; ++ci) {
     const float4 v = ci < C1 ? __ldcs(p1 + (int64_t)ci * V4) : __ldcs(p2 + (int64_t)(ci - C1) * V4);
     const float4* w4 = reinterpret_cast<const float4*>(sw + ci * CO);
