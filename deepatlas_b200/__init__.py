@@ -13,8 +13,9 @@ include/deepatlas_b200.h); importing this package without the built library rais
 from __future__ import annotations
 
 from . import _lib, evaluation, ops  # noqa: F401
-from .losses import (BendingEnergyLoss, DiceLossMultiClass, VoxelMorphLNCC, get_available_losses,  # noqa: F401
-                     get_loss_function, loss_dict)
+from .losses import (BendingEnergyLoss, CrossEntropyLoss, DiceLossMultiClass, DiceLossOnLabel, FocalLoss,  # noqa: F401
+                     L2Loss, MSELoss, NormalizedCrossCorrelationLoss, SoftCrossEntropy, VoxelMorphLNCC,
+                     get_available_losses, get_loss_function, gradientLoss, loss_dict)
 from .networks import (UNet, UNet_generator, UNet_light, VoxelMorphCVPR2018, get_available_networks,  # noqa: F401
                        get_network, network_dic)
 

@@ -90,6 +90,7 @@ SIGNATURES = {
     "da_channel_reduce": ("piilps", "rc"),
     "da_crop_clip_f32": ("ppliiiiiiiiiffs", "rc"),
     "da_crop_u8": ("ppliiiiiiiiis", "rc"),
+    "da_label_overlap_counts": ("pipiiilps", "rc"),
 }
 
 _lib = None

@@ -54,7 +54,56 @@ __global__ void __launch_bounds__(EV_THREADS) argmax_counts_kernel(const float* 
   }
 }
 
+constexpr int LC_BINS = 256;
+
+__device__ __forceinline__ int lc_label(const void* t, int kind, int64_t i) {
+  if (kind == 4) return (int)((const float*)t)[i];   // float label maps: truncation, as mask.long() (lib/transforms.py:687)
+  return ev_label(t, kind, i);
+}
+
+// counts [N][3][bins]: (#[a == c], #[b == c], #[a == c and b == c]) for two label maps; labels outside [0, bins) are skipped
+__global__ void __launch_bounds__(EV_THREADS) label_overlap_kernel(const void* __restrict__ a, int kind_a, const void* __restrict__ b,
+                                                                   int kind_b, int bins, int64_t V,
+                                                                   unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int h[3][LC_BINS];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * LC_BINS; i += EV_THREADS) (&h[0][0])[i] = 0u;
+  __syncthreads();
+  for (int64_t v = (int64_t)blockIdx.x * EV_THREADS + threadIdx.x; v < V; v += (int64_t)gridDim.x * EV_THREADS) {
+    const int la = lc_label(a, kind_a, (int64_t)n * V + v), lb = lc_label(b, kind_b, (int64_t)n * V + v);
+    if (la >= 0 && la < bins) atomicAdd(&h[0][la], 1u);
+    if (lb >= 0 && lb < bins) {
+      atomicAdd(&h[1][lb], 1u);
+      if (la == lb) atomicAdd(&h[2][lb], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * bins; i += EV_THREADS) {
+    const int q = i / bins, c = i - q * bins;
+    const unsigned int val = h[q][c];
+    if (val) atomicAdd(counts + ((int64_t)n * 3 + q) * bins + c, (unsigned long long)val);
+  }
+}
+
 }  // namespace
+
+// Two label maps a, b [N,V] (kind 0 uint8, 1 int64, 3 int32, 4 fp32 truncated) -> counts [N,3,bins] int64 =
+// (#[a == c], #[b == c], #[a == b == c]); bins <= 256.  The integer half of DiceLossOnLabel (lib/loss.py:348-391).
+DA_API int da_label_overlap_counts(const void* a, int kind_a, const void* b, int kind_b, int N, int bins, int64_t V,
+                                   int64_t* counts, cudaStream_t stream) {
+  DA_REQUIRE(a && b && counts, "da_label_overlap_counts: null pointer");
+  DA_REQUIRE(bins >= 1 && bins <= LC_BINS, "da_label_overlap_counts: unsupported bin count %d (1..256)", bins);
+  auto okk = [](int k) { return k == 0 || k == 1 || k == 3 || k == 4; };
+  DA_REQUIRE(okk(kind_a) && okk(kind_b), "da_label_overlap_counts: bad label kind");
+  cudaError_t e = cudaMemsetAsync(counts, 0, sizeof(int64_t) * (size_t)N * 3 * bins, stream);
+  if (e != cudaSuccess) { da_set_error("da_label_overlap_counts memset: %s", cudaGetErrorString(e)); return (int)e; }
+  int64_t nb = da_cdiv(V, (int64_t)EV_THREADS * 4);
+  const int64_t cap = (int64_t)DA_NUM_SMS * 8;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  label_overlap_kernel<<<dim3((unsigned)nb, N), EV_THREADS, 0, stream>>>(a, kind_a, b, kind_b, bins, V, (unsigned long long*)counts);
+  return da_check_launch("da_label_overlap_counts");
+}
 
 // logits [N,C,V] fp32; truth (nullable) [N,V] labels (kind 0 uint8, 1 int64, 3 int32); counts [N,3,C] int64 = (P, T, I);
 // pred (nullable) [N,V] uint8 receives the argmax label map.  C <= 64.

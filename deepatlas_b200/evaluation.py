@@ -45,3 +45,27 @@ def dice_per_class(logits: torch.Tensor, truths: torch.Tensor) -> torch.Tensor:
     # scipy: dice = (n_tf + n_ft) / (2 n_tt + n_tf + n_ft) in float64, then 1 - dice; same operation order here
     diff = P + T - 2.0 * I
     return 1.0 - diff / (2.0 * I + diff)
+
+
+_LKIND = dict(_KIND)
+_LKIND[torch.float32] = 4
+
+
+def label_overlap_counts(a: torch.Tensor, b: torch.Tensor, bins: int = 256) -> torch.Tensor:
+    """counts int64 [N,3,bins] = (#[a == c], #[b == c], #[a == b == c]) for two label maps with the same number of
+    elements per sample (integer dtypes, or float32 label values, truncated like ``mask.long()``)."""
+    if not a.is_cuda or not b.is_cuda:
+        raise RuntimeError("deepatlas_b200: label maps must be CUDA tensors (no CPU fallback exists)")
+    if a.shape != b.shape:
+        raise AssertionError("label maps must have the same shape")
+
+    def prep(t):
+        if t.dtype not in _LKIND:
+            t = t.float() if t.is_floating_point() else t.long()
+        return t.contiguous()
+    a, b = prep(a), prep(b)
+    N = a.shape[0]
+    V = a[0].numel()
+    counts = torch.empty((N, 3, bins), dtype=torch.int64, device=a.device)
+    _lib.call("da_label_overlap_counts", _p(a), _LKIND[a.dtype], _p(b), _LKIND[b.dtype], N, int(bins), V, _p(counts), _stream())
+    return counts

@@ -120,6 +120,35 @@ class BendingEnergyLoss(nn.Module):
         return (sums * self._coef(input.shape, input.device)[None]).sum()
 
 
+class DiceLossOnLabel(nn.Module):
+    """Dice between two label maps (lib/loss.py:348-391; not in the registry, not differentiable): background excluded,
+    ``scores = 2 I w / (w (S + T) + eps)``, ``1 - scores.mean()``.  Exact integer counts from one CUDA pass; as in the
+    reference ``n_class`` is taken from the data on first use (one host sync) and then kept."""
+
+    def __init__(self, n_class=None, eps=10e-6):
+        super().__init__()
+        self.n_class, self.eps = n_class, eps
+
+    def forward(self, source, target, weight_type="Uniform", average=True):
+        from .evaluation import label_overlap_counts
+        assert source.shape == target.shape
+        counts = label_overlap_counts(source, target)                        # (B, 3, 256)
+        if self.n_class is None:
+            present = (counts[:, :2].sum((0, 1)) > 0).nonzero()
+            self.n_class = int(present.max().item()) + 1
+        c = counts[:, :, 1:self.n_class].float()
+        source_volume, target_volume, intersection = c[:, 0], c[:, 1], c[:, 2]
+        if weight_type == "Simple":
+            weights = target_volume.reciprocal()
+            weights = torch.where(torch.isinf(weights), torch.ones_like(weights), weights)
+        elif weight_type == "Uniform":
+            weights = torch.ones(source.shape[0], source.shape[1], device=c.device)
+        else:
+            raise UnboundLocalError("cannot access local variable 'weights' where it is not associated with a value")
+        scores = (2.0 * intersection * weights) / (weights * (source_volume + target_volume) + self.eps)
+        return 1 - scores.mean()
+
+
 class NormalizedCrossCorrelationLoss(nn.Module):
     """1 - NCC (lib/loss.py:485-501): per sample cov(a,b) / (std(a) std(b)) over all voxels, mean over the batch."""
 

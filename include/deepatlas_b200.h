@@ -218,6 +218,11 @@ int da_crop_clip_f32(const float* src, float* dst, int64_t NC, int D, int H, int
 int da_crop_u8(const uint8_t* src, uint8_t* dst, int64_t NC, int D, int H, int W, int z0, int y0, int x0, int Do,
                int Ho, int Wo, da_stream_t stream);
 
+/* DiceLossOnLabel (lib/loss.py:348-391), integer half: a, b [N,V] label maps (kind 0 uint8, 1 int64, 3 int32, 4 fp32
+ * truncated as mask.long()); counts [N,3,bins] int64 = (#[a == c], #[b == c], #[a == b == c]); bins <= 256. */
+int da_label_overlap_counts(const void* a, int kind_a, const void* b, int kind_b, int N, int bins, int64_t V,
+                            int64_t* counts, da_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,6 +269,24 @@ def bending_energy(u, spacing=(1.0, 1.0, 1.0), normalize=True):
             + 2 * dxdz.mean()) / 9.0
 
 
+def dice_on_label(source, target, n_class=None, eps=10e-6, weight_type="Uniform"):
+    """DiceLossOnLabel.forward (lib/loss.py:358-391): two label maps (B,1,D,M,N), background dropped."""
+    if n_class is None:
+        n_class = int(max(torch.unique(target).max(), torch.unique(source).max()).long().item()) + 1
+    B, C1 = target.shape[:2]
+    s1 = mask_to_one_hot(source.reshape(B, C1, -1), n_class)[:, 1:, :]
+    t1 = mask_to_one_hot(target.reshape(B, C1, -1), n_class)[:, 1:, :]
+    sv, tv = s1.sum(2), t1.sum(2)
+    if weight_type == "Simple":
+        w = tv.float().reciprocal()
+        w = torch.where(torch.isinf(w), torch.ones_like(w), w)
+    else:
+        w = torch.ones(B, C1)
+    inter = s1 * t1
+    scores = (2.0 * inter.sum(2).float() * w) / (w * (sv.float() + tv.float()) + eps)
+    return 1 - scores.mean()
+
+
 def ncc_loss(a, b):
     """NormalizedCrossCorrelationLoss.forward (lib/loss.py:493-501)."""
     a = a.reshape(a.shape[0], -1)

@@ -27,8 +27,11 @@ def dry(monkeypatch, built_lib):
         seen.append(name)
 
     monkeypatch.setattr(_lib, "call", call)
+    from deepatlas_b200 import evaluation
     monkeypatch.setattr(ops, "_stream", lambda: ctypes.c_void_p(0))
     monkeypatch.setattr(ops, "_f32", lambda t, name: t.contiguous())
+    monkeypatch.setattr(evaluation, "_stream", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(evaluation, "_f32", lambda t, name: t.contiguous())
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     return seen
 
@@ -59,6 +62,10 @@ def test_new_ops_argument_lists(dry):
     ops.add(_r(1, 4, 3, 3, 3), _r(1, 4, 3, 3, 3)).sum().backward()
     ops.crop_clip(torch.rand(1, 8, 8, 8), (1, 1, 1), (4, 4, 4))
     ops.crop_labels(torch.zeros((8, 8, 8), dtype=torch.uint8), (1, 1, 1), (4, 4, 4))
+    from deepatlas_b200 import evaluation
+    evaluation.label_overlap_counts(torch.zeros((1, 1, 4, 4, 4), dtype=torch.uint8), torch.zeros((1, 1, 4, 4, 4)))
+    evaluation.argmax_counts(torch.rand(1, 3, 4, 4, 4), torch.zeros((1, 4, 4, 4), dtype=torch.int64))
+    assert "da_label_overlap_counts" in dry and "da_argmax_counts" in dry
     for name in ("da_pair_moments_fwd", "da_affine2", "da_gradient_loss_fwd", "da_gradient_loss_bwd", "da_xent_fwd", "da_xent_bwd",
                  "da_upsample_trilinear2_fwd", "da_upsample_trilinear2_bwd", "da_deconv_k2s2_dgrad", "da_deconv_k2s2_fwd",
                  "da_deconv_k2s2_wgrad", "da_channel_sum", "da_add_bcast", "da_channel_reduce", "da_crop_clip_f32", "da_crop_u8"):

@@ -275,3 +275,22 @@ def test_input_stage(cuda):
     logits = torch.randn((1, 32, 20, 24, 28), generator=g).to(cuda)
     crit = da.get_loss_function("dice")(n_class=32, weight_type="Uniform", softmax=True, eps=1e-6)
     assert torch.equal(crit(logits, got[0][1]), crit(logits, got[0][1].long()))
+
+
+def test_dice_on_label(cuda):
+    import deepatlas_b200 as da
+    from deepatlas_b200 import evaluation
+    from oracle import ref_port as P
+    g = _g()
+    a = torch.randint(0, 32, (2, 1, 9, 10, 11), generator=g)
+    b = torch.randint(0, 32, (2, 1, 9, 10, 11), generator=g)
+    b[0][b[0] == 3] = 0
+    counts = evaluation.label_overlap_counts(a.to(cuda), b.to(torch.uint8).to(cuda))
+    for c in (0, 3, 31):   # exact integer counts
+        assert int(counts[1, 0, c]) == int((a[1] == c).sum()) and int(counts[0, 1, c]) == int((b[0] == c).sum())
+        assert int(counts[1, 2, c]) == int(((a[1] == c) & (b[1] == c)).sum())
+    for dt in (torch.uint8, torch.int64, torch.float32):
+        for wt in ("Uniform", "Simple"):
+            ours = da.DiceLossOnLabel()(a.to(dt).to(cuda), b.to(dt).to(cuda), weight_type=wt)
+            assert abs(float(ours) - float(P.dice_on_label(a, b, None, 10e-6, wt))) < 1e-6, (dt, wt)
+    assert abs(float(da.DiceLossOnLabel()(a.to(cuda), a.to(cuda)))) < 1e-4     # identical maps: loss 0 up to eps

@@ -204,3 +204,24 @@ def test_variant_construction_and_crop_window():
         input_stage.crop_window((8, 8, 8), [4, 4, 4])
     with pytest.raises(RuntimeError):
         input_stage.DeviceInputStage("cpu")
+
+
+def test_dice_on_label_closing_formula(monkeypatch):
+    import deepatlas_b200 as da
+    from deepatlas_b200 import evaluation
+
+    def cpu_counts(a, b, bins=256):
+        a, b = a.reshape(a.shape[0], -1).long(), b.reshape(b.shape[0], -1).long()
+        oh = lambda t: torch.nn.functional.one_hot(t, bins).sum(1)  # noqa: E731
+        both = torch.where(a == b, a, torch.full_like(a, bins))
+        inter = torch.nn.functional.one_hot(both, bins + 1).sum(1)[:, :bins]
+        return torch.stack([oh(a), oh(b), inter], dim=1)
+    monkeypatch.setattr(evaluation, "label_overlap_counts", cpu_counts)
+    g = torch.Generator().manual_seed(230)
+    a = torch.randint(0, 6, (2, 1, 6, 7, 8), generator=g)
+    b = torch.randint(0, 6, (2, 1, 6, 7, 8), generator=g)
+    b[0][b[0] == 3] = 0
+    for wt in ("Uniform", "Simple"):
+        for n_class in (None, 8):
+            ours = da.DiceLossOnLabel(n_class=n_class)(a, b, weight_type=wt)
+            assert abs(float(ours) - float(P.dice_on_label(a, b, n_class, 10e-6, wt))) < 1e-6, (wt, n_class)

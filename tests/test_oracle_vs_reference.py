@@ -224,3 +224,13 @@ def test_port_upsample_closed_form():
     x = torch.rand((1, 2, 3, 4, 5), generator=_g(), dtype=torch.float64)
     ref_out = torch.nn.Upsample(scale_factor=2, mode="trilinear")(x)
     assert float((P.upsample_trilinear2_closed_form(x) - ref_out).abs().max()) < 1e-14
+
+
+def test_port_dice_on_label(ref):
+    g = _g()
+    a = torch.randint(0, 6, (2, 1, 6, 7, 8), generator=g)
+    b = torch.randint(0, 6, (2, 1, 6, 7, 8), generator=g)
+    b[0][b[0] == 3] = 0          # an empty target class: Simple weighting hits its inf -> 1 rule
+    for wt in ("Uniform", "Simple"):
+        assert torch.equal(P.dice_on_label(a, b, None, 10e-6, wt), ref.loss.DiceLossOnLabel()(a, b, weight_type=wt))
+        assert torch.equal(P.dice_on_label(a, b, 8, 10e-6, wt), ref.loss.DiceLossOnLabel(n_class=8)(a, b, weight_type=wt))
