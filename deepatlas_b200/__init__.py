@@ -14,7 +14,7 @@ from __future__ import annotations
 
 from . import _lib, evaluation, ops  # noqa: F401
 from .losses import (BendingEnergyLoss, CrossEntropyLoss, DiceLossMultiClass, DiceLossOnLabel, FocalLoss,  # noqa: F401
-                     L2Loss, MSELoss, NormalizedCrossCorrelationLoss, SoftCrossEntropy, VoxelMorphLNCC,
+                     L2Loss, LNCCLoss, MSELoss, NormalizedCrossCorrelationLoss, SoftCrossEntropy, VoxelMorphLNCC,
                      get_available_losses, get_loss_function, gradientLoss, loss_dict)
 from .networks import (UNet, UNet_generator, UNet_light, VoxelMorphCVPR2018, get_available_networks,  # noqa: F401
                        get_network, network_dic)

@@ -91,6 +91,10 @@ SIGNATURES = {
     "da_crop_clip_f32": ("ppliiiiiiiiiffs", "rc"),
     "da_crop_u8": ("ppliiiiiiiiis", "rc"),
     "da_label_overlap_counts": ("pipiiilps", "rc"),
+    "da_lncc_ms_workspace_bytes": ("", "size"),
+    "da_lncc_ms_coef_bytes": ("iiiiiii", "size"),
+    "da_lncc_ms_fwd": ("ppiiiiiiipppls", "rc"),
+    "da_lncc_ms_bwd": ("pppipfiiiiiiiips", "rc"),
 }
 
 _lib = None

@@ -368,3 +368,135 @@ DA_API int da_xent_bwd(const float* x, const void* target, int target_kind, int 
   xent_bwd_kernel<<<dim3(blocks_for(V), N), LX_THREADS, 0, stream>>>(a, grad_scale, grad_x, grad_target);
   return da_check_launch("da_xent_bwd");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-scale LNCCLoss (lib/loss.py:512-586; in the file but not in the registry): per scale a k^3 box filter with
+// dilation d and stride s (F.conv3d with a ones kernel, padding 0) of I, J, I^2, J^2, I*J, then
+//   lncc = cross^2 / (Ivar * Jvar + 1e-5),  cross = IJs - Is*Js/n,  Ivar = I2s - Is^2/n,  Jvar = J2s - Js^2/n,  n = k^3
+// and 1 - mean(lncc).  One thread = one window: the five sums are accumulated in fp64 (the reference's fp32 expressions
+// cancel), the per-window derivatives with respect to the five sums are kept for the backward, which is a gather over
+// the windows that contain a voxel (deterministic).  Windows are sparse in the volume (stride 2..10), so brute force over
+// the taps is a few hundred M loads per scale, mostly L1 hits.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct MsGeo { int D, H, W, k, dil, stride, Do, Ho, Wo; };
+
+// coef [N][5][Do*Ho*Wo]: d lncc / d (Is, I2s, IJs, Js, J2s); partials [gridDim.x] sums of lncc
+__global__ void __launch_bounds__(LX_THREADS) lncc_ms_fwd_kernel(const float* __restrict__ I, const float* __restrict__ J, int N, MsGeo g,
+                                                                 float* __restrict__ coef, double* __restrict__ partials) {
+  __shared__ double red[LX_WARPS];
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo, V = (int64_t)g.D * g.H * g.W;
+  const double nwin = (double)g.k * g.k * g.k;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * LX_THREADS + threadIdx.x; i < (int64_t)N * Vo; i += (int64_t)gridDim.x * LX_THREADS) {
+    const int64_t n = i / Vo, o = i - n * Vo;
+    const int xo = (int)(o % g.Wo), yo = (int)((o / g.Wo) % g.Ho), zo = (int)(o / ((int64_t)g.Wo * g.Ho));
+    const float* Ip = I + n * V + ((int64_t)zo * g.stride * g.H + (int64_t)yo * g.stride) * g.W + (int64_t)xo * g.stride;
+    const float* Jp = J + n * V + (Ip - (I + n * V));
+    double sI = 0, sJ = 0, sII = 0, sJJ = 0, sIJ = 0;
+    for (int a = 0; a < g.k; ++a)
+      for (int b = 0; b < g.k; ++b) {
+        const int64_t row = ((int64_t)a * g.dil * g.H + (int64_t)b * g.dil) * g.W;
+        float fI = 0.f, fJ = 0.f, fII = 0.f, fJJ = 0.f, fIJ = 0.f;
+        for (int c = 0; c < g.k; ++c) {
+          const float x = __ldg(Ip + row + c * g.dil), y = __ldg(Jp + row + c * g.dil);
+          fI += x; fJ += y; fII = fmaf(x, x, fII); fJJ = fmaf(y, y, fJJ); fIJ = fmaf(x, y, fIJ);
+        }
+        sI += fI; sJ += fJ; sII += fII; sJJ += fJJ; sIJ += fIJ;
+      }
+    const double cross = sIJ - sI * sJ / nwin, iv = sII - sI * sI / nwin, jv = sJJ - sJ * sJ / nwin;
+    const double den = iv * jv + 1e-5;
+    acc += cross * cross / den;
+    if (coef) {
+      const double cIJ = 2.0 * cross / den, cII = -cross * cross * jv / (den * den), cJJ = -cross * cross * iv / (den * den);
+      float* cp = coef + n * 5 * Vo + o;
+      cp[0] = (float)(-cIJ * sJ / nwin - 2.0 * cII * sI / nwin);
+      cp[Vo] = (float)cII;
+      cp[2 * Vo] = (float)cIJ;
+      cp[3 * Vo] = (float)(-cIJ * sI / nwin - 2.0 * cJJ * sJ / nwin);
+      cp[4 * Vo] = (float)cJJ;
+    }
+  }
+  const double t = block_sum<double, LX_WARPS>(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+__global__ void lncc_ms_finalize_kernel(const double* __restrict__ partials, int nb, float* __restrict__ out) {
+  double a = 0;
+  for (int i = threadIdx.x; i < nb; i += 32) a += partials[i];
+  a = warp_sum(a);
+  if (threadIdx.x == 0) out[0] = (float)a;
+}
+
+// grad[n][p] (+)= scale * sum over windows o containing p of (c1 + 2*self[p]*c2 + other[p]*c3), (c1, c2, c3) = coefficient
+// fields (Is, I2s, IJs) for the gradient of I, (Js, J2s, IJs) for the gradient of J
+__global__ void __launch_bounds__(LX_THREADS) lncc_ms_bwd_kernel(const float* __restrict__ self, const float* __restrict__ other,
+                                                                 const float* __restrict__ coef, int which, const float* __restrict__ gscale,
+                                                                 float scale, int N, MsGeo g, int accumulate, float* __restrict__ grad) {
+  const int64_t Vo = (int64_t)g.Do * g.Ho * g.Wo, V = (int64_t)g.D * g.H * g.W;
+  const float gs = __ldg(gscale) * scale;
+  const int ext = g.dil * (g.k - 1);
+  for (int64_t i = (int64_t)blockIdx.x * LX_THREADS + threadIdx.x; i < (int64_t)N * V; i += (int64_t)gridDim.x * LX_THREADS) {
+    const int64_t n = i / V, p = i - n * V;
+    const int x = (int)(p % g.W), y = (int)((p / g.W) % g.H), z = (int)(p / ((int64_t)g.W * g.H));
+    const float* c1 = coef + (n * 5 + (which ? 3 : 0)) * Vo;
+    const float* c2 = coef + (n * 5 + (which ? 4 : 1)) * Vo;
+    const float* c3 = coef + (n * 5 + 2) * Vo;
+    // windows along one axis: o*stride <= q <= o*stride + ext and (q - o*stride) % dil == 0
+    auto lo = [&](int q) { const int t = q - ext; return t <= 0 ? 0 : (t + g.stride - 1) / g.stride; };
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int zo = lo(z); zo < g.Do && zo * g.stride <= z; ++zo) {
+      if ((z - zo * g.stride) % g.dil) continue;
+      for (int yo = lo(y); yo < g.Ho && yo * g.stride <= y; ++yo) {
+        if ((y - yo * g.stride) % g.dil) continue;
+        for (int xo = lo(x); xo < g.Wo && xo * g.stride <= x; ++xo) {
+          if ((x - xo * g.stride) % g.dil) continue;
+          const int64_t o = ((int64_t)zo * g.Ho + yo) * g.Wo + xo;
+          a1 += __ldg(c1 + o); a2 += __ldg(c2 + o); a3 += __ldg(c3 + o);
+        }
+      }
+    }
+    const float r = gs * (a1 + 2.f * __ldg(self + i) * a2 + __ldg(other + i) * a3);
+    grad[i] = accumulate ? grad[i] + r : r;
+  }
+}
+
+inline int ms_out(int n, int k, int dil, int stride) { return (n - dil * (k - 1) - 1) / stride + 1; }
+
+}  // namespace
+
+DA_API int64_t da_lncc_ms_workspace_bytes(void) { return (int64_t)sizeof(double) * LX_BLOCKS * 2; }
+DA_API int64_t da_lncc_ms_coef_bytes(int N, int D, int H, int W, int k, int dil, int stride) {
+  const int Do = ms_out(D, k, dil, stride), Ho = ms_out(H, k, dil, stride), Wo = ms_out(W, k, dil, stride);
+  if (Do < 1 || Ho < 1 || Wo < 1) return 0;
+  return (int64_t)sizeof(float) * N * 5 * Do * Ho * Wo;
+}
+
+// One scale of LNCCLoss: I, J [N,1,D,H,W]; out_sum [1] = sum over all windows of lncc (the caller divides by the window
+// count); coef (nullable) receives the per-window derivatives for da_lncc_ms_bwd.
+DA_API int da_lncc_ms_fwd(const float* I, const float* J, int N, int D, int H, int W, int k, int dil, int stride, float* out_sum,
+                          float* coef, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(I && J && out_sum && workspace, "da_lncc_ms_fwd: null pointer");
+  DA_REQUIRE(k >= 1 && dil >= 1 && stride >= 1, "da_lncc_ms_fwd: bad window");
+  MsGeo g{D, H, W, k, dil, stride, ms_out(D, k, dil, stride), ms_out(H, k, dil, stride), ms_out(W, k, dil, stride)};
+  DA_REQUIRE(g.Do >= 1 && g.Ho >= 1 && g.Wo >= 1, "da_lncc_ms_fwd: window %d (dilation %d) does not fit the volume", k, dil);
+  if (workspace_bytes < da_lncc_ms_workspace_bytes()) { da_set_error("da_lncc_ms_fwd: workspace too small"); return DA_ERR_WORKSPACE; }
+  const int nb = blocks_for((int64_t)N * g.Do * g.Ho * g.Wo);
+  lncc_ms_fwd_kernel<<<nb, LX_THREADS, 0, stream>>>(I, J, N, g, coef, (double*)workspace);
+  lncc_ms_finalize_kernel<<<1, 32, 0, stream>>>((const double*)workspace, nb, out_sum);
+  return da_check_launch("da_lncc_ms_fwd", 2);
+}
+
+// grad (+)= grad_scale[0] * scale * d(sum of lncc)/d(I or J); which: 0 = gradient of I, 1 = gradient of J; accumulate: add to grad
+DA_API int da_lncc_ms_bwd(const float* I, const float* J, const float* coef, int which, const float* grad_scale, float scale, int N,
+                          int D, int H, int W, int k, int dil, int stride, int accumulate, float* grad, cudaStream_t stream) {
+  DA_REQUIRE(I && J && coef && grad_scale && grad, "da_lncc_ms_bwd: null pointer");
+  MsGeo g{D, H, W, k, dil, stride, ms_out(D, k, dil, stride), ms_out(H, k, dil, stride), ms_out(W, k, dil, stride)};
+  DA_REQUIRE(g.Do >= 1 && g.Ho >= 1 && g.Wo >= 1, "da_lncc_ms_bwd: window does not fit the volume");
+  const int64_t total = (int64_t)N * D * H * W;
+  const int64_t b = da_cdiv(total, LX_THREADS);
+  const int grid = (int)(b > (int64_t)DA_NUM_SMS * 16 ? (int64_t)DA_NUM_SMS * 16 : b);
+  lncc_ms_bwd_kernel<<<grid, LX_THREADS, 0, stream>>>(which ? J : I, which ? I : J, coef, which, grad_scale, scale, N, g, accumulate, grad);
+  return da_check_launch("da_lncc_ms_bwd");
+}

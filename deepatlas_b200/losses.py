@@ -72,6 +72,38 @@ class DiceLossMultiClass(nn.Module):
         return 1 - (weights * scores).sum() / weights.sum()
 
 
+class LNCCLoss(nn.Module):
+    """Multi-scale local NCC (lib/loss.py:512-586; in the file but not in the registry).  The scale schedule of
+    ``__stepup`` is reproduced: windows min(size)/16, /8, /4 (weights 0.1, 0.3, 0.6, dilation 2) above 128 voxels,
+    /4 and /2 (0.3, 0.7, dilation 2) above 64, else /2 (dilation 1); stride max(int((k + 1) / 4), 1)."""
+
+    def initialize(self, kernel_sz=[9, 9, 9], voxel_weights=None):
+        pass
+
+    @staticmethod
+    def schedule(img_sz):
+        max_scale = min(img_sz)
+        if max_scale > 128:
+            scale, weight, dilation = [int(max_scale / 16), int(max_scale / 8), int(max_scale / 4)], [0.1, 0.3, 0.6], [2, 2, 2]
+        elif max_scale > 64:
+            scale, weight, dilation = [int(max_scale / 4), int(max_scale / 2)], [0.3, 0.7], [2, 2]
+        else:
+            scale, weight, dilation = [int(max_scale / 2)], [1.0], [1]
+        step = [max(int((k + 1) / 4), 1) for k in scale]
+        return list(zip(scale, dilation, step, weight))
+
+    def forward(self, input, target, inst_weights=None, train=None):
+        N, _, D, H, W = input.shape
+        total = 0.0
+        for k, dil, step, weight in self.schedule(list(input.shape[2:])):
+            count = N
+            for n in (D, H, W):
+                count *= (n - dil * (k - 1) - 1) // step + 1
+            s = ops.lncc_ms_sum(input, target, k, dil, step)
+            total = total + (1 - s[0] / count) * weight
+        return total
+
+
 class VoxelMorphLNCC(nn.Module):
     def __init__(self, filter_size=9, eps=1e-6):
         super().__init__()

@@ -796,6 +796,46 @@ def xent_sums(x, target, mode, class_weight=None, gamma=0.0, focal_softmax=True,
     return XentFunction.apply(x, target, mode, class_weight, gamma, focal_softmax, ignore_index)
 
 
+class LnccMsSumFunction(torch.autograd.Function):
+    """One scale of the multi-scale LNCCLoss (lib/loss.py:545-586): sum over all windows (k^3 ones filter, dilation,
+    stride, no padding) of cross^2 / (Ivar * Jvar + 1e-5), as a 1-element tensor."""
+
+    @staticmethod
+    def forward(ctx, I, J, k: int, dil: int, stride: int):
+        I, J = _f32(I, "input"), _f32(J, "target")
+        if I.shape != J.shape or I.dim() != 5 or I.shape[1] != 1:
+            raise ValueError(f"LNCCLoss: input and target must both be (N,1,D,H,W), got {tuple(I.shape)} / {tuple(J.shape)}")
+        N, _, D, H, W = I.shape
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        out = torch.empty((1,), dtype=torch.float32, device=I.device)
+        coef = _ws(_lib.size("da_lncc_ms_coef_bytes", N, D, H, W, k, dil, stride), I.device) if need else None
+        nb = _lib.size("da_lncc_ms_workspace_bytes")
+        ws = _ws(nb, I.device)
+        _lib.call("da_lncc_ms_fwd", _p(I), _p(J), N, D, H, W, k, dil, stride, _p(out), _p(coef), _p(ws), nb, _stream())
+        ctx.save_for_backward(I, J, coef if coef is not None else torch.empty(0, device=I.device))
+        ctx.cfg = (k, dil, stride)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        I, J, coef = ctx.saved_tensors
+        k, dil, stride = ctx.cfg
+        N, _, D, H, W = I.shape
+        g = _f32(g, "grad_out").reshape(1)
+        gI = gJ = None
+        if ctx.needs_input_grad[0]:
+            gI = torch.empty_like(I)
+            _lib.call("da_lncc_ms_bwd", _p(I), _p(J), _p(coef), 0, _p(g), 1.0, N, D, H, W, k, dil, stride, 0, _p(gI), _stream())
+        if ctx.needs_input_grad[1]:
+            gJ = torch.empty_like(J)
+            _lib.call("da_lncc_ms_bwd", _p(I), _p(J), _p(coef), 1, _p(g), 1.0, N, D, H, W, k, dil, stride, 0, _p(gJ), _stream())
+        return gI, gJ, None, None, None
+
+
+def lncc_ms_sum(I, J, k, dil, stride):
+    return LnccMsSumFunction.apply(I, J, int(k), int(dil), int(stride))
+
+
 # ------------------------------------------------------------------------------------------------------
 # device-side input stage  (lib/transforms.py:79-80, 124-158)
 # ------------------------------------------------------------------------------------------------------

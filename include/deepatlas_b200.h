@@ -223,6 +223,17 @@ int da_crop_u8(const uint8_t* src, uint8_t* dst, int64_t NC, int D, int H, int W
 int da_label_overlap_counts(const void* a, int kind_a, const void* b, int kind_b, int N, int bins, int64_t V,
                             int64_t* counts, da_stream_t stream);
 
+/* Multi-scale LNCCLoss (lib/loss.py:512-586), one scale per call: k^3 ones filter with dilation `dil` and stride `stride`
+ * (F.conv3d, padding 0) over I, J, I^2, J^2, I*J [N,1,D,H,W]; out_sum [1] = sum over windows of
+ * cross^2 / (Ivar*Jvar + 1e-5); coef (nullable, da_lncc_ms_coef_bytes) keeps the per-window derivatives for the backward.
+ * Backward: grad (+)= grad_scale[0] (device scalar) * scale * d out_sum / d I (which 0) or J (which 1). */
+int64_t da_lncc_ms_workspace_bytes(void);
+int64_t da_lncc_ms_coef_bytes(int N, int D, int H, int W, int k, int dil, int stride);
+int da_lncc_ms_fwd(const float* I, const float* J, int N, int D, int H, int W, int k, int dil, int stride, float* out_sum,
+                   float* coef, void* workspace, int64_t workspace_bytes, da_stream_t stream);
+int da_lncc_ms_bwd(const float* I, const float* J, const float* coef, int which, const float* grad_scale, float scale, int N,
+                   int D, int H, int W, int k, int dil, int stride, int accumulate, float* grad, da_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,6 +287,31 @@ def dice_on_label(source, target, n_class=None, eps=10e-6, weight_type="Uniform"
     return 1 - scores.mean()
 
 
+def lncc_multiscale(I, J):
+    """LNCCLoss.forward (lib/loss.py:512-586): the scale schedule of __stepup, F.conv3d box filters with dilation and
+    stride, the reference's cancellation-form cross / variance expressions, eps 1e-5."""
+    ms = min(I.shape[2:])
+    if ms > 128:
+        scale, weight, dilation = [int(ms / 16), int(ms / 8), int(ms / 4)], [0.1, 0.3, 0.6], [2, 2, 2]
+    elif ms > 64:
+        scale, weight, dilation = [int(ms / 4), int(ms / 2)], [0.3, 0.7], [2, 2]
+    else:
+        scale, weight, dilation = [int(ms / 2)], [1.0], [1]
+    total = 0.0
+    for k, w, d in zip(scale, weight, dilation):
+        step = max(int((k + 1) / 4), 1)
+        f = torch.ones(1, 1, k, k, k, dtype=I.dtype)
+        conv = lambda t: F.conv3d(t, f, padding=0, dilation=d, stride=step).view(I.shape[0], -1)  # noqa: E731
+        Is, Js, I2s, J2s, IJs = conv(I), conv(J), conv(I ** 2), conv(J ** 2), conv(I * J)
+        n = float(k ** 3)
+        Im, Jm = Is / n, Js / n
+        cross = IJs - Jm * Is - Im * Js + Jm * Im * n
+        Iv = I2s - 2 * Im * Is + Im ** 2 * n
+        Jv = J2s - 2 * Jm * Js + Jm ** 2 * n
+        total = total + (1 - (cross * cross / (Iv * Jv + 1e-5)).mean()) * w
+    return total
+
+
 def ncc_loss(a, b):
     """NormalizedCrossCorrelationLoss.forward (lib/loss.py:493-501)."""
     a = a.reshape(a.shape[0], -1)

@@ -54,6 +54,8 @@ def test_new_ops_argument_lists(dry):
     for loss in (L("cross_entropy")()(x, t), L("cross_entropy")(weight=torch.ones(4))(x, t.to(torch.uint8)),
                  L("focal")(4)(x, t), L("soft_cross_entropy")(softmax=True)(x, soft), L("soft_cross_entropy")()(x, soft)):
         loss.backward()
+    da.LNCCLoss()(_r(1, 1, 12, 14, 16), _r(1, 1, 12, 14, 16)).backward()
+    assert "da_lncc_ms_fwd" in dry and "da_lncc_ms_bwd" in dry
     y = ops.upsample_trilinear2(_r(1, 2, 3, 4, 5))
     y.sum().backward()
     w, bias = _r(6, 4, 2, 2, 2), _r(6)

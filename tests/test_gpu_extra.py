@@ -294,3 +294,26 @@ def test_dice_on_label(cuda):
             ours = da.DiceLossOnLabel()(a.to(dt).to(cuda), b.to(dt).to(cuda), weight_type=wt)
             assert abs(float(ours) - float(P.dice_on_label(a, b, None, 10e-6, wt))) < 1e-6, (dt, wt)
     assert abs(float(da.DiceLossOnLabel()(a.to(cuda), a.to(cuda)))) < 1e-4     # identical maps: loss 0 up to eps
+
+
+@pytest.mark.parametrize("size", [(12, 14, 16), (66, 70, 68), (132, 130, 136)])
+def test_lncc_multiscale(cuda, size):
+    """All three branches of the scale schedule.  The reference's fp32 expressions cancel, so the
+    bar is the precision ladder: our error against the fp64 restatement <= max(1e-4, 3 x the fp32 restatement's own)."""
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    g = _g()
+    I, J = torch.rand((1, 1) + size, generator=g), torch.rand((1, 1) + size, generator=g)
+    J = 0.6 * J + 0.4 * I                      # correlated pair: lncc well away from 0
+    I64, J64 = I.double().requires_grad_(True), J.double().requires_grad_(True)
+    truth = P.lncc_multiscale(I64, J64)
+    truth.backward()
+    I32, J32 = I.clone().requires_grad_(True), J.clone().requires_grad_(True)
+    ref32 = P.lncc_multiscale(I32, J32)
+    ref32.backward()
+    Ig, Jg = I.to(cuda).requires_grad_(True), J.to(cuda).requires_grad_(True)
+    loss = da.LNCCLoss()(Ig, Jg)
+    loss.backward()
+    assert rel_err(loss, truth) < max(TOL, 3 * rel_err(ref32, truth))
+    for ours, r32, t64 in ((Ig.grad, I32.grad, I64.grad), (Jg.grad, J32.grad, J64.grad)):
+        assert rel_err(ours, t64) < max(TOL, 3 * rel_err(r32, t64))

@@ -234,3 +234,18 @@ def test_port_dice_on_label(ref):
     for wt in ("Uniform", "Simple"):
         assert torch.equal(P.dice_on_label(a, b, None, 10e-6, wt), ref.loss.DiceLossOnLabel()(a, b, weight_type=wt))
         assert torch.equal(P.dice_on_label(a, b, 8, 10e-6, wt), ref.loss.DiceLossOnLabel(n_class=8)(a, b, weight_type=wt))
+
+
+@pytest.mark.parametrize("size", [(12, 14, 16), (66, 68, 70)])
+def test_port_lncc_multiscale(ref, size, monkeypatch):
+    """The reference builds its filters with .cuda() (lib/loss.py:539): identity here, the arithmetic is device independent."""
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    g = _g()
+    I, J = torch.rand((1, 1) + size, generator=g), torch.rand((1, 1) + size, generator=g)
+    assert torch.equal(P.lncc_multiscale(I, J), ref.loss.LNCCLoss()(I, J))
+    import deepatlas_b200 as da
+    sched = da.LNCCLoss.schedule(list(size))
+    crit = ref.loss.LNCCLoss()
+    crit(I, J)
+    assert [s[0] for s in sched] == crit.scale and [s[1] for s in sched] == crit.dilation
+    assert [s[2] for s in sched] == [st[0] for st in crit.step] and [s[3] for s in sched] == crit.scale_weight
