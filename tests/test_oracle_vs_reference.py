@@ -249,3 +249,35 @@ def test_port_lncc_multiscale(ref, size, monkeypatch):
     crit(I, J)
     assert [s[0] for s in sched] == crit.scale and [s[1] for s in sched] == crit.dilation
     assert [s[2] for s in sched] == [st[0] for st in crit.step] and [s[3] for s in sched] == crit.scale_weight
+
+
+def test_checkpoint_round_trip_through_reference_code(tmp_path):
+    """The on-disk contract: a '.pth.tar' written by the reference's own save_checkpoint from a
+    REFERENCE model restores into the mirror through the reference's own initialize_model (strict=True), optimizer
+    state included -- and the other way round (models/base.py:70-120)."""
+    import deepatlas_b200 as da
+    refm = ref_import.load(with_models=True)
+    import models.base as base
+    for name, args, kw in (("UNet_light", (1, 4), dict(bias=True, BN=True)), ("voxel_morph_cvpr", (), {})):
+        torch.manual_seed(230)
+        r = refm.get_network(name)(*args, **kw)
+        r.weights_init()
+        m = da.get_network(name)(*args, **kw)          # different (default) initialisation
+        opt_r = torch.optim.Adam(r.parameters(), lr=1e-3)
+        opt_m = torch.optim.Adam(m.parameters(), lr=1e-3)
+        state = {"epoch": 3, "model_state_dict": r.state_dict(), "optimizer_state_dict": opt_r.state_dict(), "best_score": 0.5}
+        base.BaseExperiment.save_checkpoint(state, True, str(tmp_path), prefix=name)
+        epoch, best = base.BaseExperiment.initialize_model(m, opt_m, str(tmp_path / f"{name}_model_best.pth.tar"))
+        assert (epoch, best) == (3, 0.5)
+        for k, v in r.state_dict().items():
+            assert torch.equal(v, m.state_dict()[k]), k
+        # and back: a checkpoint of the mirror restores into the reference class
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(1.0)
+        state = {"epoch": 4, "model_state_dict": m.state_dict(), "optimizer_state_dict": opt_m.state_dict(), "seg_best_score": torch.tensor(0.25)}
+        base.BaseExperiment.save_checkpoint(state, False, str(tmp_path), prefix=name + "_mirror")
+        epoch, best = base.BaseExperiment.initialize_model(r, opt_r, str(tmp_path / f"{name}_mirror_checkpoint.pth.tar"))
+        assert (epoch, best) == (4, 0.25)
+        for k, v in m.state_dict().items():
+            assert torch.equal(v, r.state_dict()[k]), k
