@@ -34,6 +34,8 @@ SIGNATURES = {
     "da_warp_dice_sums_fwd": ("ppipiiiiiiiiipppls", "rc"),
     "da_warp_dice_sums_bwd": ("ppipipppiiiiiiiipppls", "rc"),
     "da_softmax_fwd": ("ppiils", "rc"),
+    "da_softmax_dice_fwd": ("ppiiilpppls", "rc"),
+    "da_softmax_dice_bwd": ("ppiiilppppps", "rc"),
     "da_softmax_bwd": ("pppiils", "rc"),
     "da_argmax_counts": ("ppiiilpps", "rc"),
     # lncc

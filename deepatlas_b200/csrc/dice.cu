@@ -52,15 +52,21 @@ template <int CP>
 __global__ void __launch_bounds__(DICE_THREADS) dice_sums_kernel(const float* __restrict__ source,
                                                                  const void* __restrict__ target, int kind,
                                                                  int softmax, int C, int64_t V,
-                                                                 float* __restrict__ partials) {
+                                                                 float* __restrict__ partials, float* __restrict__ probs_out) {
   const int n = blockIdx.y;
   const float* s = source + (int64_t)n * C * V;
+  float* po = probs_out ? probs_out + (int64_t)n * C * V : nullptr;
   float aS[CP], aT[CP], aI[CP], p[CP];
 #pragma unroll
   for (int c = 0; c < CP; ++c) aS[c] = aT[c] = aI[c] = 0.f;
   for (int64_t v = (int64_t)blockIdx.x * DICE_THREADS + threadIdx.x; v < V;
        v += (int64_t)gridDim.x * DICE_THREADS) {
     load_probs<CP>(s, V, v, C, softmax != 0, p);
+    if (po) {  // the probabilities are needed again downstream (anatomy term): written here instead of by a second pass
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) po[(int64_t)c * V + v] = p[c];
+    }
     if (kind == TK_SOFT) {
       const float* t = (const float*)target + (int64_t)n * C * V;
 #pragma unroll
@@ -112,7 +118,7 @@ template <int CP>
 __global__ void __launch_bounds__(DICE_THREADS) dice_bwd_kernel(
     const float* __restrict__ source, const void* __restrict__ target, int kind, int softmax, int C, int64_t V,
     const float* __restrict__ gS, const float* __restrict__ gT, const float* __restrict__ gI,
-    float* __restrict__ grad_source, float* __restrict__ grad_target) {
+    float* __restrict__ grad_source, float* __restrict__ grad_target, const float* __restrict__ gprob) {
   const int n = blockIdx.y;
   __shared__ float sg[3][CP];
   for (int i = threadIdx.x; i < 3 * CP; i += DICE_THREADS) {
@@ -142,6 +148,12 @@ __global__ void __launch_bounds__(DICE_THREADS) dice_bwd_kernel(
       for (int c = 0; c < CP; ++c) g[c] = sg[0][c] + ((lab == c) ? sg[2][c] : 0.f);
     }
     if (!gs) continue;
+    if (gprob) {  // a second consumer of the probabilities: its gradient joins the Dice part before the softmax Jacobian
+      const float* gq = gprob + (int64_t)n * C * V;
+#pragma unroll
+      for (int c = 0; c < CP; ++c)
+        if (c < C) g[c] += gq[(int64_t)c * V + v];
+    }
     if (softmax) {
       float dot = 0.f;
 #pragma unroll
@@ -226,7 +238,7 @@ DA_API int da_dice_sums_fwd(const float* source, const void* target, int target_
   }
   const int nb = dice_blocks(V);
   dim3 grid(nb, N);
-#define CALL(CP) dice_sums_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(source, target, target_kind, apply_softmax, C, V, (float*)workspace)
+#define CALL(CP) dice_sums_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(source, target, target_kind, apply_softmax, C, V, (float*)workspace, nullptr)
   DICE_DISPATCH(CALL)
 #undef CALL
   int rc = da_check_launch("da_dice_sums_fwd");
@@ -234,6 +246,41 @@ DA_API int da_dice_sums_fwd(const float* source, const void* target, int target_
   dim3 g2((3 * C + 127) / 128, N);
   dice_finalize_kernel<<<g2, 128, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
   return da_check_launch("da_dice_sums_fwd/finalize");
+}
+
+// softmax + Dice sums + the probabilities themselves in ONE pass over the logits: for a prediction that feeds both the
+// supervised Dice term and, as probabilities, a second consumer (the anatomy term of the joint step).  Replaces
+// da_dice_sums_fwd(apply_softmax) + da_softmax_fwd; probs [N,C,V].
+DA_API int da_softmax_dice_fwd(const float* logits, const void* target, int target_kind, int N, int C, int64_t V, float* sums,
+                               float* probs, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  DA_REQUIRE(logits && target && sums && probs && workspace, "da_softmax_dice_fwd: null pointer");
+  DA_REQUIRE(C >= 1 && C <= 64, "da_softmax_dice_fwd: unsupported class count %d (1..64)", C);
+  DA_REQUIRE(target_kind >= 0 && target_kind <= 3, "da_softmax_dice_fwd: bad target kind");
+  if (workspace_bytes < da_dice_workspace_bytes(N, C, V)) { da_set_error("da_softmax_dice_fwd: workspace too small"); return DA_ERR_WORKSPACE; }
+  const int nb = dice_blocks(V);
+  dim3 grid(nb, N);
+#define CALL(CP) dice_sums_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(logits, target, target_kind, 1, C, V, (float*)workspace, probs)
+  DICE_DISPATCH(CALL)
+#undef CALL
+  int rc = da_check_launch("da_softmax_dice_fwd");
+  if (rc) return rc;
+  dim3 g2((3 * C + 127) / 128, N);
+  dice_finalize_kernel<<<g2, 128, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
+  return da_check_launch("da_softmax_dice_fwd/finalize");
+}
+
+// Backward of da_softmax_dice_fwd: grad_logits = softmax Jacobian applied to (Dice part from gS, gI [+ gT for a soft
+// target]) + grad_probs, in one pass (replaces da_dice_sums_bwd + da_softmax_bwd + the sum of their two results).
+// grad_probs nullable.
+DA_API int da_softmax_dice_bwd(const float* logits, const void* target, int target_kind, int N, int C, int64_t V, const float* gS,
+                               const float* gT, const float* gI, const float* grad_probs, float* grad_logits, cudaStream_t stream) {
+  DA_REQUIRE(logits && target && gS && gI && grad_logits, "da_softmax_dice_bwd: null pointer");
+  DA_REQUIRE(C >= 1 && C <= 64, "da_softmax_dice_bwd: unsupported class count %d (1..64)", C);
+  dim3 grid(dice_blocks(V), N);
+#define CALL(CP) dice_bwd_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(logits, target, target_kind, 1, C, V, gS, gT, gI, grad_logits, nullptr, grad_probs)
+  DICE_DISPATCH(CALL)
+#undef CALL
+  return da_check_launch("da_softmax_dice_bwd");
 }
 
 // gS,gT,gI [N,C]: upstream gradients w.r.t. the three sums (gT may be null).
@@ -244,7 +291,7 @@ DA_API int da_dice_sums_bwd(const float* source, const void* target, int target_
   DA_REQUIRE(C >= 1 && C <= 64, "da_dice_sums_bwd: unsupported class count %d (1..64)", C);
   DA_REQUIRE(grad_target == nullptr || target_kind == TK_SOFT, "da_dice_sums_bwd: grad_target needs a soft target");
   dim3 grid(dice_blocks(V), N);
-#define CALL(CP) dice_bwd_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(source, target, target_kind, apply_softmax, C, V, gS, gT, gI, grad_source, grad_target)
+#define CALL(CP) dice_bwd_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(source, target, target_kind, apply_softmax, C, V, gS, gT, gI, grad_source, grad_target, nullptr)
   DICE_DISPATCH(CALL)
 #undef CALL
   return da_check_launch("da_dice_sums_bwd");

@@ -14,6 +14,8 @@ The lambdas are not in the reference (paper hyper-parameters); they are configur
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -49,12 +51,18 @@ class JointModel(nn.Module):
         P_m = self.seg(I_m)
         P_t = self.seg(I_t)
         disp, I_w, phi = self.reg(I_m, I_t)
+        # softmax(P_m) has two consumers (supervised Dice, anatomy term): one pass yields the Dice sums AND the
+        # probabilities, and one backward pass takes both gradients (no separate softmax, no sum of two 629 MB gradients)
+        if os.environ.get("DA_JOINT_UNFUSED") == "1":   # A/B switch: separate softmax and Dice passes
+            sup_m, prob_m = self.sup_dice(P_m, S_m), ops.softmax(P_m)
+        else:
+            sup_m, prob_m = self.sup_dice.forward_with_probs(P_m, S_m)
         parts = {
             "sim": self.sim_loss(I_w, I_t),
             "reg": self.reg_loss(disp),
             # dice(grid_sample(softmax(P_m), phi), onehot(S_t)): warp and Dice sums fused, labels stand for the one-hot
-            "ana": self.ana_dice.forward_warped(ops.softmax(P_m), phi, S_t),
-            "sup": self.sup_dice(P_m, S_m) + self.sup_dice(P_t, S_t),
+            "ana": self.ana_dice.forward_warped(prob_m, phi, S_t),
+            "sup": sup_m + self.sup_dice(P_t, S_t),
         }
         loss = lam["sim"] * parts["sim"] + lam["reg"] * parts["reg"] + lam["ana"] * parts["ana"] + lam["sup"] * parts["sup"]
         return loss, parts

@@ -40,6 +40,19 @@ class DiceLossMultiClass(nn.Module):
         sums = ops.dice_sums(source, target, apply_softmax=self.softmax)  # (B, 3, C)
         return self._closing(sums)
 
+    def forward_with_probs(self, source, target):
+        """``(forward(source, target), softmax(source))`` for a softmax=True loss, from one pass over the logits: for a
+        prediction whose probabilities have a second consumer (the joint step warps them for the anatomy term)."""
+        if not self.softmax:
+            raise ValueError("forward_with_probs needs softmax=True (the source must be logits)")
+        assert source.shape[0] == target.shape[0] and tuple(source.shape[-3:]) == tuple(target.shape[-3:])
+        if self.weight_type not in ("Simple", "Volume", "Uniform"):
+            raise ValueError("Class weighting type {} does not exists!".format(self.weight_type))
+        if self.n_class is None:
+            self.n_class = source.shape[1]
+        sums, probs = ops.softmax_dice(source, target)
+        return self._closing(sums), probs
+
     def forward_warped(self, source, deform_field, target):
         """``forward(grid_sample(source, deform_field), target)`` for a label-mask ``target`` and probability ``source``
         (the anatomy term of the joint step, same F.grid_sample call as voxel_morph.py:90-91) without materialising the

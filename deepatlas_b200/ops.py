@@ -148,6 +148,59 @@ def dice_sums(source, target, apply_softmax=False):
     return DiceSumsFunction.apply(source, target, apply_softmax)
 
 
+class SoftmaxDiceFunction(torch.autograd.Function):
+    """(sums[N,3,C], probs[N,C,...]) = Dice sums of softmax(logits) against ``target`` and the softmax itself, one pass;
+    the backward folds the gradient arriving at ``probs`` into the same pass (no second softmax backward, no sum of
+    two full-size gradients)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        logits = _f32(logits, "source")
+        N, C = logits.shape[:2]
+        V = logits[0, 0].numel()
+        if not target.is_cuda:
+            raise RuntimeError("deepatlas_b200: 'target' must be a CUDA tensor")
+        if target.is_floating_point():
+            target = _f32(target, "target")
+            if target.numel() != logits.numel():
+                raise ValueError("dice: soft target must have the shape of source")
+            kind = 2
+        else:
+            if target.dtype not in _KIND:
+                target = target.long()
+            target = target.contiguous()
+            if target.numel() != N * V:
+                raise ValueError("dice: label target must have N*D*H*W elements")
+            kind = _KIND[target.dtype]
+        sums = torch.empty((N, 3, C), dtype=torch.float32, device=logits.device)
+        probs = torch.empty_like(logits)
+        nb = _lib.size("da_dice_workspace_bytes", N, C, V)
+        ws = _ws(nb, logits.device)
+        _lib.call("da_softmax_dice_fwd", _p(logits), _p(target), kind, N, C, V, _p(sums), _p(probs), _p(ws), nb, _stream())
+        ctx.save_for_backward(logits, target)
+        ctx.kind = kind
+        return sums, probs
+
+    @staticmethod
+    def backward(ctx, g, gp):
+        logits, target = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        N, C = logits.shape[:2]
+        V = logits[0, 0].numel()
+        g = torch.zeros((N, 3, C), device=logits.device) if g is None else _f32(g, "grad_sums")
+        gS, gT, gI = g[:, 0].contiguous(), g[:, 1].contiguous(), g[:, 2].contiguous()
+        gp = _f32(gp, "grad_probs") if gp is not None else None
+        gx = torch.empty_like(logits)
+        _lib.call("da_softmax_dice_bwd", _p(logits), _p(target), ctx.kind, N, C, V, _p(gS), _p(gT), _p(gI), _p(gp), _p(gx),
+                  _stream())
+        return gx, None
+
+
+def softmax_dice(logits, target):
+    return SoftmaxDiceFunction.apply(logits, target)
+
+
 class WarpedDiceSumsFunction(torch.autograd.Function):
     """sums[N,3,C] of dice(grid_sample(prob, phi), onehot(labels)) without materialising the warped map: the anatomy
     term of the joint step; see csrc/warp_dice.cu for the structure of the backward."""

@@ -234,6 +234,15 @@ int da_lncc_ms_fwd(const float* I, const float* J, int N, int D, int H, int W, i
 int da_lncc_ms_bwd(const float* I, const float* J, const float* coef, int which, const float* grad_scale, float scale, int N,
                    int D, int H, int W, int k, int dil, int stride, int accumulate, float* grad, da_stream_t stream);
 
+/* softmax + Dice sums + the probabilities in one pass over the logits, for a prediction that feeds the supervised Dice
+ * term and, as probabilities, a second consumer (the anatomy term of the joint step): replaces da_dice_sums_fwd
+ * (apply_softmax) + da_softmax_fwd, and in the backward da_dice_sums_bwd + da_softmax_bwd + the sum of their results.
+ * probs, grad_probs (nullable), grad_logits [N,C,V]; targets as for da_dice_sums_fwd. */
+int da_softmax_dice_fwd(const float* logits, const void* target, int target_kind, int N, int C, int64_t V, float* sums,
+                        float* probs, void* workspace, int64_t workspace_bytes, da_stream_t stream);
+int da_softmax_dice_bwd(const float* logits, const void* target, int target_kind, int N, int C, int64_t V, const float* gS,
+                        const float* gT, const float* gI, const float* grad_probs, float* grad_logits, da_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,3 +317,32 @@ def test_lncc_multiscale(cuda, size):
     assert rel_err(loss, truth) < max(TOL, 3 * rel_err(ref32, truth))
     for ours, r32, t64 in ((Ig.grad, I32.grad, I64.grad), (Jg.grad, J32.grad, J64.grad)):
         assert rel_err(ours, t64) < max(TOL, 3 * rel_err(r32, t64))
+
+
+@pytest.mark.parametrize("C", [4, 32])
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+def test_softmax_dice_with_probs_equals_the_two_pass_form(cuda, C, dtype):
+    """forward_with_probs == (forward, softmax) and its single backward pass == the sum of the two separate backwards."""
+    import deepatlas_b200 as da
+    from deepatlas_b200 import ops
+    g = _g()
+    size = (9, 10, 12)
+    x = torch.randn((2, C) + size, generator=g)
+    t = torch.randint(0, C, (2,) + size, generator=g).to(dtype).to(cuda)
+    cot = torch.randn((2, C) + size, generator=g).to(cuda)
+    crit = da.get_loss_function("dice")(n_class=C, weight_type="Uniform", softmax=True, eps=1e-6)
+    xa = x.to(cuda).requires_grad_(True)
+    la, pa = crit.forward_with_probs(xa, t)
+    (3.0 * la + (pa * cot).sum()).backward()
+    xb = x.to(cuda).requires_grad_(True)
+    lb, pb = crit(xb, t), ops.softmax(xb)
+    (3.0 * lb + (pb * cot).sum()).backward()
+    assert torch.equal(la, lb) and torch.equal(pa, pb)
+    assert rel_err(xa.grad, xb.grad) < 1e-5
+    # only one of the two outputs used downstream
+    xc = x.to(cuda).requires_grad_(True)
+    lc, _ = crit.forward_with_probs(xc, t)
+    lc.backward()
+    xd = x.to(cuda).requires_grad_(True)
+    crit(xd, t).backward()
+    assert rel_err(xc.grad, xd.grad) < 1e-6
