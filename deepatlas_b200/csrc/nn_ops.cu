@@ -11,7 +11,10 @@
 namespace {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_SPLITS = 32;  // blocks per channel for the statistics passes
+#ifndef DA_BN_SPLITS
+#define DA_BN_SPLITS 32
+#endif
+constexpr int BN_SPLITS = DA_BN_SPLITS;  // blocks per channel for the statistics passes
 
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) { return (act && z <= 0.f) ? z * slope : z; }
 __device__ __forceinline__ float act_grad(float z, int act, float slope) { return (act && z <= 0.f) ? slope : 1.f; }
