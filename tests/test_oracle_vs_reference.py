@@ -2,6 +2,8 @@
 imported from /root/reference where they lie (build container only; skipped on the GPU box, where the golden
 fixtures made by oracle/make_golden.py take over).  fp32 on CPU; the port must be BIT-identical because it
 restates the reference on top of the same ATen calls."""
+import os
+
 import pytest
 import torch
 
@@ -281,3 +283,66 @@ def test_checkpoint_round_trip_through_reference_code(tmp_path):
         assert (epoch, best) == (4, 0.25)
         for k, v in m.state_dict().items():
             assert torch.equal(v, r.state_dict()[k]), k
+
+
+def test_reference_trainer_through_the_registry_seams(tmp_path, monkeypatch):
+    """BASELINE config C1 (plumbing): the reference's own SegmentationExperiment.train() runs two epochs on synthetic 16^3
+    volumes on the CPU with the harness shims of SURVEY.md Appendix A and writes its checkpoints; after install() the
+    SAME trainer code constructs this package's network and loss through its registries (models/segmentation.py:81-88)
+    and its own initialize_model() restores the checkpoint it has just written into them (strict=True)."""
+    import deepatlas_b200 as da
+    refm = ref_import.load(with_models=True)
+    seg = refm.segmentation
+    n_classes, size = 4, (16, 16, 16)
+
+    class SyntheticDataset(torch.utils.data.Dataset):     # lib/datasets.py:68: [image (1,D,H,W) f32, seg (D,H,W) u8, name]
+        def __init__(self, list_file, data_dir, with_seg=True, preload=False, pre_transform=None, n_samples=2, **kw):
+            g = torch.Generator().manual_seed(230)
+            self.items = [(torch.rand((1,) + size, generator=g), torch.randint(0, n_classes, size, generator=g, dtype=torch.uint8))
+                          for _ in range(2)]
+
+        def __len__(self):
+            return len(self.items)
+
+        def __getitem__(self, i):
+            return [self.items[i][0], self.items[i][1], f"case{i}"]
+
+    monkeypatch.setattr(seg.med_data, "get_seg_dataset", lambda name: SyntheticDataset)
+    monkeypatch.setattr(seg.vis, "make_segmentation_image_summary", lambda *a, **k: torch.zeros(3, 8, 8))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "manual_seed", lambda *a, **k: None)
+
+    def config():
+        return dict(debug_mode=True, resume_dir="", random_seed=230, data="MindBoggle", n_epochs=2, samples_per_epoch=2, batch_size=1,
+                    valid_batch_size=1, print_batch_period=50, valid_epoch_period=1, save_ckpts_epoch_period=1, model="UNet_light",
+                    model_settings={"in_channel": 1, "n_classes": n_classes, "bias": True, "BN": True}, n_classes=n_classes,
+                    class_name={k: str(k) for k in range(1, n_classes)}, crop_size=None, loss="dice",
+                    loss_settings={"n_class": n_classes, "weight_type": "Uniform", "no_bg": False, "softmax": True, "eps": 1e-6},
+                    learning_rate=1e-3, lr_mode="multiStep", milestones=[0.5, 1], gamma=0.2, num_samples=1, preload=True,
+                    data_dir=str(tmp_path / "data"), valid_data_dir=str(tmp_path / "data"), training_list_file="train.txt",
+                    validation_list_file="valid.txt", testing_list_file="test.txt", log_dir=str(tmp_path / "logs"))
+
+    exp = seg.SegmentationExperiment(config())
+    exp.train()
+    ckpt = os.path.join(exp.ckpoint_dir, "checkpoint.pth.tar")
+    assert os.path.isfile(ckpt) and os.path.isfile(os.path.join(exp.ckpoint_dir, "train_config.json"))
+    assert type(exp.model).__module__.startswith("lib.network_factory")
+
+    keep_n, keep_l = dict(refm.network_dic), dict(refm.loss_dict)
+    try:
+        da.install(refm.network_factory, refm.loss)
+        exp2 = seg.SegmentationExperiment(config())
+        exp2.setup_model()
+        exp2.setup_loss()
+        exp2.setup_optimizer()
+        assert isinstance(exp2.model, da.UNet_light) and isinstance(exp2.criterion, da.DiceLossMultiClass)
+        epoch, best = exp2.initialize_model(exp2.model, exp2.optimizer, ckpt)      # the reference's own loader, strict=True
+        assert epoch == 2
+        for k, v in exp.model.state_dict().items():
+            assert torch.equal(v, exp2.model.state_dict()[k]), k
+        with pytest.raises(RuntimeError):                                          # and there is no CPU path behind it
+            exp2.model(torch.rand((1, 1) + size))
+    finally:
+        refm.network_dic.clear(); refm.network_dic.update(keep_n)
+        refm.loss_dict.clear(); refm.loss_dict.update(keep_l)
