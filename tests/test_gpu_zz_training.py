@@ -1,0 +1,55 @@
+"""A short TRAINING run on the GPU against the same run restated on the CPU oracle: the loop of
+models/segmentation.py:139-160 (zero_grad, forward, Dice on uint8 labels, backward, Adam step) for three steps.
+Judged on the loss trajectory: Adam's first updates are lr * sign(g), so parameters whose gradient is analytically zero
+(a conv bias in front of a BatchNorm) move by +-lr at random in BOTH implementations without touching any output."""
+import pytest
+import torch
+
+from parity_util import cpu_state, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_three_adam_steps_follow_the_oracle(cuda):
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    n_classes, size, steps = 4, (16, 24, 16), 3
+    torch.manual_seed(230)
+    net = da.get_network("UNet_light")(1, n_classes, bias=True, BN=True).to(cuda)
+    net.weights_init()
+    net.train()
+    g = torch.Generator().manual_seed(230)
+    x = torch.rand((1, 1) + size, generator=g)
+    lab = torch.randint(0, n_classes, (1,) + size, generator=g, dtype=torch.uint8)
+    # the oracle's copy: float64 leaves (the truth rung), same Adam
+    sd = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else (v.double() if v.is_floating_point() else v.clone()))
+          for k, v in cpu_state(net).items()}
+    leaves = [v for v in sd.values() if v.is_floating_point() and v.requires_grad]
+    opt_ref = torch.optim.Adam(leaves, lr=1e-3)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    crit = da.get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", no_bg=False, softmax=True, eps=1e-6)
+    xg, lg = x.to(cuda), lab.to(cuda)
+    ours, ref = [], []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = crit(net(xg), lg)
+        loss.backward()
+        opt.step()
+        ours.append(float(loss.detach()))
+        opt_ref.zero_grad()
+        stats = {}
+        y = P.unet_generator_forward(x.double(), sd, 1, True, stats_out=stats)
+        l_ref = P.dice_multiclass(y, lab.long(), n_classes, "Uniform", False, True, 1e-6)
+        l_ref.backward()
+        opt_ref.step()
+        for k, v in stats.items():      # running statistics move as nn.BatchNorm3d moves them
+            sd[k] = v
+        ref.append(float(l_ref.detach()))
+    assert ours[-1] < ours[0], ours                       # it trains
+    for a, b in zip(ours, ref):
+        assert abs(a - b) <= 1e-3 * abs(b), (ours, ref)
+    # the running statistics after three steps (momentum 0.1, unbiased variance) agree as well
+    after = net.state_dict()
+    for k in ("encoders.0.0.BN.running_mean", "encoders.0.0.BN.running_var", "decoders.decBlock2.1.BN.running_var"):
+        assert rel_err(after[k], sd[k]) < 1e-2, k
+    assert int(after["encoders.0.0.BN.num_batches_tracked"]) == steps
