@@ -170,6 +170,48 @@ __global__ void __launch_bounds__(DICE_THREADS) dice_bwd_kernel(
 }
 
 
+// The hot instantiation of the backward -- label target, softmax inside, optionally a second gradient arriving at the
+// probabilities (GP) -- as its own kernel: the general one carries four uniform branches (target kind, softmax,
+// grad_target, gprob) and at CP = 32 ptxas keeps both sides alive, 255 registers plus 1.4 KB of spills per thread.
+// Here the upstream gradient of channel c is formed on the fly (never stored as an array).
+template <int CP, bool GP>
+__global__ void __launch_bounds__(DICE_THREADS) softmax_dice_bwd_label_kernel(
+    const float* __restrict__ source, const void* __restrict__ target, int kind, int C, int64_t V, const float* __restrict__ gS,
+    const float* __restrict__ gI, const float* __restrict__ gprob, float* __restrict__ grad_source) {
+  const int n = blockIdx.y;
+  __shared__ float sg[2][CP];
+  for (int i = threadIdx.x; i < 2 * CP; i += DICE_THREADS) {
+    const int q = i / CP, c = i - q * CP;
+    sg[q][c] = (c < C) ? (q == 0 ? gS : gI)[n * C + c] : 0.f;
+  }
+  __syncthreads();
+  const float* s = source + (int64_t)n * C * V;
+  const float* gq = GP ? gprob + (int64_t)n * C * V : nullptr;
+  float* gs = grad_source + (int64_t)n * C * V;
+  float p[CP], u[CP];
+  for (int64_t v = (int64_t)blockIdx.x * DICE_THREADS + threadIdx.x; v < V; v += (int64_t)gridDim.x * DICE_THREADS) {
+    if (GP) {
+#pragma unroll
+      for (int c = 0; c < CP; ++c) u[c] = (c < C) ? gq[(int64_t)c * V + v] : 0.f;
+    }
+    load_probs<CP>(s, V, v, C, true, p);
+    const int lab = load_label(target, kind, (int64_t)n * V + v);
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      const float g = sg[0][c] + ((lab == c) ? sg[1][c] : 0.f) + (GP ? u[c] : 0.f);
+      if (GP) u[c] = g;
+      dot = fmaf(p[c], g, dot);
+    }
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      const float g = GP ? u[c] : sg[0][c] + ((lab == c) ? sg[1][c] : 0.f);
+      if (c < C) gs[(int64_t)c * V + v] = p[c] * (g - dot);
+    }
+  }
+}
+
+
 // channel softmax (F.softmax(dim=1), lib/loss.py:427 semantics) materialised once for the anatomy branch,
 // where the probabilities are themselves warped.
 template <int CP>
@@ -277,6 +319,18 @@ DA_API int da_softmax_dice_bwd(const float* logits, const void* target, int targ
   DA_REQUIRE(logits && target && gS && gI && grad_logits, "da_softmax_dice_bwd: null pointer");
   DA_REQUIRE(C >= 1 && C <= 64, "da_softmax_dice_bwd: unsupported class count %d (1..64)", C);
   dim3 grid(dice_blocks(V), N);
+  if (target_kind != TK_SOFT && C <= 32) {
+    if (grad_probs) {
+#define CALL(CP) softmax_dice_bwd_label_kernel<CP, true><<<grid, DICE_THREADS, 0, stream>>>(logits, target, target_kind, C, V, gS, gI, grad_probs, grad_logits)
+      DICE_DISPATCH(CALL)
+#undef CALL
+    } else {
+#define CALL(CP) softmax_dice_bwd_label_kernel<CP, false><<<grid, DICE_THREADS, 0, stream>>>(logits, target, target_kind, C, V, gS, gI, nullptr, grad_logits)
+      DICE_DISPATCH(CALL)
+#undef CALL
+    }
+    return da_check_launch("da_softmax_dice_bwd/label");
+  }
 #define CALL(CP) dice_bwd_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(logits, target, target_kind, 1, C, V, gS, gT, gI, grad_logits, nullptr, grad_probs)
   DICE_DISPATCH(CALL)
 #undef CALL
@@ -291,6 +345,12 @@ DA_API int da_dice_sums_bwd(const float* source, const void* target, int target_
   DA_REQUIRE(C >= 1 && C <= 64, "da_dice_sums_bwd: unsupported class count %d (1..64)", C);
   DA_REQUIRE(grad_target == nullptr || target_kind == TK_SOFT, "da_dice_sums_bwd: grad_target needs a soft target");
   dim3 grid(dice_blocks(V), N);
+  if (apply_softmax && target_kind != TK_SOFT && grad_source && C <= 32) {   // (at 64 classes the general kernel is the spill-free one)
+#define CALL(CP) softmax_dice_bwd_label_kernel<CP, false><<<grid, DICE_THREADS, 0, stream>>>(source, target, target_kind, C, V, gS, gI, nullptr, grad_source)
+    DICE_DISPATCH(CALL)
+#undef CALL
+    return da_check_launch("da_dice_sums_bwd/label");
+  }
 #define CALL(CP) dice_bwd_kernel<CP><<<grid, DICE_THREADS, 0, stream>>>(source, target, target_kind, apply_softmax, C, V, gS, gT, gI, grad_source, grad_target, nullptr)
   DICE_DISPATCH(CALL)
 #undef CALL
