@@ -1,6 +1,7 @@
 """The C-ABI boundary: include/deepatlas_b200.h, the ctypes table in deepatlas_b200/_lib.py and the symbols the
 built shared library exports must agree (no compute calls -- runs without a GPU)."""
 import ctypes
+import os
 import subprocess
 
 import pytest
@@ -54,3 +55,17 @@ def test_no_cpu_fallback_and_missing_library_is_loud(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libdeepatlas_b200.so"))
     with pytest.raises(RuntimeError, match="not built"):
         _lib.load()
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/deepatlas_b200.h is what a C (not C++) host would include: it must compile as C99 with warnings on."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "deepatlas_b200.h"\nint main(void) { return da_version() == 0; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
