@@ -225,3 +225,23 @@ def test_dice_on_label_closing_formula(monkeypatch):
         for n_class in (None, 8):
             ours = da.DiceLossOnLabel(n_class=n_class)(a, b, weight_type=wt)
             assert abs(float(ours) - float(P.dice_on_label(a, b, n_class, 10e-6, wt))) < 1e-6, (wt, n_class)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under deepatlas_b200/ may import it (or tests/), and only bench.py's CPU
+    legs and __graft_entry__.smoke() may do so at the repo root."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "deepatlas_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for n in names:
+                assert not (n == "oracle" or n.startswith("oracle.") or n == "tests" or n.startswith("tests.") or n == "parity_util"), (fn, n)
