@@ -28,6 +28,21 @@ int da_check_launch(const char* what, int nkernels = 1);
 static __host__ __device__ inline int64_t da_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t da_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE attribute: one process may drive several GPUs
+// (tests, a user who moves a model), so "configured once" must be tracked per device.  first() returns true until it
+// has been called once for the current device (a benign race between threads just sets the attribute twice).
+struct DaPerDeviceOnce {
+  unsigned long long done[2] = {0ull, 0ull};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) d = 0;
+    d &= 127;
+    const unsigned long long bit = 1ull << (d & 63);
+    const unsigned long long old = __atomic_fetch_or(&done[d >> 6], bit, __ATOMIC_RELAXED);
+    return (old & bit) == 0;
+  }
+};
+
 // number of SMs on a B200; grids of persistent / grid-stride kernels are sized in multiples of it
 #define DA_NUM_SMS 148
 

@@ -739,10 +739,9 @@ int launch_tiled(const float* x1, const float* x2, const float* wp, const float*
                  cudaStream_t stream) {
   const int tiles_x = (g.Wo + TX - 1) / TX, tiles_y = (g.Ho + TY - 1) / TY, tiles_z = (g.Do + TZ - 1) / TZ;
   const size_t smem = sizeof(float) * (CK * HZ * HY * HXP + CK * 27 * CO);
-  static bool configured = false;
-  if (!configured) {
+  static DaPerDeviceOnce configured;
+  if (configured.first()) {
     cudaFuncSetAttribute(conv3d_tiled_kernel<CK, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
   }
   dim3 grid(tiles_x * tiles_y * tiles_z, g.Cop / CO, g.N);
   conv3d_tiled_kernel<CK, CO><<<grid, TILED_THREADS, smem, stream>>>(x1, x2, wp, bias, out, g, tiles_x, tiles_y);
@@ -871,12 +870,11 @@ int launch_fwd_tma(const float* x1, const float* x2, const float* wp, const floa
   } else {
     m2 = m1;
   }
-  static bool configured = false;
-  if (!configured) {
+  static DaPerDeviceOnce configured;
+  if (configured.first()) {
     cudaFuncSetAttribute(conv3d_fwd_tma_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdTmaCfg<CO>::SMEM_BYTES);
     if constexpr (CO >= 8)
       cudaFuncSetAttribute(conv3d_fwd_tma2_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd2Cfg<CO>::SMEM_BYTES);
-    configured = true;
   }
   const int tiles_x = (g.Wo + TX - 1) / TX, tiles_y = (g.Ho + TY - 1) / TY, tiles_z = (g.Do + TZ - 1) / TZ;
   dim3 grid(tiles_x * tiles_y * tiles_z, g.Cop / CO, g.N);
@@ -945,13 +943,12 @@ inline unsigned long long* umma_dbg_buffer() {
 }
 
 int launch_umma(const UmmaArgs& a, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static DaPerDeviceOnce configured;
+  if (configured.first()) {
     cudaFuncSetAttribute(conv3d_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
     cudaFuncSetAttribute(conv3d_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
     cudaFuncSetAttribute(conv3d_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
     cudaFuncSetAttribute(conv3d_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
-    configured = true;
   }
   dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N * a.nco);
   if (a.dbg) {
@@ -1246,11 +1243,10 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
   const int Cin = C1 + C2;
   const int64_t count = (int64_t)Cin * Cout * 27;
   const int tiles_x = (Wi + WU_XT - 1) / WU_XT, tiles_y = (Hi + WU_YT - 1) / WU_YT;
-  static bool configured = false;
-  if (!configured) {
+  static DaPerDeviceOnce configured;
+  if (configured.first()) {
     cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WU_SMEM_BYTES);
     cudaFuncSetAttribute(conv3d_wgrad_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WV_SMEM_BYTES);
-    configured = true;
   }
   int rc, nregions;
   float* bias_partials = nullptr;  // set when the kernel folds the bias gradient in
@@ -1362,11 +1358,10 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
     if (wgrad_umma_ok(N, Di, Hi, Wi))
       return run_wgrad_umma(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, partials, cap, stream);
     float* bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
-    static bool configured = false;
-    if (!configured) {
+    static DaPerDeviceOnce configured;
+    if (configured.first()) {
       cudaFuncSetAttribute(conv3d_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM);
       cudaFuncSetAttribute(conv3d_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WTM_SMEM_BYTES);
-      configured = true;
     }
     const bool use_tma = !tma_disabled() && (Wi & 3) == 0;
     auto launch_t = [&](const float* xin, int C, int ci_off, int Cin_total_, const float* gout, int Cout_, int co_off,
@@ -1424,10 +1419,9 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
     const int tpr = (ntiles + nregions - 1) / nregions;
     nregions = (ntiles + tpr - 1) / tpr;
     float* bias_partials = grad_bias ? partials + (int64_t)nregions * count : nullptr;
-    static bool configured_s2 = false;
-    if (!configured_s2) {
+    static DaPerDeviceOnce configured_s2;
+    if (configured_s2.first()) {
       cudaFuncSetAttribute(conv3d_wgrad_s2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_BYTES);
-      configured_s2 = true;
     }
     auto launch_s2 = [&](const float* xin, int C, int ci_off, float* bp) -> int {
       WgTiledArgs a;

@@ -396,10 +396,9 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
     int r = da_make_volume_map(&mx, x, N, Cin, D, H, W, DT_TX, DT_TY, 1, DT_CI);
     if (!r) r = da_make_volume_map(&mdy, dy, N, Cout, 2 * D, 2 * H, 2 * W, 2 * DT_TX, 2 * DT_TY, 2, DT_CO);
     if (r) return r;
-    static bool configured = false;
-    if (!configured) {
+    static DaPerDeviceOnce configured;
+    if (configured.first()) {
       cudaFuncSetAttribute(deconv_k2s2_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
-      configured = true;
     }
     deconv_k2s2_wgrad_tma_kernel<<<dim3(groups, nregions), DT_THREADS, DT_SMEM_BYTES, stream>>>(mx, mdy, a);
     int rc = da_check_launch("da_deconv_k2s2_wgrad_tma");

@@ -34,7 +34,13 @@ class FlatGradBucket:
     """All parameter gradients as views into ONE contiguous fp32 buffer.
 
     ``p.grad`` of every parameter is pre-set to a view of ``self.flat`` so autograd accumulates straight
-    into the bucket; ``zero()`` is one memset, ``allreduce()`` one collective (sum, then 1/world scaling)."""
+    into the bucket; ``zero()`` is one memset, ``allreduce()`` one collective (sum, then 1/world scaling).
+
+    The reference trainer calls ``optimizer.zero_grad()`` (models/segmentation.py:142), whose default
+    ``set_to_none=True`` drops the views: the next backward would then allocate fresh gradients OUTSIDE the bucket and
+    ``allreduce()`` would average zeros.  ``rebind()`` -- called by ``allreduce()`` -- detects that (``p.grad`` is None
+    or does not alias its slot), copies such gradients into the bucket and restores the views, so the collective is
+    always over the real gradients.  Prefer ``zero()`` / ``zero_grad()`` of the bucket (one memset, views kept)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
@@ -43,11 +49,15 @@ class FlatGradBucket:
         dev = self.params[0].device
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._views: List[torch.Tensor] = []
         off = 0
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            v = self.flat[off:off + n].view_as(p)
+            self._views.append(v)
+            p.grad = v
             off += n
+        self.rebound = 0   # gradients found outside the bucket so far (diagnostic)
 
     @property
     def nbytes(self) -> int:
@@ -55,12 +65,36 @@ class FlatGradBucket:
 
     def zero(self):
         self.flat.zero_()
+        self.rebind(copy=False)
+
+    zero_grad = zero
+
+    def rebind(self, copy: bool = True) -> int:
+        """Make every ``p.grad`` a view of its bucket slot again.  With ``copy`` a gradient that autograd produced
+        outside the bucket (after ``optimizer.zero_grad(set_to_none=True)``) is copied into its slot first; a
+        parameter without a gradient gets a zeroed slot.  Returns the number of parameters that had to be fixed."""
+        fixed = 0
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is not None and g.data_ptr() == v.data_ptr() and g.shape == v.shape and g.is_contiguous():
+                continue
+            fixed += 1
+            if copy:
+                if g is None:
+                    v.zero_()
+                else:
+                    v.copy_(g)
+            p.grad = v
+        self.rebound += fixed
+        return fixed
 
     def allreduce(self, world: int | None = None):
-        """One collective per step.  No-op for a single process."""
+        """One collective per step.  No collective for a single process (the views are still re-checked)."""
         if not dist.is_available() or not dist.is_initialized():
+            self.rebind(copy=True)
             return
         world = world or dist.get_world_size()
+        self.rebind(copy=True)   # every rank does this before the collective: the bucket always holds the real gradients
         if world == 1:
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
@@ -75,12 +109,24 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0):
         dist.broadcast(t.data, src)
 
 
-def shard_pairs(num_items: int, rank: int, world: int, seed: int = 230, epoch: int = 0):
+def shard_pairs(num_items: int, rank: int, world: int, seed: int = 230, epoch: int = 0, drop_last: bool = False):
     """Rank-strided slice of the shuffled ordered-pair index list.  Pair id -> (fixed, moving) follows
-    lib/datasets.py:344-359: fixed = id // (N-1); moving = id % (N-1), +1 if >= fixed."""
+    lib/datasets.py:344-359: fixed = id // (N-1); moving = id % (N-1), +1 if >= fixed.
+
+    EVERY rank gets the same number of pairs (one gradient all-reduce per pair: unequal counts would leave some
+    ranks waiting in NCCL for a collective the others never issue).  When N(N-1) is not a multiple of ``world`` the
+    shuffled list is padded by wrapping around, as torch's DistributedSampler does (``drop_last=True`` truncates
+    instead); ``len(shard_pairs(...)) == ceil(N(N-1) / world)`` (floor with ``drop_last``) on all ranks."""
+    if not (0 <= rank < world):
+        raise ValueError(f"shard_pairs: rank {rank} outside world of {world}")
     n_pairs = num_items * (num_items - 1)
     g = torch.Generator().manual_seed(seed + epoch)
     perm = torch.randperm(n_pairs, generator=g).tolist()
+    if drop_last:
+        perm = perm[:(n_pairs // world) * world]
+    elif n_pairs % world and n_pairs:
+        pad = world - n_pairs % world
+        perm = perm + (perm * ((pad + n_pairs - 1) // n_pairs))[:pad]
     out = []
     for pid in perm[rank::world]:
         fixed = pid // (num_items - 1)

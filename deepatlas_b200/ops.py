@@ -32,7 +32,17 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
         raise RuntimeError(f"deepatlas_b200: '{name}' must be a CUDA tensor (no CPU fallback exists)")
     if t.dtype != torch.float32:
         raise RuntimeError(f"deepatlas_b200: '{name}' must be float32, got {t.dtype}")
+    _check_device(t, name)
     return t.contiguous()
+
+
+def _check_device(t: torch.Tensor, name: str):
+    """Kernels launch on the CURRENT device's current stream (``_stream()``): a tensor living on another GPU would be
+    dereferenced in the wrong context.  Fail loudly instead; ``with torch.cuda.device(t.device):`` is the fix."""
+    cur = torch.cuda.current_device()
+    if t.device.index != cur:
+        raise RuntimeError(f"deepatlas_b200: '{name}' lives on {t.device} but the current CUDA device is cuda:{cur}; "
+                           f"wrap the call in `with torch.cuda.device({t.device.index}):` (one process per GPU is the supported layout)")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -177,6 +187,10 @@ class SoftmaxDiceFunction(torch.autograd.Function):
         nb = _lib.size("da_dice_workspace_bytes", N, C, V)
         ws = _ws(nb, logits.device)
         _lib.call("da_softmax_dice_fwd", _p(logits), _p(target), kind, N, C, V, _p(sums), _p(probs), _p(ws), nb, _stream())
+        if kind == 2 and ctx.needs_input_grad[1]:
+            # the fused backward forms only the logits gradient; DiceSumsFunction handles differentiable soft targets
+            raise RuntimeError("deepatlas_b200: softmax_dice does not differentiate a soft target; "
+                               "use dice_sums(source, target, apply_softmax=True) for a target that requires grad")
         ctx.save_for_backward(logits, target)
         ctx.kind = kind
         return sums, probs

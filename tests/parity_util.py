@@ -1,5 +1,37 @@
 """Shared helpers for the parity tests (test infrastructure; may import oracle/)."""
+import contextlib
+import json
+import os
+
 import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT_PATH = os.path.join(_ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def report(test, **metrics):
+    """Append one line of measured parity numbers (worst error ratios, not just a pass bit) to
+    gpurun_out/parity_report.jsonl; tools/summarise_parity.py turns the file into profiles/rNN_parity.md."""
+    line = json.dumps(dict(test=test, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in metrics.items()}))
+    print("PARITY " + line)
+    try:
+        os.makedirs(os.path.dirname(REPORT_PATH), exist_ok=True)
+        with open(REPORT_PATH, "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
+@contextlib.contextmanager
+def conv_impl(name):
+    """Selects the k3 convolution kernels for the enclosed CUDA calls: 'auto' (size heuristics, what a user gets),
+    'umma' (tcgen05 forward / data gradient / weight gradient wherever structurally possible), 'ffma', 'direct'."""
+    from deepatlas_b200 import _lib
+    _lib.call("da_set_conv_impl", {"auto": 0, "direct": 1, "ffma": 2, "umma": 3}[name])
+    try:
+        yield
+    finally:
+        _lib.call("da_set_conv_impl", 0)
 
 
 def rel_err(a, b):
@@ -53,6 +85,7 @@ def check_grads_vs_truth(ours, ref32, truth64, tol, slack=3.0, floor=1e-3):
     gradients (conv bias in front of a BatchNorm) are judged on an absolute scale.  Returns the worst ratio."""
     gmax = max(float(v.abs().max()) for v in truth64.values())
     worst = (0.0, None)
+    worst_abs = (0.0, None)
     for k, t in truth64.items():
         assert k in ours, f"missing gradient {k}"
         scale = max(float(t.abs().max()), floor * gmax)
@@ -62,7 +95,10 @@ def check_grads_vs_truth(ours, ref32, truth64, tol, slack=3.0, floor=1e-3):
         assert e_ours <= bound, f"grad {k}: ours-vs-fp64 {e_ours:.3e} > bound {bound:.3e} (reference fp32-vs-fp64 {e_ref:.3e})"
         if e_ours / bound > worst[0]:
             worst = (e_ours / bound, k)
-    return worst
+        if e_ours > worst_abs[0]:
+            worst_abs = (e_ours, k, e_ref)
+    return {"worst_ratio_to_bound": worst[0], "worst_ratio_param": worst[1], "worst_rel_err_vs_fp64": worst_abs[0],
+            "worst_rel_err_param": worst_abs[1], "reference_fp32_rel_err_same_param": worst_abs[2] if len(worst_abs) > 2 else None}
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -99,3 +99,41 @@ def test_single_process_is_a_no_op():
     assert torch.equal(before, b.flat) and float(before.abs().sum()) > 0
     b.zero()
     assert float(lin.weight.grad.abs().sum()) == 0.0
+
+
+def test_shard_pairs_equal_lengths_on_every_rank():
+    """5 volumes = 20 ordered pairs over 8 ranks: every rank must run the same number of steps (one all-reduce each),
+    otherwise the job hangs in NCCL at the end of the epoch.  Padding wraps around like DistributedSampler."""
+    from deepatlas_b200.dist import shard_pairs
+    N, world = 5, 8
+    shards = [shard_pairs(N, r, world, seed=230) for r in range(world)]
+    assert {len(s) for s in shards} == {3}                      # ceil(20 / 8)
+    allp = [p for s in shards for p in s]
+    assert len(set(allp)) == 20                                  # every pair is still visited
+    dropped = [shard_pairs(N, r, world, seed=230, drop_last=True) for r in range(world)]
+    assert {len(s) for s in dropped} == {2} and len({p for s in dropped for p in s}) == 16
+    with pytest.raises(ValueError):
+        shard_pairs(N, 8, world)
+
+
+def test_bucket_survives_optimizer_zero_grad_set_to_none():
+    """The reference trainer calls optimizer.zero_grad() (models/segmentation.py:142), default set_to_none=True: the
+    next backward allocates gradients outside the bucket.  allreduce() must find them, copy them in and re-bind."""
+    from deepatlas_b200.dist import FlatGradBucket
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(3, 2)
+    b = FlatGradBucket(lin.parameters())
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    opt.zero_grad()                                              # set_to_none=True: p.grad is None now
+    assert lin.weight.grad is None
+    lin(torch.ones(1, 3)).sum().backward()                       # fresh gradient tensors, not views of the bucket
+    expect = torch.cat([p.grad.flatten().clone() for p in lin.parameters()])
+    assert float(b.flat.abs().sum()) == 0.0
+    b.allreduce()
+    assert b.rebound == 2
+    assert torch.equal(b.flat, expect)
+    for p in lin.parameters():
+        assert b.flat.data_ptr() <= p.grad.data_ptr() < b.flat.data_ptr() + b.nbytes
+    b.zero()                                                     # the bucket's own zero keeps the views
+    lin(torch.ones(1, 3)).sum().backward()
+    assert torch.equal(b.flat, expect) and b.rebind() == 0

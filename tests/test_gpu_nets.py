@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from parity_util import MaskRecorder, MaskReplay, check_grads_vs_truth, cpu_state, oracle_joint_loss, rel_err
+from parity_util import MaskRecorder, MaskReplay, check_grads_vs_truth, conv_impl, cpu_state, oracle_joint_loss, rel_err, report
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4        # forward outputs (north star)
@@ -14,8 +14,15 @@ def _param_grads(model):
     return {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
 
 
+# impl "umma": every k3 s1 p1 forward, data gradient and weight gradient of the network runs on the tcgen05 kernels
+# (conv3d_umma*_kernel, conv3d_wgrad_umma*_kernel) whatever the size heuristics say -- the kernels that carry the
+# benchmark step -- including the multi-chunk accumulation, the two-source concatenation and the fused bias/activation
+IMPLS = ["auto", "umma"]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("n_classes,size,bn", [(4, (32, 32, 32), True), (32, (16, 24, 16), True), (3, (16, 16, 24), False)])
-def test_unet_light(cuda, n_classes, size, bn):
+def test_unet_light(cuda, n_classes, size, bn, impl):
     import deepatlas_b200 as da
     from oracle import ref_port as P
     torch.manual_seed(230)
@@ -28,10 +35,11 @@ def test_unet_light(cuda, n_classes, size, bn):
     sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else (v.double() if v.is_floating_point() else v))
             for k, v in cpu_state(net).items()}
     crit = da.get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", softmax=True, eps=1e-6)
-    with MaskRecorder() as rec:   # the oracle takes the CUDA path's activation branches (parity_util.MaskReplay)
-        y = net(x.to(cuda))
-    loss = crit(y, lab.to(cuda))
-    loss.backward()
+    with conv_impl(impl):
+        with MaskRecorder() as rec:   # the oracle takes the CUDA path's activation branches (parity_util.MaskReplay)
+            y = net(x.to(cuda))
+        loss = crit(y, lab.to(cuda))
+        loss.backward()
     stats = {}
     replay = MaskReplay(rec.masks)
     with replay:
@@ -51,8 +59,10 @@ def test_unet_light(cuda, n_classes, size, bn):
     decided = (top2[:, 0] - top2[:, 1]) > 1e-5 * y64.abs().max()
     assert torch.equal(y.argmax(1).cpu()[decided], y_ref.argmax(1)[decided])
     assert decided.float().mean() > 0.99
-    check_grads_vs_truth(_param_grads(net), {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.requires_grad},
-                         {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.requires_grad}, GTOL)
+    w = check_grads_vs_truth(_param_grads(net), {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.requires_grad},
+                             {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.requires_grad}, GTOL)
+    report("unet_light", impl=impl, classes=n_classes, size=list(size), bn=bn, logits_rel_err_vs_fp32=rel_err(y, y_ref),
+           logits_rel_err_vs_fp64=rel_err(y, y64), reference_fp32_vs_fp64=rel_err(y_ref, y64), mask_flips=replay.flips, **w)
     if bn:  # running statistics updated exactly like nn.BatchNorm3d
         for k, v in stats.items():
             assert rel_err(net.state_dict()[k], v) < 1e-4, k
@@ -85,8 +95,9 @@ def test_unet_32base(cuda):
                          {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.requires_grad}, GTOL)
 
 
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("size", [(32, 48, 32), (16, 16, 16), (24, 20, 36)])
-def test_voxelmorph(cuda, size):
+def test_voxelmorph(cuda, size, impl):
     import deepatlas_b200 as da
     from oracle import ref_port as P
     torch.manual_seed(230)
@@ -95,7 +106,7 @@ def test_voxelmorph(cuda, size):
     g = torch.Generator().manual_seed(230)
     s, t = torch.rand((1, 1) + size, generator=g), torch.rand((1, 1) + size, generator=g)
     sd = {k: v.clone().requires_grad_(True) for k, v in cpu_state(net).items()}
-    with MaskRecorder() as rec:
+    with conv_impl(impl), MaskRecorder() as rec:
         out = net(s.to(cuda), t.to(cuda))
     replay = MaskReplay(rec.masks)
     with replay:
@@ -104,34 +115,43 @@ def test_voxelmorph(cuda, size):
         assert a.shape == b.shape
         assert rel_err(a, b) < TOL, f"{name}: rel err {rel_err(a, b):.3e}"
     lncc, bend = da.get_loss_function("lncc")(), da.get_loss_function("bendingEnergy")()
-    (lncc(out[1], t.to(cuda)) + 1000.0 * bend(out[0])).backward()
+    with conv_impl(impl):
+        (lncc(out[1], t.to(cuda)) + 1000.0 * bend(out[0])).backward()
     (P.lncc(ref[1], t) + 1000.0 * P.bending_energy(ref[0])).backward()
     sd64 = {k: v.double().requires_grad_(True) for k, v in cpu_state(net).items()}
     replay.restart()
     with replay:
         r64 = P.voxelmorph_forward(s.double(), t.double(), sd64)
     (P.lncc(r64[1], t.double()) + 1000.0 * P.bending_energy(r64[0])).backward()
-    check_grads_vs_truth(_param_grads(net), {k: v.grad for k, v in sd.items()}, {k: v.grad for k, v in sd64.items()}, GTOL)
+    w = check_grads_vs_truth(_param_grads(net), {k: v.grad for k, v in sd.items()}, {k: v.grad for k, v in sd64.items()}, GTOL)
+    report("voxelmorph", impl=impl, size=list(size), disp_rel_err=rel_err(out[0], ref[0]), warped_rel_err=rel_err(out[1], ref[1]), **w)
 
 
-@pytest.mark.parametrize("C,size", [(4, (16, 16, 16)), (32, (16, 24, 16))])
-def test_joint_step(cuda, C, size):
+# the last case is sized so that the AUTOMATIC selection (what bench.py runs) takes the tcgen05 forward / data-gradient /
+# weight-gradient kernels on the full- and half-resolution levels (>= 65 536 voxels, W >= 20/24) and the tiled FFMA
+# kernels below, i.e. the same mix of kernels as the 160x192x160 benchmark step
+@pytest.mark.parametrize("C,size,impl", [(4, (16, 16, 16), "auto"), (32, (16, 24, 16), "auto"), (4, (16, 16, 16), "umma"),
+                                         (32, (16, 24, 16), "umma"), (8, (64, 64, 128), "auto")])
+def test_joint_step(cuda, C, size, impl):
     from deepatlas_b200.joint import JointModel, make_synthetic_pair
     from oracle import ref_port as P
     torch.manual_seed(230)
     model = JointModel(n_classes=C).to(cuda)
     model.weights_init()
     batch = make_synthetic_pair(size, C, seed=230, device=cuda)
-    with MaskRecorder() as rec:
-        loss, parts = model.joint_loss(*batch)
-    loss.backward()
+    with conv_impl(impl):
+        with MaskRecorder() as rec:
+            loss, parts = model.joint_loss(*batch)
+        loss.backward()
     replay = MaskReplay(rec.masks)
     ref_loss, ref_grads = oracle_joint_loss(model, batch, P, replay=replay)
     true_loss, true_grads = oracle_joint_loss(model, batch, P, dtype=torch.float64, replay=replay)
     assert rel_err(loss, true_loss) < max(TOL, 3 * rel_err(ref_loss, true_loss))
     ours = _param_grads(model)
     assert len(true_grads) >= 60
-    check_grads_vs_truth(ours, ref_grads, true_grads, GTOL)
+    w = check_grads_vs_truth(ours, ref_grads, true_grads, GTOL)
+    report("joint_step", impl=impl, classes=C, size=list(size), loss_rel_err_vs_fp64=rel_err(loss, true_loss),
+           reference_fp32_loss_rel_err=rel_err(ref_loss, true_loss), mask_flips=replay.flips, **w)
 
 
 def test_registry_errors_and_install(built_lib):
