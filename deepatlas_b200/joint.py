@@ -78,3 +78,48 @@ def make_synthetic_pair(size, n_classes, seed=230, device="cpu"):
     S_m = torch.randint(0, n_classes, (1, D, H, W), generator=g, dtype=torch.uint8)
     S_t = torch.randint(0, n_classes, (1, D, H, W), generator=g, dtype=torch.uint8)
     return tuple(t.to(device) for t in (I_m, S_m, I_t, S_t))
+
+
+class RegOnlyModel(nn.Module):
+    """BASELINE.json config #3: registration net + trilinear warp + LNCC + bending energy (no segmentation net).
+    L = l_sim * lncc(I_w, I_t) + l_reg * bendingEnergy(disp); the ingredients are lib/network_factory/voxel_morph.py:62-92
+    and lib/loss.py:589-617,674-730."""
+
+    def __init__(self, lambdas=None):
+        super().__init__()
+        self.reg = get_network("voxel_morph_cvpr")()
+        self.lambdas = dict(DEFAULT_LAMBDAS, **(lambdas or {}))
+        self.sim_loss = get_loss_function("lncc")()
+        self.reg_loss = get_loss_function("bendingEnergy")()
+
+    def weights_init(self):
+        self.reg.weights_init()
+
+    def trainable_parameters(self):
+        return list(self.reg.parameters())
+
+    def joint_loss(self, I_m, S_m, I_t, S_t):
+        disp, I_w, _ = self.reg(I_m, I_t)
+        parts = {"sim": self.sim_loss(I_w, I_t), "reg": self.reg_loss(disp)}
+        return self.lambdas["sim"] * parts["sim"] + self.lambdas["reg"] * parts["reg"], parts
+
+
+class SegOnlyModel(nn.Module):
+    """BASELINE.json configs #1/#2: one segmentation net + supervised Dice (models/segmentation.py:152-157 with
+    train_seg.py:54-55's loss settings); one volume per step."""
+
+    def __init__(self, n_classes=4, in_channel=1, seg_name="UNet"):
+        super().__init__()
+        self.n_classes = n_classes
+        self.seg = get_network(seg_name)(in_channel, n_classes, bias=True, BN=True)
+        self.sup_dice = get_loss_function("dice")(n_class=n_classes, weight_type="Uniform", softmax=True, eps=1e-6)
+
+    def weights_init(self):
+        self.seg.weights_init()
+
+    def trainable_parameters(self):
+        return list(self.seg.parameters())
+
+    def joint_loss(self, I_m, S_m, I_t=None, S_t=None):
+        sup = self.sup_dice(self.seg(I_m), S_m)
+        return sup, {"sup": sup}
