@@ -52,6 +52,7 @@ SIGNATURES = {
     # conv
     "da_umma_debug_read": ("p", "rc"),
     "da_set_conv_impl": ("i", "rc"),
+    "da_set_conv_split": ("i", "rc"),
     "da_conv3d_pack_bytes": ("iii", "size"),
     "da_conv3d_dgrad_workspace_bytes": ("iiiiiiii", "size"),
     "da_conv3d_wgrad_workspace_bytes": ("iii", "size"),

@@ -18,6 +18,8 @@
 //   conv3d_dgrad_s2_kernel<CO>      gather form of the stride-2 transposed conv
 //   conv3d_wgrad_kernel<KS,CI,CO>   lane = voxel along W, register accumulators, butterfly reduce
 //   reduce_partials_kernel          fixed-order second stage (deterministic)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -919,16 +921,26 @@ inline bool umma_enabled() {
   }
   return g_use_umma == 1 && g_force_direct != 2;
 }
-constexpr int64_t UMMA_IMG_BYTES = UmmaCfg::W_BYTES;  // 92160
+constexpr int64_t UMMA_IMG_BYTES = UMMA_IMG_STRIDE_BYTES;  // 92160
+// operand format of the tensor-core kernels: 0 = 3xBF16 (default; products to 2^-17, twice the channels per MMA),
+// 1 = 3xTF32 (products to 2^-21).  da_set_conv_split() or DA_CONV_SPLIT=tf32|bf16 before the first call.
+int g_conv_split = -1;
+inline bool split_tf32() {
+  if (g_conv_split < 0) {
+    const char* e = getenv("DA_CONV_SPLIT");
+    g_conv_split = (e && strcmp(e, "tf32") == 0) ? 1 : 0;
+  }
+  return g_conv_split == 1;
+}
 inline bool fwd_umma_ok(const ConvGeom& g) {
-  // one launch covers a 16 x 16 channel block: below ~50k voxels a launch no longer amortises its fixed cost and the
-  // tiled FFMA kernel (one launch per layer) wins (measured on UNet's 32^3 levels: 768 launches per layer)
+  // one launch covers a block of 16 output channels: below ~50k voxels a launch no longer amortises its fixed cost and
+  // the tiled FFMA kernel (one launch per layer) wins (measured on UNet's 32^3 levels)
   if (g_force_direct == 3) return g.stride == 1 && g.pad == 1;  // tests: tensor-core path whatever the size heuristics say
   return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 &&
          (int64_t)g.Do * g.Ho * g.Wo >= 65536;
 }
 inline int64_t umma_workspace_bytes(int Cin, int Cout) {
-  return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + UM_KC - 1) / UM_KC) * UMMA_IMG_BYTES + 256;
+  return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + 15) / 16) * UMMA_IMG_BYTES + 256;
 }
 
 unsigned long long* g_umma_dbg = nullptr;
@@ -942,21 +954,23 @@ inline unsigned long long* umma_dbg_buffer() {
   return g_umma_dbg;
 }
 
-int launch_umma(const UmmaArgs& a, cudaStream_t stream) {
+template <int MODE>
+int launch_umma_mode(const UmmaArgs& a, cudaStream_t stream) {
   static DaPerDeviceOnce configured;
+  constexpr int SMEM = UmmaCfg<MODE>::SMEM_BYTES;
   if (configured.first()) {
-    cudaFuncSetAttribute(conv3d_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
-    cudaFuncSetAttribute(conv3d_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
-    cudaFuncSetAttribute(conv3d_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
-    cudaFuncSetAttribute(conv3d_umma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UmmaCfg::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_umma_kernel<false, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(conv3d_umma_kernel<false, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(conv3d_umma_kernel<true, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaFuncSetAttribute(conv3d_umma_kernel<true, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
   }
   dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N * a.nco);
   if (a.dbg) {
-    if (a.accumulate) conv3d_umma_kernel<true, true><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
-    else conv3d_umma_kernel<true, false><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+    if (a.accumulate) conv3d_umma_kernel<true, true, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
+    else conv3d_umma_kernel<true, false, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
   } else {
-    if (a.accumulate) conv3d_umma_kernel<false, true><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
-    else conv3d_umma_kernel<false, false><<<grid, UM_THREADS, UmmaCfg::SMEM_BYTES, stream>>>(a);
+    if (a.accumulate) conv3d_umma_kernel<false, true, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
+    else conv3d_umma_kernel<false, false, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
   }
   return da_check_launch("conv3d_umma");
 }
@@ -965,9 +979,14 @@ int launch_umma(const UmmaArgs& a, cudaStream_t stream) {
 int run_conv_umma(const float* x1, const float* x2, const float* weight, float* wp, const float* bias, float* out, const ConvGeom& g,
                   int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
   const int Cin = g.C1 + g.C2;
-  constexpr int CB = UM_CB, KC = UM_KC;
+  constexpr int CB = UM_CB;
+  const bool tf32 = split_tf32();
+  // channel chunks of a launch: 16 as 3xTF32; 32 as 3xBF16, the last one 16 if that covers the remainder
+  const int KC = tf32 ? 16 : 32;
   const int nco = (g.Cout + CB - 1) / CB, nk = (Cin + KC - 1) / KC;
-  umma_prep_weights_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, wp, d1, a_is_dim0, flip, Cin, KC, g.Cout, b_off, CB);
+  const int last_nch = (!tf32 && Cin - (nk - 1) * 32 <= 16) ? 2 : 4;
+  if (tf32) umma_prep_weights_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, wp, d1, a_is_dim0, flip, Cin, KC, g.Cout, b_off, CB);
+  else umma_prep_weights16_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, reinterpret_cast<uint16_t*>(wp), d1, a_is_dim0, flip, Cin, g.Cout, b_off, last_nch);
   int rc = da_check_launch("umma_prep_weights");
   if (rc) return rc;
   UmmaArgs a;
@@ -977,7 +996,6 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, float* 
   a.N = g.N; a.D = g.Do; a.H = g.Ho; a.W = g.Wo; a.Cout = g.Cout;
   a.act = g.act; a.slope = g.slope;
   a.tiles_x = (g.Wo + UM_TX - 1) / UM_TX; a.tiles_y = (g.Ho + UM_TY - 1) / UM_TY;
-  // planes per CTA: enough CTAs for ~4 waves, at least 8 planes to amortise the two-plane pipeline fill
   int zg = g.Do;
   const int xy = a.tiles_x * a.tiles_y * g.N * nco;
   // planes per CTA: minimise waves x (planes per CTA + pipeline fill); one CTA per SM
@@ -998,7 +1016,9 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, float* 
   for (int ik = 0; ik < nk; ++ik) {
     a.wimg = wp + (int64_t)ik * (UMMA_IMG_BYTES / 4);
     a.c0 = ik * KC; a.accumulate = ik > 0; a.last = ik == nk - 1;
-    rc = launch_umma(a, stream);
+    if (tf32) rc = launch_umma_mode<0>(a, stream);
+    else if (ik == nk - 1 && last_nch == 2) rc = launch_umma_mode<2>(a, stream);
+    else rc = launch_umma_mode<1>(a, stream);
     if (rc) return rc;
   }
   return DA_OK;
@@ -1087,6 +1107,11 @@ DA_API int da_umma_debug_read(int64_t* out6) {
 // gradient where they apply), 1 = always the generic direct kernels, 2 = tiled exact-FFMA kernels only (the parity
 // tests cross-check all of them), 3 = tcgen05 forward/dgrad whenever structurally possible (ignores the size heuristics).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
+DA_API int da_set_conv_split(int split) {
+  DA_REQUIRE(split == 0 || split == 1, "da_set_conv_split: split must be 0 (3xBF16) or 1 (3xTF32)");
+  g_conv_split = split;
+  return DA_OK;
+}
 DA_API int da_set_conv_impl(int impl) {
   DA_REQUIRE(impl >= 0 && impl <= 3, "da_set_conv_impl: impl must be 0 (auto), 1 (direct), 2 (tiled FFMA, no tensor cores) or 3 (tensor cores forced)");
   g_force_direct = impl;
@@ -1247,6 +1272,10 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
   if (configured.first()) {
     cudaFuncSetAttribute(conv3d_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WU_SMEM_BYTES);
     cudaFuncSetAttribute(conv3d_wgrad_umma_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WV_SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_wgrad_umma16_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WbCfg<16>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_wgrad_umma16_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WbCfg<32>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_wgrad_umma16_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WbCfg<16>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv3d_wgrad_umma16_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WbCfg<32>::SMEM_BYTES);
   }
   int rc, nregions;
   float* bias_partials = nullptr;  // set when the kernel folds the bias gradient in
@@ -1260,8 +1289,11 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     const float* p1 = transposed ? x1 : dy; const float* p2 = transposed ? x2 : nullptr;
     a.H1 = transposed ? Cout : C1; a.H2 = transposed ? 0 : C2;
     a.P1 = transposed ? C1 : Cout; a.P2 = transposed ? C2 : 0;
-    a.nH1 = (a.H1 + 15) / 16; a.nP1 = (a.P1 + 15) / 16;
-    const int nHB = a.nH1 + (a.H2 + 15) / 16;
+    // 3xBF16 (default): halo-side blocks of 32 channels when a halo tensor has more than 16 (96 of 128 MMA rows useful)
+    const bool bf16 = !split_tf32() && Wi >= WB_XBOX;
+    const int cib = (bf16 && (a.H1 > 16 || a.H2 > 16)) ? 32 : 16;
+    a.nH1 = (a.H1 + cib - 1) / cib; a.nP1 = (a.P1 + 15) / 16;
+    const int nHB = a.nH1 + (a.H2 + cib - 1) / cib;
     a.nPB = a.nP1 + (a.P2 + 15) / 16;
     const int groups = nHB * a.nPB;
     nregions = DA_NUM_SMS / groups;
@@ -1280,13 +1312,31 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     a.partials = partials; a.region_stride = count; a.D = Di; a.tiles_x = tiles_x; a.tiles_y = tiles_y;
     bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
     a.bias_partials = bias_partials;
+    a.dbg = nullptr;
     CUtensorMap mh1, mh2, mp1, mp2;
-    rc = da_make_volume_map(&mh1, h1, N, a.H1, Di, Hi, Wi, 24, 4, 1, 16);
-    if (!rc) rc = a.H2 ? da_make_volume_map(&mh2, h2, N, a.H2, Di, Hi, Wi, 24, 4, 1, 16) : (mh2 = mh1, 0);
-    if (!rc) rc = da_make_volume_map(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 6, 1, 16);
-    if (!rc) rc = a.P2 ? da_make_volume_map(&mp2, p2, N, a.P2, Di, Hi, Wi, 16, 6, 1, 16) : (mp2 = mp1, 0);
-    if (rc) return rc;
-    conv3d_wgrad_umma_tma_kernel<<<dim3(groups, nregions), WU_THREADS, WV_SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+    if (bf16) {
+      rc = da_make_volume_map_xcy(&mh1, h1, N, a.H1, Di, Hi, Wi, WB_XBOX, cib, 4);
+      if (!rc) rc = a.H2 ? da_make_volume_map_xcy(&mh2, h2, N, a.H2, Di, Hi, Wi, WB_XBOX, cib, 4) : (mh2 = mh1, 0);
+      if (!rc) rc = da_make_volume_map_xcy(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 16, 6);
+      if (!rc) rc = a.P2 ? da_make_volume_map_xcy(&mp2, p2, N, a.P2, Di, Hi, Wi, 16, 16, 6) : (mp2 = mp1, 0);
+      if (rc) return rc;
+      a.dbg = umma_dbg_buffer();
+      const dim3 grid(groups, nregions);
+      if (a.dbg) {
+        if (cib == 32) conv3d_wgrad_umma16_kernel<32, true><<<grid, WbCfg<32>::THREADS, WbCfg<32>::SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+        else conv3d_wgrad_umma16_kernel<16, true><<<grid, WbCfg<16>::THREADS, WbCfg<16>::SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+      } else {
+        if (cib == 32) conv3d_wgrad_umma16_kernel<32, false><<<grid, WbCfg<32>::THREADS, WbCfg<32>::SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+        else conv3d_wgrad_umma16_kernel<16, false><<<grid, WbCfg<16>::THREADS, WbCfg<16>::SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+      }
+    } else {
+      rc = da_make_volume_map(&mh1, h1, N, a.H1, Di, Hi, Wi, 24, 4, 1, 16);
+      if (!rc) rc = a.H2 ? da_make_volume_map(&mh2, h2, N, a.H2, Di, Hi, Wi, 24, 4, 1, 16) : (mh2 = mh1, 0);
+      if (!rc) rc = da_make_volume_map(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 6, 1, 16);
+      if (!rc) rc = a.P2 ? da_make_volume_map(&mp2, p2, N, a.P2, Di, Hi, Wi, 16, 6, 1, 16) : (mp2 = mp1, 0);
+      if (rc) return rc;
+      conv3d_wgrad_umma_tma_kernel<<<dim3(groups, nregions), WU_THREADS, WV_SMEM_BYTES, stream>>>(mh1, mh2, mp1, mp2, a);
+    }
     rc = da_check_launch("conv3d_wgrad_umma_tma");
   } else {
     const int ntiles = N * Di * tiles_y * tiles_x;

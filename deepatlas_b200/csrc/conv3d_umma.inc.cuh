@@ -1,5 +1,10 @@
-// Tensor-core (tcgen05, 3xTF32) variant of the k3 s1 p1 convolution forward / data gradient.
-// Included by conv3d.cu inside its anonymous namespace.
+// Tensor-core (tcgen05) variant of the k3 s1 p1 convolution forward / data gradient.  Included by conv3d.cu inside its
+// anonymous namespace.  Three operand formats (template MODE), all with fp32 accumulation in TMEM:
+//   0  3xTF32: kind::tf32, 16 input channels per launch (four 16-byte K chunks of 4 floats), products exact to 2^-21
+//   1  3xBF16: kind::f16 on bf16 hi/lo pairs (x = hi + lo to 2^-17, round-to-nearest), 32 input channels per launch
+//      (four 16-byte K chunks of 8 bf16): same shared-memory bytes, same MMA count and the same ~104 cycles per MMA
+//      as mode 0 (tools/probes/umma16_probe.cu), i.e. twice the channels per MMA
+//   2  3xBF16 with 16 input channels per launch (two K chunks): narrow layers and the remainder of Cin % 32
 //
 // Implicit GEMM, output-stationary in TMEM:
 //   D[f][(kx,co)] = sum_{kz,ky,ci} X[ci][plane zo+kz-1][f + (ky-1)*PX] * W[co][ci][kz][ky][kx]      f = in-plane position
@@ -31,27 +36,33 @@ constexpr int UM_NPROD = 96;                   // producer threads (3 warps): 20
 constexpr int UM_NEPI = 512;                   // epilogue threads: warp w handles TMEM lane quadrant w%4, M tile (w/4)%2, output-channel half w/8
 constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-15 epilogue, 16 MMA issue, 17-19 producers (640 threads)
 constexpr int UM_MMA_WARP = UM_NEPI / 32;
-constexpr int UM_CB = 16, UM_KC = 16;          // output channels per launch, input channels per launch
+constexpr int UM_PF = 3;                       // L2 prefetch distance of the producers, in planes
+constexpr int UM_CB = 16;                      // output channels per launch
 constexpr int UM_NB = 3 * UM_CB;               // columns of one accumulator block: (kx, co)
 constexpr int UM_N = 3 * UM_NB;                // MMA N: three blocks = three output planes in flight
-constexpr int UM_NCH = UM_KC / 4;
 constexpr int UM_WROWS = 5 * UM_NB;            // weight rows: kz blocks in the order 2,1,0,2,1 (any cyclic rotation is contiguous)
 static_assert(UM_MT * 128 + 2 * UM_PX <= UM_PFA, "shifted A rows must stay inside the slot");
 static_assert(UM_MT * UM_MSTEP >= UM_TY * UM_PX, "M tiles must cover the output rows");
 
+template <int MODE>
 struct UmmaCfg {
-  static constexpr int SLOT_FLOATS = 2 * UM_NCH * UM_PFA * 4;        // hi + lo
-  static constexpr int RING_BYTES = 3 * SLOT_FLOATS * 4;
-  static constexpr int W_FLOATS = 2 * 3 * UM_NCH * UM_WROWS * 4;     // [hi|lo][ky][ci/4][row][4]
-  static constexpr int W_BYTES = W_FLOATS * 4;
+  static constexpr bool BF = MODE != 0;
+  static constexpr int EPC = BF ? 8 : 4;                             // input channels per 16-byte K chunk
+  static constexpr int NCH = MODE == 2 ? 2 : 4;                      // K chunks per launch
+  static constexpr int KC = EPC * NCH;                               // input channels per launch: 16, 32, 16
+  static constexpr int SLOT_BYTES = 2 * NCH * UM_PFA * 16;           // hi + lo
+  static constexpr int RING_BYTES = 3 * SLOT_BYTES;
+  static constexpr int W_BYTES = 2 * 3 * NCH * UM_WROWS * 16;        // [hi|lo][ky][ci/EPC][row][16 bytes]
   static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + 128;
   static constexpr int TMEM_COLS = 512;
   static_assert(UM_MT * UM_N <= 512, "accumulators exceed TMEM");
 };
+constexpr int UMMA_IMG_STRIDE_BYTES = UmmaCfg<0>::W_BYTES;  // 92160: every weight image of a layer sits at this pitch
 
 struct UmmaArgs {
   const float* x1; const float* x2; int C1, C2;
   const float* wimg;          // prepared weight image of (co block 0, this channel chunk); block ib is img_stride floats further
+                              // (fp32 hi/lo in mode 0, bf16 hi/lo otherwise)
   int64_t img_stride; int nco; // output-channel blocks of the layer = blockIdx.z % nco
   const float* bias; float* out;
   int N, D, H, W, Cout;
@@ -59,7 +70,7 @@ struct UmmaArgs {
   int accumulate, last;       // add to the existing output; apply bias + activation
   int act; float slope;
   int tiles_x, tiles_y, zg;   // z planes per CTA
-  int flags;                  // debug (DA_UMMA_FLAGS): bit 0 = skip the output stores
+  int flags;                  // debug (DA_UMMA_FLAGS): bit 0 = skip the output stores, bit 1 = no L2 prefetch
   unsigned long long* dbg;    // optional cycle counters of the MMA warp (DA_UMMA_DEBUG=1): acc wait, plane wait, issue, total, steps
 };
 
@@ -82,6 +93,34 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 covers fp16 and bf16 operands (the instruction descriptor says which); K = 16 per instruction
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (BF) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+// instruction descriptor: fp32 accumulate, A and B both K-major, format 2 = tf32 / 1 = bf16, N at bit 17, M at bit 24
+template <bool BF>
+__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
+  const uint32_t fmt = BF ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// x = hi + lo with both halves bf16 (round to nearest): |x - hi - lo| <= 2^-18 |x|.  Packs two values per register,
+// the first in the low half (= the lower K index).
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -120,17 +159,18 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
-template <bool DBG, bool ACC>   // cycle counters (DA_UMMA_DEBUG=1); a.accumulate (further input-channel chunks)
+template <bool DBG, bool ACC, int MODE>   // cycle counters (DA_UMMA_DEBUG=1); a.accumulate (further input-channel chunks); operand format
 __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) {
-  using Cfg = UmmaCfg;
-  constexpr int N = UM_N, NCH = UM_NCH, NB = UM_NB;
+  using Cfg = UmmaCfg<MODE>;
+  constexpr int N = UM_N, NCH = Cfg::NCH, NB = UM_NB;
+  constexpr bool BF = Cfg::BF;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t plane_full[3], plane_empty[3], acc_full[UM_MT], acc_empty[UM_MT];
   __shared__ uint32_t tmem_base_s;
   __shared__ float edge_s[2][8][2][16];  // warp-edge rows of the kx fold (static: keeps LDS/STS addressing)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  float* ring = reinterpret_cast<float*>(smem);
-  float* sw = reinterpret_cast<float*>(smem + Cfg::RING_BYTES);
+  uint8_t* ring = smem;
+  uint8_t* sw = smem + Cfg::RING_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tb = blockIdx.x;
@@ -150,7 +190,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     for (int i = 0; i < UM_MT; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], UM_NEPI / UM_MT); }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < Cfg::W_FLOATS / 4; i += UM_THREADS)
+  for (int i = threadIdx.x; i < Cfg::W_BYTES / 16; i += UM_THREADS)
     reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wimg) + i);
   // rows UM_PLANE .. UM_PFA of every chunk are only read by discarded accumulator rows; zero them once (no NaN patterns)
   for (int i = threadIdx.x; i < 3 * 2 * NCH * (UM_PFA - UM_PLANE); i += UM_THREADS) {
@@ -178,62 +218,144 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 
   if (warp > UM_MMA_WARP) {
     // =============================== producers ===============================
-    // thread = one 4-channel chunk (grp) x PPT fixed in-plane positions: everything but the plane offset is loop
-    // invariant, and all 4*PPT loads of a plane are in flight together (one memory latency per plane)
-    constexpr int TPG = UM_NPROD / NCH;          // 24 threads per channel chunk
-    constexpr int PPT = UM_PLANE / TPG;          // 14 positions per thread
+    // thread = one 16-byte K chunk (grp: 4 channels as tf32, 8 as bf16) x PPT fixed in-plane positions: everything but
+    // the plane offset is loop invariant, and 56 loads per thread are in flight together (one or two memory latencies
+    // per plane)
+    constexpr int TPG = UM_NPROD / NCH;          // 24 (48) threads per channel chunk
+    constexpr int PPT = UM_PLANE / TPG;          // 14 (7) positions per thread
     static_assert(TPG * NCH == UM_NPROD && PPT * TPG == UM_PLANE, "producer mapping must tile the plane exactly");
     const int tp = threadIdx.x - (UM_NEPI + 32);
     const int grp = tp / TPG, ti = tp - grp * TPG;
-    const int cend = min(a.c0 + UM_KC, a.C1 + a.C2);
-    const float* cb[4];
-    bool cok[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = a.c0 + 4 * grp + e;
-      cok[e] = c < cend;
-      cb[e] = !cok[e] ? a.x1 : ((c < a.C1) ? a.x1 + ((int64_t)n * a.C1 + c) * V : a.x2 + ((int64_t)n * a.C2 + (c - a.C1)) * V);
-    }
-    int oxy[PPT];
-#pragma unroll
-    for (int b = 0; b < PPT; ++b) {
-      const int f = ti + TPG * b;
-      const int hy = f / UM_PX, hx = f - hy * UM_PX;
-      const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
-      oxy[b] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? gy * a.W + gx : -1;
-    }
-    for (int pi = 0; pi < nsteps; ++pi) {
-      const int slot = pi % 3, use = pi / 3;
-      if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
-      const int zi = z0 - 1 + pi;
-      float4* shi = reinterpret_cast<float4*>(ring + slot * Cfg::SLOT_FLOATS) + grp * UM_PFA;
-      float4* slo = shi + NCH * UM_PFA;
-      const bool zok = zi >= 0 && zi < a.D;
-      const int64_t zoff = (int64_t)zi * HW;
-      float v[PPT][4];
-#pragma unroll
-      for (int b = 0; b < PPT; ++b)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) v[b][e] = (zok && oxy[b] >= 0 && cok[e]) ? __ldg(cb[e] + zoff + oxy[b]) : 0.f;
+    const int cend = min(a.c0 + Cfg::KC, a.C1 + a.C2);
+    // The staged loads are latency bound (56 loads per thread, one DRAM round trip per batch): pull the row segments
+    // of the plane UM_PF steps ahead into L2 now, so that the loads proper find them there.  One task = one
+    // (channel, row) segment of 42 floats = at most three 128-byte lines.
+    const float* const pf1 = a.x1 + (int64_t)n * a.C1 * V;                                         // channel c <  C1: pf1 + c*V
+    const float* const pf2 = a.x2 ? a.x2 + ((int64_t)n * a.C2 - a.C1) * V : a.x1;                  // channel c >= C1: pf2 + c*V
+    auto prefetch_plane = [&](int zi) {
+      if ((a.flags & 2) || zi < 0 || zi >= a.D) return;
+      int tpv;   // opaque copy: keeps the per-task addresses from being hoisted out of the plane loop (registers)
+      asm volatile("mov.u32 %0, %1;" : "=r"(tpv) : "r"(tp));
+      const int xa = max(X0 - 1, 0), xb = min(X0 + UM_TX, a.W - 1);
+#pragma unroll 1
+      for (int t = tpv; t < Cfg::KC * (UM_TY + 2); t += UM_NPROD) {
+        const int c = a.c0 + t / (UM_TY + 2), gy = Y0 - 1 + t % (UM_TY + 2);
+        if (c >= cend || gy < 0 || gy >= a.H) continue;
+        const float* row = (c < a.C1 ? pf1 : pf2) + (int64_t)c * V + (int64_t)zi * HW + gy * a.W;
+        prefetch_l2(row + xa);
+        prefetch_l2(row + min(xa + 32, xb));
+        prefetch_l2(row + xb);
+      }
+    };
+    prefetch_plane(z0 - 1 + 1);
+    prefetch_plane(z0 - 1 + 2);
+    if constexpr (!BF) {
+      int oxy[PPT];
 #pragma unroll
       for (int b = 0; b < PPT; ++b) {
-        float h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          h[e] = __uint_as_float(__float_as_uint(v[b][e]) & 0xffffe000u);
-          l[e] = v[b][e] - h[e];
-        }
-        shi[ti + TPG * b] = make_float4(h[0], h[1], h[2], h[3]);
-        slo[ti + TPG * b] = make_float4(l[0], l[1], l[2], l[3]);
+        const int f = ti + TPG * b;
+        const int hy = f / UM_PX, hx = f - hy * UM_PX;
+        const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
+        oxy[b] = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) ? gy * a.W + gx : -1;
       }
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      mbar_arrive(&plane_full[slot]);
+      const float* cb[4];
+      bool cok[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = a.c0 + 4 * grp + e;
+        cok[e] = c < cend;
+        cb[e] = !cok[e] ? a.x1 : ((c < a.C1) ? a.x1 + ((int64_t)n * a.C1 + c) * V : a.x2 + ((int64_t)n * a.C2 + (c - a.C1)) * V);
+      }
+      for (int pi = 0; pi < nsteps; ++pi) {
+        const int slot = pi % 3, use = pi / 3;
+        if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
+        const int zi = z0 - 1 + pi;
+        if (pi + UM_PF < nsteps) prefetch_plane(zi + UM_PF);
+        float4* shi = reinterpret_cast<float4*>(ring + slot * Cfg::SLOT_BYTES) + grp * UM_PFA;
+        float4* slo = shi + NCH * UM_PFA;
+        const bool zok = zi >= 0 && zi < a.D;
+        const int64_t zoff = (int64_t)zi * HW;
+        float v[PPT][4];
+#pragma unroll
+        for (int b = 0; b < PPT; ++b)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[b][e] = (zok && oxy[b] >= 0 && cok[e]) ? __ldg(cb[e] + zoff + oxy[b]) : 0.f;
+#pragma unroll
+        for (int b = 0; b < PPT; ++b) {
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = __uint_as_float(__float_as_uint(v[b][e]) & 0xffffe000u);
+            l[e] = v[b][e] - h[e];
+          }
+          shi[ti + TPG * b] = make_float4(h[0], h[1], h[2], h[3]);
+          slo[ti + TPG * b] = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&plane_full[slot]);
+      }
+    } else {
+      // eight channels per chunk: channel e of the chunk lives at b1 + e*V while e < esplit (first source) and at
+      // b2 + e*V beyond (second source of a concatenation; b2 is biased by -esplit*V), e >= nv is zero padding
+      const int cg0 = a.c0 + 8 * grp;
+      const int nv = max(0, min(8, cend - cg0));
+      const float* b1; const float* b2; int esplit;
+      if (cg0 >= a.C1) {
+        b1 = a.x2 ? a.x2 + ((int64_t)n * a.C2 + (cg0 - a.C1)) * V : a.x1; esplit = 8; b2 = b1;
+      } else {
+        b1 = a.x1 + ((int64_t)n * a.C1 + cg0) * V; esplit = min(8, a.C1 - cg0);
+        b2 = a.x2 ? a.x2 + (int64_t)n * a.C2 * V - (int64_t)esplit * V : b1;
+      }
+      constexpr int BATCH = 7, NBATCH = PPT / BATCH;   // 56 loads in flight per thread
+      static_assert(NBATCH * BATCH == PPT, "load batches must tile the thread's positions");
+      const int Vi = (int)V;   // 8 * V < 2^31 (checked by the host): 32-bit element offsets, no per-channel pointers
+      for (int pi = 0; pi < nsteps; ++pi) {
+        const int slot = pi % 3, use = pi / 3;
+        if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
+        const int zi = z0 - 1 + pi;
+        if (pi + UM_PF < nsteps) prefetch_plane(zi + UM_PF);
+        uint4* shi = reinterpret_cast<uint4*>(ring + slot * Cfg::SLOT_BYTES) + grp * UM_PFA;
+        uint4* slo = shi + NCH * UM_PFA;
+        const bool zok = zi >= 0 && zi < a.D;
+        const float* p1 = b1 + (int64_t)zi * HW;
+        const float* p2 = b2 + (int64_t)zi * HW;
+        // the in-plane offsets are recomputed per plane (14 registers would otherwise be pinned for the whole walk and
+        // the kernel spills); the volatile move keeps the compiler from hoisting them back out of the loop
+        int tiv;
+        asm volatile("mov.u32 %0, %1;" : "=r"(tiv) : "r"(ti));
+#pragma unroll
+        for (int q = 0; q < NBATCH; ++q) {
+          float v[BATCH][8];
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            const int f = tiv + TPG * (q * BATCH + b);
+            const int hy = f / UM_PX, hx = f - hy * UM_PX;
+            const int gy = Y0 - 1 + hy, gx = X0 - 1 + hx;
+            const bool ok = zok && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+            const int o = gy * a.W + gx;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[b][e] = (ok && e < nv) ? __ldg((e < esplit ? p1 : p2) + (e * Vi + o)) : 0.f;
+          }
+#pragma unroll
+          for (int b = 0; b < BATCH; ++b) {
+            uint4 h, l;
+            split_bf16x2(v[b][0], v[b][1], h.x, l.x);
+            split_bf16x2(v[b][2], v[b][3], h.y, l.y);
+            split_bf16x2(v[b][4], v[b][5], h.z, l.z);
+            split_bf16x2(v[b][6], v[b][7], h.w, l.w);
+            shi[ti + TPG * (q * BATCH + b)] = h;
+            slo[ti + TPG * (q * BATCH + b)] = l;
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&plane_full[slot]);
+      }
     }
   } else if (warp == UM_MMA_WARP) {
     // =============================== MMA issue ===============================
     uint32_t elected;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(elected));
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = umma_idesc<BF>(128, N);
     const uint32_t ring_s = smem_u32(ring), sw_s = smem_u32(sw);
     constexpr uint32_t A_LBO = UM_PFA * 16, B_LBO = UM_WROWS * 16;
     const uint64_t adesc0 = umma_desc(0, A_LBO, 128), bdesc0 = umma_desc(0, B_LBO, 128);
@@ -244,7 +366,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       mbar_wait(&plane_full[pi % 3], (pi / 3) & 1);
       const long long t1 = DBG ? clock64() : 0;
       t_plane += t1 - t0;
-      const uint32_t slot_s = ring_s + (uint32_t)(pi % 3) * (Cfg::SLOT_FLOATS * 4);
+      const uint32_t slot_s = ring_s + (uint32_t)(pi % 3) * Cfg::SLOT_BYTES;
       const uint32_t brot = sw_s + (uint32_t)(2 - pi % 3) * (NB * 16);  // block b of this step holds kz = (pi - b) mod 3
 #pragma unroll 1
       for (int mt = 0; mt < UM_MT; ++mt) {
@@ -259,14 +381,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
             const uint32_t arow = slot_s + (uint32_t)(mt * UM_MSTEP + ky * UM_PX) * 16;  // (PX + mt*MSTEP) + (ky-1)*PX
             const uint32_t wt = brot + (uint32_t)(ky * NCH * UM_WROWS) * 16;
 #pragma unroll
-            for (int j2 = 0; j2 < UM_KC / 8; ++j2) {
+            for (int j2 = 0; j2 < NCH / 2; ++j2) {   // one instruction contracts two K chunks (8 tf32 / 16 bf16 channels)
               const uint64_t a_hi = umma_desc_at(adesc0, arow + (uint32_t)(2 * j2) * A_LBO);
               const uint64_t a_lo = umma_desc_at(adesc0, arow + (uint32_t)(2 * j2) * A_LBO + NCH * UM_PFA * 16);
               const uint64_t b_hi = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO);
               const uint64_t b_lo = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO + 3 * NCH * UM_WROWS * 16);
-              umma_tf32(dcol, a_hi, b_hi, idesc, 1u);
-              umma_tf32(dcol, a_lo, b_hi, idesc, 1u);
-              umma_tf32(dcol, a_hi, b_lo, idesc, 1u);
+              umma_ss<BF>(dcol, a_hi, b_hi, idesc, 1u);
+              umma_ss<BF>(dcol, a_lo, b_hi, idesc, 1u);
+              umma_ss<BF>(dcol, a_hi, b_lo, idesc, 1u);
             }
           }
           umma_commit(&acc_full[mt]);
@@ -419,8 +541,9 @@ __global__ void umma_prep_weights_kernel(const float* __restrict__ src, float* _
   // grid (blocks, channel chunks, output-channel blocks): all images of a layer in one launch, image (ib, ik) at
   // dst + (ib * nk + ik) * W_FLOATS
   const int c0 = blockIdx.y * kc, co0 = blockIdx.z * cb;
-  dst += (int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * UmmaCfg::W_FLOATS;
-  const int total = UmmaCfg::W_FLOATS;
+  dst += (int64_t)(blockIdx.z * gridDim.y + blockIdx.y) * (UMMA_IMG_STRIDE_BYTES / 4);
+  constexpr int UM_NCH = UmmaCfg<0>::NCH, UM_KC = UmmaCfg<0>::KC;
+  const int total = UmmaCfg<0>::W_BYTES / 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int e = i & 3;
     int r = i >> 2;
@@ -440,5 +563,37 @@ __global__ void umma_prep_weights_kernel(const float* __restrict__ src, float* _
     }
     const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     dst[i] = s ? (v - hi) : hi;
+  }
+}
+
+// bf16 hi/lo weight image of one (16-output-channel block, 32-input-channel chunk; the last chunk of a layer may be a
+// 16-channel one, last_nch = 2):  [hi|lo][ky][ci/8][row = t*48 + kx*16 + co][8 bf16], image (ib, ik) at
+// dst + (ib * nk + ik) * UMMA_IMG_STRIDE_BYTES.  Chunk ik starts at input channel 32 * ik.
+__global__ void umma_prep_weights16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int d1, int a_is_dim0, int flip,
+                                           int A, int B, int b_off, int last_nch) {
+  const int ik = blockIdx.y, c0 = ik * 32, co0 = blockIdx.z * UM_CB;
+  const int nch = (ik == (int)gridDim.y - 1) ? last_nch : 4;
+  dst += (int64_t)(blockIdx.z * gridDim.y + ik) * (UMMA_IMG_STRIDE_BYTES / 2);
+  const int half = 3 * nch * UM_WROWS * 8;   // elements of the hi (or lo) part
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x) {
+    const int e = i & 7;
+    int r = i >> 3;
+    const int row = r % UM_WROWS; r /= UM_WROWS;
+    const int j = r % nch;
+    const int ky = r / nch;
+    const int t = row / UM_NB, kx = (row % UM_NB) / UM_CB, b = co0 + row % UM_CB, ai = c0 + 8 * j + e;
+    const int kz = (t == 0 || t == 3) ? 2 : ((t == 1 || t == 4) ? 1 : 0);
+    float v = 0.f;
+    if (ai < A && b < B) {
+      const int tap = (kz * 3 + ky) * 3 + kx;
+      const int ts = flip ? (26 - tap) : tap;
+      const int i0 = a_is_dim0 ? ai : (b + b_off);
+      const int i1 = a_is_dim0 ? (b + b_off) : ai;
+      v = src[((int64_t)i0 * d1 + i1) * 27 + ts];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    dst[i] = *reinterpret_cast<const uint16_t*>(&hi);
+    dst[half + i] = *reinterpret_cast<const uint16_t*>(&lo);
   }
 }

@@ -83,3 +83,19 @@ inline int da_make_volume_map(CUtensorMap* map, const float* base, int N, int C,
   if (r != CUDA_SUCCESS) { da_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DA_ERR_UNSUPPORTED; }
   return DA_OK;
 }
+
+// The same volume with the channel dimension second: map dims {W, C, H, D, N}, box {bx, bc, by, 1, 1}, coordinates
+// (x, c, y, z, n).  The box lands in shared memory as [by rows][bc channels][bx] -- threads whose lanes run along
+// channels then read it with a pitch of bx floats instead of by*bx.
+inline int da_make_volume_map_xcy(CUtensorMap* map, const float* base, int N, int C, int D, int H, int W, int bx, int bc, int by) {
+  da_encode_tiled_fn enc = da_get_encode_tiled();
+  if (!enc) { da_set_error("cuTensorMapEncodeTiled unavailable"); return DA_ERR_UNSUPPORTED; }
+  cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t strides[4] = {(cuuint64_t)W * H * D * 4, (cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * D * C * 4};
+  cuuint32_t box[5] = {(cuuint32_t)bx, (cuuint32_t)bc, (cuuint32_t)by, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { da_set_error("cuTensorMapEncodeTiled (x, c, y order) failed (%d)", (int)r); return DA_ERR_UNSUPPORTED; }
+  return DA_OK;
+}

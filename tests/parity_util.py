@@ -25,13 +25,31 @@ def report(test, **metrics):
 @contextlib.contextmanager
 def conv_impl(name):
     """Selects the k3 convolution kernels for the enclosed CUDA calls: 'auto' (size heuristics, what a user gets),
-    'umma' (tcgen05 forward / data gradient / weight gradient wherever structurally possible), 'ffma', 'direct'."""
+    'umma' (tcgen05 forward / data gradient / weight gradient wherever structurally possible, default 3xBF16 operands),
+    'umma_tf32' (the same kernels with 3xTF32 operands), 'ffma', 'direct'."""
     from deepatlas_b200 import _lib
-    _lib.call("da_set_conv_impl", {"auto": 0, "direct": 1, "ffma": 2, "umma": 3}[name])
+    _lib.call("da_set_conv_impl", CONV_IMPLS[name][0])
+    _lib.call("da_set_conv_split", CONV_IMPLS[name][1])
     try:
         yield
     finally:
         _lib.call("da_set_conv_impl", 0)
+        _lib.call("da_set_conv_split", 0)
+
+
+# Width of the band around zero (relative to max|pre-activation| of the layer) inside which the CUDA path and the oracle
+# may take different activation branches.  The exact-FFMA and 3xTF32 kernels differ from ATen by fp32 summation order
+# only (2e-5 after a dozen layers with batch-1 BatchNorm); the default 3xBF16 tensor path carries products to 2^-17, so
+# its forward error -- asserted separately to stay below the 1e-4 north-star tolerance -- is what sets the band there.
+MASK_BAND = {"auto": 1e-4, "umma": 1e-4, "umma_tf32": 2e-5, "ffma": 2e-5, "direct": 2e-5}
+
+
+def max_flips(replay):
+    """Allowed number of activation-mask flips: a fixed floor plus the share of elements expected inside the band."""
+    return 64 + int(4 * replay.eps * replay.count)
+
+
+CONV_IMPLS = {"auto": (0, 0), "direct": (1, 0), "ffma": (2, 0), "umma": (3, 0), "umma_tf32": (3, 1)}
 
 
 def rel_err(a, b):
@@ -151,7 +169,7 @@ class MaskReplay:
     elements whose oracle sign differed; each must have |pre-activation| <= eps * max|pre-activation|."""
 
     def __init__(self, masks, eps=2e-5):
-        self.masks, self.eps, self.flips, self._i = masks, eps, 0, 0
+        self.masks, self.eps, self.flips, self.count, self._i = masks, eps, 0, 0, 0
 
     def restart(self):
         self._i = 0
@@ -166,6 +184,7 @@ class MaskReplay:
             assert m.shape == x.shape, f"activation {self._i - 1}: recorded {tuple(m.shape)} vs oracle {tuple(x.shape)}"
             diff = m != (x.detach() > 0)
             n = int(diff.sum())
+            self.count += m.numel()
             if n:
                 worst = float(x.detach()[diff].abs().max()) / max(float(x.detach().abs().max()), 1e-30)
                 assert worst <= self.eps, f"activation {self._i - 1}: mask differs at |z|/max|z| = {worst:.2e} (not round-off)"

@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from parity_util import rel_err, rel_err_quantile
+from parity_util import conv_impl, rel_err, rel_err_quantile
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -188,15 +188,22 @@ CONV_CASES = [
     (64, 64, 64, 3, 1, (20, 24, 20), False),    # deepest decoder level of UNet_light at the benchmark size
     (16, 0, 32, 3, 1, (32, 32, 40), False),     # 32-channel output blocks (tensor-core path: CB = 32, KC = 8)
     (24, 0, 48, 3, 1, (30, 33, 44), False),     # ragged everything: partial channel chunk / block, odd extents
+    (12, 9, 16, 3, 1, (16, 20, 24), False),     # the concatenation boundary falls inside an 8-channel K chunk of the bf16 tensor path
+    (35, 30, 20, 3, 1, (12, 12, 24), False),    # 65 input channels: two 32-channel launches + a 16-channel one holding a single channel
+    (96, 0, 32, 3, 1, (8, 12, 40), False),      # three full 32-channel launches accumulate through the output
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", ["auto", "direct", "ffma", "umma"])
+@pytest.mark.parametrize("impl", ["auto", "direct", "ffma", "umma", "umma_tf32"])
 @pytest.mark.parametrize("slope", [None, 0.0])
 def test_conv3d(cuda, case, impl, slope):
     from deepatlas_b200 import _lib, ops
     C1, C2, Cout, ks, stride, size, transposed = case
+    # activation-mask flips: a pre-activation within the kernel's round-off of zero may land on either side.  The exact
+    # FFMA / 3xTF32 kernels differ from ATen by fp32 summation order only; the 3xBF16 tensor path carries products to
+    # 2^-17, so its round-off band (and hence the number of voxels inside it) is wider
+    band, max_flips = (4e-5, 256) if impl in ("auto", "umma") else (1e-5, 4)
     if impl not in ("auto", "umma") and slope is not None:
         pytest.skip("activation epilogue covered by the auto run")
     g = _g()
@@ -223,7 +230,7 @@ def test_conv3d(cuda, case, impl, slope):
         flipped = pos != mask_box["gpu_pos"]
         mask_box["flipped"] = int(flipped.sum())
         if mask_box["flipped"]:
-            assert float(y.detach()[flipped].abs().max()) < 1e-5 * float(y.detach().abs().max()), "mask differs away from zero"
+            assert float(y.detach()[flipped].abs().max()) < band * float(y.detach().abs().max()), "mask differs away from zero"
         return torch.where(mask_box["gpu_pos"], y, y * slope)
 
     def gpu(*a):
@@ -232,17 +239,14 @@ def test_conv3d(cuda, case, impl, slope):
         mask_box["gpu_pos"] = out.detach().cpu() > 0
         return out
 
-    if impl == "umma" and (ks != 3 or stride != 1):
+    if impl.startswith("umma") and (ks != 3 or stride != 1):
         pytest.skip("tensor-core path covers k3 s1 p1")
     ins = [x1] + ([x2] if C2 else []) + [w, b]
-    _lib.call("da_set_conv_impl", {"auto": 0, "direct": 1, "ffma": 2, "umma": 3}[impl])
-    try:
+    with conv_impl(impl):
         res = _run_both(gpu, cpu, ins, cuda)
-    finally:
-        _lib.call("da_set_conv_impl", 0)
     _check(*res, what=f"conv3d {case} {impl} slope={slope}")
     if slope is not None:
-        assert mask_box["flipped"] <= 4, f"{mask_box['flipped']} activation-mask flips"
+        assert mask_box["flipped"] <= max_flips, f"{mask_box['flipped']} activation-mask flips"
 
 
 @pytest.mark.parametrize("slope", [0.01, 0.0, None])

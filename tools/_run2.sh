@@ -1,0 +1,6 @@
+set -x
+python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "test_conv3d" 2>&1 | tail -15
+for sh in 16,0,16,160,192,160 32,16,16,160,192,160 32,0,32,80,96,80 64,32,32,80,96,80 64,64,64,40,48,40; do
+  DA_UMMA_DEBUG=1 DA_SHAPE=$sh python tools/profile_conv.py
+  DA_CONV_SPLIT=tf32 DA_SHAPE=$sh python tools/profile_conv.py
+done
