@@ -18,7 +18,7 @@
 //   conv3d_dgrad_s2_kernel<CO>      gather form of the stride-2 transposed conv
 //   conv3d_wgrad_kernel<KS,CI,CO>   lane = voxel along W, register accumulators, butterfly reduce
 //   reduce_partials_kernel          fixed-order second stage (deterministic)
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -922,8 +922,9 @@ inline bool umma_enabled() {
   return g_use_umma == 1 && g_force_direct != 2;
 }
 constexpr int64_t UMMA_IMG_BYTES = UMMA_IMG_STRIDE_BYTES;  // 92160
-// operand format of the tensor-core kernels: 0 = 3xBF16 (default; products to 2^-17, twice the channels per MMA),
-// 1 = 3xTF32 (products to 2^-21).  da_set_conv_split() or DA_CONV_SPLIT=tf32|bf16 before the first call.
+// operand format of the tensor-core kernels: 0 = 3xFP16 (default: fp16 hi/lo pairs of per-tensor scaled operands, 22
+// significant bits, twice the channels per MMA), 1 = 3xTF32.  da_set_conv_split() or DA_CONV_SPLIT=tf32|fp16 before
+// the first call.
 int g_conv_split = -1;
 inline bool split_tf32() {
   if (g_conv_split < 0) {
@@ -940,7 +941,22 @@ inline bool fwd_umma_ok(const ConvGeom& g) {
          (int64_t)g.Do * g.Ho * g.Wo >= 65536;
 }
 inline int64_t umma_workspace_bytes(int Cin, int Cout) {
-  return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + 15) / 16) * UMMA_IMG_BYTES + 256;
+  return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + 15) / 16) * UMMA_IMG_BYTES + 256;   // + the max-abs slots
+}
+// max|.| of up to four device arrays (null = absent) into out[slot] (out: 4 floats, zeroed here); one memset + one kernel
+int run_absmax(const float* p0, int64_t n0, int s0, const float* p1, int64_t n1, int s1, const float* p2, int64_t n2, int s2,
+               const float* p3, int64_t n3, int s3, float* out, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out, 0, 4 * sizeof(float), stream);
+  if (e != cudaSuccess) { da_set_error("absmax: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+  AbsmaxArgs a;
+  a.p[0] = p0; a.n[0] = p0 ? n0 : 0; a.slot[0] = s0; a.p[1] = p1; a.n[1] = p1 ? n1 : 0; a.slot[1] = s1;
+  a.p[2] = p2; a.n[2] = p2 ? n2 : 0; a.slot[2] = s2; a.p[3] = p3; a.n[3] = p3 ? n3 : 0; a.slot[3] = s3;
+  const int64_t total = a.n[0] + a.n[1] + a.n[2] + a.n[3];
+  int64_t nb = da_cdiv(total, 256 * 16);
+  if (nb > 8 * DA_NUM_SMS) nb = 8 * DA_NUM_SMS;
+  if (nb < 1) nb = 1;
+  absmax_kernel<<<(unsigned)nb, 256, 0, stream>>>(a, out);
+  return da_check_launch("absmax");
 }
 
 unsigned long long* g_umma_dbg = nullptr;
@@ -976,8 +992,8 @@ int launch_umma_mode(const UmmaArgs& a, cudaStream_t stream) {
 }
 
 // weight source indexing arguments as for repack(); wp must hold umma_workspace_bytes(Cin, Cout)
-int run_conv_umma(const float* x1, const float* x2, const float* weight, float* wp, const float* bias, float* out, const ConvGeom& g,
-                  int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
+int run_conv_umma(const float* x1, const float* x2, const float* weight, int64_t wcount, float* wp, const float* bias, float* out,
+                  const ConvGeom& g, int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
   const int Cin = g.C1 + g.C2;
   constexpr int CB = UM_CB;
   const bool tf32 = split_tf32();
@@ -985,11 +1001,22 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, float* 
   const int KC = tf32 ? 16 : 32;
   const int nco = (g.Cout + CB - 1) / CB, nk = (Cin + KC - 1) / KC;
   const int last_nch = (!tf32 && Cin - (nk - 1) * 32 <= 16) ? 2 : 4;
-  if (tf32) umma_prep_weights_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, wp, d1, a_is_dim0, flip, Cin, KC, g.Cout, b_off, CB);
-  else umma_prep_weights16_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, reinterpret_cast<uint16_t*>(wp), d1, a_is_dim0, flip, Cin, g.Cout, b_off, last_nch);
-  int rc = da_check_launch("umma_prep_weights");
+  float* amax = reinterpret_cast<float*>(reinterpret_cast<char*>(wp) + (int64_t)nco * nk * UMMA_IMG_BYTES);   // 4 floats at the end of the images
+  int rc;
+  if (tf32) {
+    umma_prep_weights_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, wp, d1, a_is_dim0, flip, Cin, KC, g.Cout, b_off, CB);
+  } else {
+    // 3xFP16: per-tensor power-of-two scales from max|input| (both sources) and max|weight| (the whole tensor: every
+    // output-channel block and a data gradient's channel slice share one scale)
+    const int64_t V = (int64_t)g.Di * g.Hi * g.Wi;
+    rc = run_absmax(x1, (int64_t)g.N * g.C1 * V, 0, x2, (int64_t)g.N * g.C2 * V, 0, weight, wcount, 1, nullptr, 0, 0, amax, stream);
+    if (rc) return rc;
+    umma_prep_weights16_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, reinterpret_cast<uint16_t*>(wp), d1, a_is_dim0, flip, Cin, g.Cout, b_off, last_nch, amax);
+  }
+  rc = da_check_launch("umma_prep_weights");
   if (rc) return rc;
   UmmaArgs a;
+  a.amax = amax;
   a.dbg = umma_dbg_buffer();
   { static int fl = -1; if (fl < 0) { const char* e = getenv("DA_UMMA_FLAGS"); fl = e ? atoi(e) : 0; } a.flags = fl; }
   a.x1 = x1; a.x2 = x2; a.C1 = g.C1; a.C2 = g.C2; a.bias = bias; a.out = out;
@@ -1108,7 +1135,7 @@ DA_API int da_umma_debug_read(int64_t* out6) {
 // tests cross-check all of them), 3 = tcgen05 forward/dgrad whenever structurally possible (ignores the size heuristics).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
 DA_API int da_set_conv_split(int split) {
-  DA_REQUIRE(split == 0 || split == 1, "da_set_conv_split: split must be 0 (3xBF16) or 1 (3xTF32)");
+  DA_REQUIRE(split == 0 || split == 1, "da_set_conv_split: split must be 0 (3xFP16) or 1 (3xTF32)");
   g_conv_split = split;
   return DA_OK;
 }
@@ -1158,8 +1185,8 @@ DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const
     if (rc1 >= 0) return rc1;
   }
   if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
-    return transposed ? run_conv_umma(x1, x2, weight, wp, bias, out, g, Cout, 1, 1, 0, stream)
-                      : run_conv_umma(x1, x2, weight, wp, bias, out, g, Cin, 0, 0, 0, stream);
+    return transposed ? run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cout, 1, 1, 0, stream)
+                      : run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cin, 0, 0, 0, stream);
   if (ks == 3 && aligned16(wp) && fwd_tma_ok(x1, x2, out, g))
     return transposed ? run_conv_tma(x1, x2, weight, wp, bias, out, g, Cin, Cout, 1, 1, 0, stream)
                       : run_conv_tma(x1, x2, weight, wp, bias, out, g, Cout, Cin, 0, 0, 0, stream);
@@ -1215,8 +1242,8 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
       if (rc1 >= 0) return rc1;
     }
     if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
-      return transposed ? run_conv_umma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, 0, 0, ci_off, stream)
-                        : run_conv_umma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
+      return transposed ? run_conv_umma(dy, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cout, 0, 0, ci_off, stream)
+                        : run_conv_umma(dy, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
     if (ks == 3 && aligned16(wp) && fwd_tma_ok(dy, nullptr, dx, g))
       return transposed ? run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, Cout, 0, 0, ci_off, stream)
                         : run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, Cin_total, 1, 1, ci_off, stream);
@@ -1240,7 +1267,7 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
       zero_insert2_kernel<<<(unsigned)nb, 256, 0, stream>>>(dy, dyz, (int64_t)N * Cout, Do, Ho, Wo);
       int rc = da_check_launch("conv3d_dgrad_s2/zero_insert");
       if (rc) return rc;
-      return run_conv_umma(dyz, nullptr, weight, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
+      return run_conv_umma(dyz, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
     }
   }
   int rc = repack(weight, wp, Cout, Cin_total, T, 1, 0, Cout, 0, Cdx, ci_off, Cp, stream);
@@ -1289,7 +1316,7 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     const float* p1 = transposed ? x1 : dy; const float* p2 = transposed ? x2 : nullptr;
     a.H1 = transposed ? Cout : C1; a.H2 = transposed ? 0 : C2;
     a.P1 = transposed ? C1 : Cout; a.P2 = transposed ? C2 : 0;
-    // 3xBF16 (default): halo-side blocks of 32 channels when a halo tensor has more than 16 (96 of 128 MMA rows useful)
+    // 3xFP16 (default): halo-side blocks of 32 channels when a halo tensor has more than 16 (96 of 128 MMA rows useful)
     const bool bf16 = !split_tf32() && Wi >= WB_XBOX;
     const int cib = (bf16 && (a.H1 > 16 || a.H2 > 16)) ? 32 : 16;
     a.nH1 = (a.H1 + cib - 1) / cib; a.nP1 = (a.P1 + 15) / 16;
@@ -1315,6 +1342,13 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     a.dbg = nullptr;
     CUtensorMap mh1, mh2, mp1, mp2;
     if (bf16) {
+      // per-tensor scales: slot 0 = halo-side tensors, slot 1 = plain-side tensors; the slots sit behind the partials
+      float* amax = partials + (int64_t)cap * count + (int64_t)WG_MAX_REGIONS * (Cin > Cout ? Cin : Cout);
+      const int64_t V = (int64_t)Di * Hi * Wi;
+      rc = run_absmax(h1, (int64_t)N * a.H1 * V, 0, h2, (int64_t)N * a.H2 * V, 0, p1, (int64_t)N * a.P1 * V, 1, p2, (int64_t)N * a.P2 * V, 1, amax,
+                      stream);
+      if (rc) return rc;
+      a.amax = amax;
       rc = da_make_volume_map_xcy(&mh1, h1, N, a.H1, Di, Hi, Wi, WB_XBOX, cib, 4);
       if (!rc) rc = a.H2 ? da_make_volume_map_xcy(&mh2, h2, N, a.H2, Di, Hi, Wi, WB_XBOX, cib, 4) : (mh2 = mh1, 0);
       if (!rc) rc = da_make_volume_map_xcy(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 16, 6);

@@ -1,10 +1,14 @@
 // Tensor-core (tcgen05) variant of the k3 s1 p1 convolution forward / data gradient.  Included by conv3d.cu inside its
 // anonymous namespace.  Three operand formats (template MODE), all with fp32 accumulation in TMEM:
 //   0  3xTF32: kind::tf32, 16 input channels per launch (four 16-byte K chunks of 4 floats), products exact to 2^-21
-//   1  3xBF16: kind::f16 on bf16 hi/lo pairs (x = hi + lo to 2^-17, round-to-nearest), 32 input channels per launch
-//      (four 16-byte K chunks of 8 bf16): same shared-memory bytes, same MMA count and the same ~104 cycles per MMA
-//      as mode 0 (tools/probes/umma16_probe.cu), i.e. twice the channels per MMA
-//   2  3xBF16 with 16 input channels per launch (two K chunks): narrow layers and the remainder of Cin % 32
+//   1  3xFP16: kind::f16 on fp16 hi/lo pairs of the operands scaled by a power of two (per tensor, from its max-abs:
+//      max|x| * 2^k in [2^13, 2^14), so hi + lo carries 22 significant bits for everything within 2^17 of the maximum
+//      and an absolute error below 2^-39 max|x| beneath that -- the accuracy class of 3xTF32, measured against fp64
+//      in the parity tests), 32 input channels per launch (four 16-byte K chunks of 8 halves): same shared-memory
+//      bytes, same MMA count and the same ~104 cycles per MMA as mode 0 (tools/probes/umma16_probe.cu), i.e. twice
+//      the channels per MMA.  (bf16 pairs need no scaling but carry 16 bits: weight gradients of the first layers
+//      came out 1e-2 off the fp64 oracle, against 1e-4 for 3xTF32 -- measured, rejected.)
+//   2  3xFP16 with 16 input channels per launch (two K chunks): narrow layers and the remainder of Cin % 32
 //
 // Implicit GEMM, output-stationary in TMEM:
 //   D[f][(kx,co)] = sum_{kz,ky,ci} X[ci][plane zo+kz-1][f + (ky-1)*PX] * W[co][ci][kz][ky][kx]      f = in-plane position
@@ -36,7 +40,6 @@ constexpr int UM_NPROD = 96;                   // producer threads (3 warps): 20
 constexpr int UM_NEPI = 512;                   // epilogue threads: warp w handles TMEM lane quadrant w%4, M tile (w/4)%2, output-channel half w/8
 constexpr int UM_THREADS = UM_NEPI + 32 + UM_NPROD;  // warps 0-15 epilogue, 16 MMA issue, 17-19 producers (640 threads)
 constexpr int UM_MMA_WARP = UM_NEPI / 32;
-constexpr int UM_PF = 3;                       // L2 prefetch distance of the producers, in planes
 constexpr int UM_CB = 16;                      // output channels per launch
 constexpr int UM_NB = 3 * UM_CB;               // columns of one accumulator block: (kx, co)
 constexpr int UM_N = 3 * UM_NB;                // MMA N: three blocks = three output planes in flight
@@ -62,7 +65,8 @@ constexpr int UMMA_IMG_STRIDE_BYTES = UmmaCfg<0>::W_BYTES;  // 92160: every weig
 struct UmmaArgs {
   const float* x1; const float* x2; int C1, C2;
   const float* wimg;          // prepared weight image of (co block 0, this channel chunk); block ib is img_stride floats further
-                              // (fp32 hi/lo in mode 0, bf16 hi/lo otherwise)
+                              // (fp32 hi/lo in mode 0, scaled fp16 hi/lo otherwise)
+  const float* amax;          // modes 1, 2: device pointer to {max|input|, max|weight|} (absmax_kernel), which fix the scales
   int64_t img_stride; int nco; // output-channel blocks of the layer = blockIdx.z % nco
   const float* bias; float* out;
   int N, D, H, W, Cout;
@@ -70,7 +74,7 @@ struct UmmaArgs {
   int accumulate, last;       // add to the existing output; apply bias + activation
   int act; float slope;
   int tiles_x, tiles_y, zg;   // z planes per CTA
-  int flags;                  // debug (DA_UMMA_FLAGS): bit 0 = skip the output stores, bit 1 = no L2 prefetch
+  int flags;                  // debug (DA_UMMA_FLAGS): bit 0 = skip the output stores
   unsigned long long* dbg;    // optional cycle counters of the MMA warp (DA_UMMA_DEBUG=1): acc wait, plane wait, issue, total, steps
 };
 
@@ -106,21 +110,61 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
   if constexpr (BF) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
   else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
-// instruction descriptor: fp32 accumulate, A and B both K-major, format 2 = tf32 / 1 = bf16, N at bit 17, M at bit 24
+// instruction descriptor: fp32 accumulate, A and B both K-major, format 2 = tf32 / 0 = fp16, N at bit 17, M at bit 24
 template <bool BF>
 __device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-  const uint32_t fmt = BF ? 1u : 2u;
+  const uint32_t fmt = BF ? 0u : 2u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// x = hi + lo with both halves bf16 (round to nearest): |x - hi - lo| <= 2^-18 |x|.  Packs two values per register,
-// the first in the low half (= the lower K index).
-__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __low2float(h), b - __high2float(h));
+// Power-of-two scale 2^k that puts a tensor's max-abs into [2^13, 2^14) (fp16 overflows at 2^16), and its inverse.
+// amax = 0 or denormal gives the clamp 2^100 (the products are zero anyway).
+__device__ __forceinline__ int scale_exp_from_amax(float amax) {
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xffu) - 127;   // floor(log2(amax)) of a normal number
+  return max(-100, min(100, 13 - e));
+}
+__device__ __forceinline__ float pow2f(int k) { return __uint_as_float((uint32_t)(k + 127) << 23); }
+// x (already scaled) = hi + lo with both halves fp16, round to nearest: |x - hi - lo| <= 2^-24 |x| while lo is a normal
+// number, 2^-25 absolute below.  Packs two values per register, the first in the low half (= the lower K index).
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 l = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// max|x| over up to four segments into out[slot] (slots hold non-negative floats: their bit patterns order like
+// unsigned integers, so atomicMax works on them).  out must be zeroed before the launch.
+struct AbsmaxArgs { const float* p[4]; int64_t n[4]; int slot[4]; };
+__global__ void __launch_bounds__(256) absmax_kernel(AbsmaxArgs a, float* __restrict__ out) {
+  __shared__ float red[8];
+  for (int s = 0; s < 4; ++s) {
+    if (!a.p[s] || a.n[s] <= 0) continue;   // uniform over the grid
+    const float* p = a.p[s];
+    const int64_t n = a.n[s];
+    float m = 0.f;
+    const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x, nth = (int64_t)gridDim.x * 256;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const int64_t n4 = n >> 2;
+      for (int64_t i = tid; i < n4; i += nth) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+      for (int64_t i = (n4 << 2) + tid; i < n; i += nth) m = fmaxf(m, fabsf(__ldg(p + i)));
+    } else {
+      for (int64_t i = tid; i < n; i += nth) m = fmaxf(m, fabsf(__ldg(p + i)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float r = red[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) r = fmaxf(r, red[w]);
+      atomicMax(reinterpret_cast<unsigned int*>(out) + a.slot[s], __float_as_uint(r));
+    }
+  }
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -218,7 +262,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 
   if (warp > UM_MMA_WARP) {
     // =============================== producers ===============================
-    // thread = one 16-byte K chunk (grp: 4 channels as tf32, 8 as bf16) x PPT fixed in-plane positions: everything but
+    // thread = one 16-byte K chunk (grp: 4 channels as tf32, 8 as fp16) x PPT fixed in-plane positions: everything but
     // the plane offset is loop invariant, and 56 loads per thread are in flight together (one or two memory latencies
     // per plane)
     constexpr int TPG = UM_NPROD / NCH;          // 24 (48) threads per channel chunk
@@ -227,28 +271,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     const int tp = threadIdx.x - (UM_NEPI + 32);
     const int grp = tp / TPG, ti = tp - grp * TPG;
     const int cend = min(a.c0 + Cfg::KC, a.C1 + a.C2);
-    // The staged loads are latency bound (56 loads per thread, one DRAM round trip per batch): pull the row segments
-    // of the plane UM_PF steps ahead into L2 now, so that the loads proper find them there.  One task = one
-    // (channel, row) segment of 42 floats = at most three 128-byte lines.
-    const float* const pf1 = a.x1 + (int64_t)n * a.C1 * V;                                         // channel c <  C1: pf1 + c*V
-    const float* const pf2 = a.x2 ? a.x2 + ((int64_t)n * a.C2 - a.C1) * V : a.x1;                  // channel c >= C1: pf2 + c*V
-    auto prefetch_plane = [&](int zi) {
-      if ((a.flags & 2) || zi < 0 || zi >= a.D) return;
-      int tpv;   // opaque copy: keeps the per-task addresses from being hoisted out of the plane loop (registers)
-      asm volatile("mov.u32 %0, %1;" : "=r"(tpv) : "r"(tp));
-      const int xa = max(X0 - 1, 0), xb = min(X0 + UM_TX, a.W - 1);
-#pragma unroll 1
-      for (int t = tpv; t < Cfg::KC * (UM_TY + 2); t += UM_NPROD) {
-        const int c = a.c0 + t / (UM_TY + 2), gy = Y0 - 1 + t % (UM_TY + 2);
-        if (c >= cend || gy < 0 || gy >= a.H) continue;
-        const float* row = (c < a.C1 ? pf1 : pf2) + (int64_t)c * V + (int64_t)zi * HW + gy * a.W;
-        prefetch_l2(row + xa);
-        prefetch_l2(row + min(xa + 32, xb));
-        prefetch_l2(row + xb);
-      }
-    };
-    prefetch_plane(z0 - 1 + 1);
-    prefetch_plane(z0 - 1 + 2);
     if constexpr (!BF) {
       int oxy[PPT];
 #pragma unroll
@@ -270,7 +292,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
         const int slot = pi % 3, use = pi / 3;
         if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
         const int zi = z0 - 1 + pi;
-        if (pi + UM_PF < nsteps) prefetch_plane(zi + UM_PF);
         float4* shi = reinterpret_cast<float4*>(ring + slot * Cfg::SLOT_BYTES) + grp * UM_PFA;
         float4* slo = shi + NCH * UM_PFA;
         const bool zok = zi >= 0 && zi < a.D;
@@ -309,11 +330,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       constexpr int BATCH = 7, NBATCH = PPT / BATCH;   // 56 loads in flight per thread
       static_assert(NBATCH * BATCH == PPT, "load batches must tile the thread's positions");
       const int Vi = (int)V;   // 8 * V < 2^31 (checked by the host): 32-bit element offsets, no per-channel pointers
+      const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax)));
       for (int pi = 0; pi < nsteps; ++pi) {
         const int slot = pi % 3, use = pi / 3;
         if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
         const int zi = z0 - 1 + pi;
-        if (pi + UM_PF < nsteps) prefetch_plane(zi + UM_PF);
         uint4* shi = reinterpret_cast<uint4*>(ring + slot * Cfg::SLOT_BYTES) + grp * UM_PFA;
         uint4* slo = shi + NCH * UM_PFA;
         const bool zok = zi >= 0 && zi < a.D;
@@ -339,10 +360,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 #pragma unroll
           for (int b = 0; b < BATCH; ++b) {
             uint4 h, l;
-            split_bf16x2(v[b][0], v[b][1], h.x, l.x);
-            split_bf16x2(v[b][2], v[b][3], h.y, l.y);
-            split_bf16x2(v[b][4], v[b][5], h.z, l.z);
-            split_bf16x2(v[b][6], v[b][7], h.w, l.w);
+            split_f16x2(v[b][0] * sc, v[b][1] * sc, h.x, l.x);
+            split_f16x2(v[b][2] * sc, v[b][3] * sc, h.y, l.y);
+            split_f16x2(v[b][4] * sc, v[b][5] * sc, h.z, l.z);
+            split_f16x2(v[b][6] * sc, v[b][7] * sc, h.w, l.w);
             shi[ti + TPG * (q * BATCH + b)] = h;
             slo[ti + TPG * (q * BATCH + b)] = l;
           }
@@ -381,7 +402,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
             const uint32_t arow = slot_s + (uint32_t)(mt * UM_MSTEP + ky * UM_PX) * 16;  // (PX + mt*MSTEP) + (ky-1)*PX
             const uint32_t wt = brot + (uint32_t)(ky * NCH * UM_WROWS) * 16;
 #pragma unroll
-            for (int j2 = 0; j2 < NCH / 2; ++j2) {   // one instruction contracts two K chunks (8 tf32 / 16 bf16 channels)
+            for (int j2 = 0; j2 < NCH / 2; ++j2) {   // one instruction contracts two K chunks (8 tf32 / 16 fp16 channels)
               const uint64_t a_hi = umma_desc_at(adesc0, arow + (uint32_t)(2 * j2) * A_LBO);
               const uint64_t a_lo = umma_desc_at(adesc0, arow + (uint32_t)(2 * j2) * A_LBO + NCH * UM_PFA * 16);
               const uint64_t b_hi = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO);
@@ -423,6 +444,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 #pragma unroll
     for (int c = 0; c < 8; ++c) bv[c] = (a.last && a.bias && co0 + ch0 + c < a.Cout) ? __ldg(a.bias + co0 + ch0 + c) : 0.f;
     const bool do_act = a.last && a.act;
+    // modes 1, 2: the operands were scaled by 2^kx and 2^kw; one exact multiplication undoes it (a combined exponent
+    // below -126 means results under 2^-90: flushed to zero)
+    float us = 1.f;
+    if constexpr (BF) us = pow2f(max(-126, -(scale_exp_from_amax(__ldg(a.amax)) + scale_exp_from_amax(__ldg(a.amax + 1)))));
     // The kx fold needs row f-1 (tap 0) and f+1 (tap 2).  Inside a warp they come by shuffle; the two rows at the warp's
     // ends need the neighbouring warp's edge values, which travel through shared memory.  A store -> barrier -> load
     // chain inside the step cost 1k of its 4.7k cycles (shared memory is saturated by the MMA operand fetch, every round
@@ -494,11 +519,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       if (ol > 0) store_edges(op - HW);
       if (lane == 31) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][0][ch0 + c] = v[0][c];
+        for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][0][ch0 + c] = BF ? v[0][c] * us : v[0][c];
       }
       if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][1][ch0 + c] = v[2][c];
+        for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][1][ch0 + c] = BF ? v[2][c] * us : v[2][c];
       }
       __syncwarp();
 #pragma unroll
@@ -507,7 +532,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
         float right = __shfl_sync(0xffffffffu, v[2][c], (lane + 1) & 31);
         if (lane == 0) left = 0.f;      // wrapped around: the true neighbour lives in another warp (added by store_edges)
         if (lane == 31) right = 0.f;
-        float r = v[1][c] + left + right + old[c] + bv[c];
+        float r = v[1][c] + left + right;
+        if constexpr (BF) r *= us;
+        r += old[c] + bv[c];
         pend[c] = r;
         if (do_act) r = r > 0.f ? r : r * a.slope;
         if (valid && !edge_lane && co0 + ch0 + c < a.Cout && !(a.flags & 1)) op[(int64_t)c * V] = r;
@@ -566,15 +593,16 @@ __global__ void umma_prep_weights_kernel(const float* __restrict__ src, float* _
   }
 }
 
-// bf16 hi/lo weight image of one (16-output-channel block, 32-input-channel chunk; the last chunk of a layer may be a
-// 16-channel one, last_nch = 2):  [hi|lo][ky][ci/8][row = t*48 + kx*16 + co][8 bf16], image (ib, ik) at
-// dst + (ib * nk + ik) * UMMA_IMG_STRIDE_BYTES.  Chunk ik starts at input channel 32 * ik.
+// Scaled fp16 hi/lo weight image of one (16-output-channel block, 32-input-channel chunk; the last chunk of a layer may
+// be a 16-channel one, last_nch = 2):  [hi|lo][ky][ci/8][row = t*48 + kx*16 + co][8 halves], image (ib, ik) at
+// dst + (ib * nk + ik) * UMMA_IMG_STRIDE_BYTES.  Chunk ik starts at input channel 32 * ik.  amax[1] = max|weight|.
 __global__ void umma_prep_weights16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int d1, int a_is_dim0, int flip,
-                                           int A, int B, int b_off, int last_nch) {
+                                           int A, int B, int b_off, int last_nch, const float* __restrict__ amax) {
   const int ik = blockIdx.y, c0 = ik * 32, co0 = blockIdx.z * UM_CB;
   const int nch = (ik == (int)gridDim.y - 1) ? last_nch : 4;
   dst += (int64_t)(blockIdx.z * gridDim.y + ik) * (UMMA_IMG_STRIDE_BYTES / 2);
   const int half = 3 * nch * UM_WROWS * 8;   // elements of the hi (or lo) part
+  const float sc = pow2f(scale_exp_from_amax(__ldg(amax + 1)));
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
     int r = i >> 3;
@@ -589,10 +617,10 @@ __global__ void umma_prep_weights16_kernel(const float* __restrict__ src, uint16
       const int ts = flip ? (26 - tap) : tap;
       const int i0 = a_is_dim0 ? ai : (b + b_off);
       const int i1 = a_is_dim0 ? (b + b_off) : ai;
-      v = src[((int64_t)i0 * d1 + i1) * 27 + ts];
+      v = src[((int64_t)i0 * d1 + i1) * 27 + ts] * sc;
     }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
     dst[i] = *reinterpret_cast<const uint16_t*>(&hi);
     dst[half + i] = *reinterpret_cast<const uint16_t*>(&lo);
   }

@@ -272,7 +272,8 @@ struct WgUmmaTmaArgs {
   int tiles_x, tiles_y;
   int ncols, zlen, nunits;  // work unit = (column, z segment of zlen planes); unit u -> CTA u % gridDim.y
   float* bias_partials;     // nullable: [region][P1+P2] sums of the plain-side tensor (= bias gradient when that is dY)
-  unsigned long long* dbg;  // optional cycle counters (DA_UMMA_DEBUG=1, 3xBF16 kernel): MMA warp waiting for operands / total,
+  const float* amax;        // 3xFP16 kernel: device pointer to {max|halo-side tensors|, max|plain-side tensors|} (absmax_kernel)
+  unsigned long long* dbg;  // optional cycle counters (DA_UMMA_DEBUG=1, 3xFP16 kernel): MMA warp waiting for operands / total,
                             // B producer warp waiting for raw tiles / for a free stage / total, TMA thread waiting, tiles
 };
 
@@ -510,11 +511,12 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 3xBF16 variant of the TMA-fed kernel (the default): kind::f16 MMAs on bf16 hi/lo pairs contract K = 16 positions per
-// instruction at the cycle cost of a K = 8 tf32 one (tools/probes/umma16_probe.cu), and the halo-side block may be 32
-// channels wide, so 96 of the 128 MMA rows are useful instead of 48.
+// 3xFP16 variant of the TMA-fed kernel (the default): kind::f16 MMAs on fp16 hi/lo pairs of the operands scaled per
+// tensor by a power of two (see conv3d_umma.inc.cuh, mode 1) contract K = 16 positions per instruction at the cycle cost
+// of a K = 8 tf32 one (tools/probes/umma16_probe.cu), and the halo-side block may be 32 channels wide, so 96 of the 128
+// MMA rows are useful instead of 48.
 //   D[(t, ci)][(kz, ky, co)] += sum_k A[(t, ci)][k] * B[(kz, ky, co)][k]     k = (pair p, xe, ye): positions x0+2p+xe, y0+ye
-// * A 16-byte K chunk holds 8 bf16 = one x-PAIR x 4 y-rows.  The kx shift is again free, but now through two
+// * A 16-byte K chunk holds 8 halves = one x-PAIR x 4 y-rows.  The kx shift is again free, but now through two
 //   interleaved images of X: block b = [CIB ci][(xe, ye)] holds the positions x0-1+b+xe, i.e. even blocks are the
 //   pairs of the kx = 0 / 2 alignment and odd blocks those of kx = 1.  MMA row CIB*t + ci of the K chunk of pair p
 //   then simply reads block 2p + t (LBO = two blocks = one pair, SBO = 128 B; rows t >= 3 compute garbage).
@@ -667,6 +669,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     const int p = tb & 7, co = (tb >> 3) & 15, kz = tb >> 7;
     int q = -1, k = 0;
     float bsum = 0.f;  // bias gradient: the kz = 1 tasks see every dY value of the tile exactly once (rows 1..4)
+    const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax + 1)));
     long long d_raw = 0, d_empty = 0;
     const long long d_begin = DBG ? clock64() : 0;
     for (int u = region; u < a.nunits; u += R) {
@@ -682,6 +685,8 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
 #pragma unroll
         for (int r = 0; r < 6; ++r) v[r] = *reinterpret_cast<const float2*>(src + r * 256);
         if (kz == 1) bsum += ((v[1].x + v[1].y) + (v[2].x + v[2].y)) + ((v[3].x + v[3].y) + (v[4].x + v[4].y));
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { v[r].x *= sc; v[r].y *= sc; }
         const long long d1 = DBG ? clock64() : 0;
         if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
         if (DBG) d_empty += clock64() - d1;
@@ -689,10 +694,10 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {   // K element (xe, ye) = dY row y0 + ye - ky + 1 = v[ye - ky + 2]
           uint4 h, l;
-          split_bf16x2(v[2 - ky].x, v[3 - ky].x, h.x, l.x);
-          split_bf16x2(v[4 - ky].x, v[5 - ky].x, h.y, l.y);
-          split_bf16x2(v[2 - ky].y, v[3 - ky].y, h.z, l.z);
-          split_bf16x2(v[4 - ky].y, v[5 - ky].y, h.w, l.w);
+          split_f16x2(v[2 - ky].x, v[3 - ky].x, h.x, l.x);
+          split_f16x2(v[4 - ky].x, v[5 - ky].x, h.y, l.y);
+          split_f16x2(v[2 - ky].y, v[3 - ky].y, h.z, l.z);
+          split_f16x2(v[4 - ky].y, v[5 - ky].y, h.w, l.w);
           *reinterpret_cast<uint4*>(st + ky * 256) = h;
           *reinterpret_cast<uint4*>(st + Cfg::B_BYTES + ky * 256) = l;
         }
@@ -718,6 +723,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     constexpr int NT = 17 * CIB;                       // blocks 0..16 carry data (rows t <= 2 of pairs 0..7)
     constexpr int TPT = (NT + 32 * Cfg::NAW - 1) / (32 * Cfg::NAW);
     const int ta0 = (warp - 14) * 32 + lane;
+    const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax)));
     for (int k = 0; k < ntl; ++k) {
       const int s = k & 1, use = k >> 1;
       mbar_wait(&rawfull[k % WB_NR], (k / WB_NR) & 1);
@@ -742,10 +748,10 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
         const int ta = ta0 + 32 * Cfg::NAW * j;
         if (ta < NT) {
           uint4 h, l;
-          split_bf16x2(v[j][0], v[j][1], h.x, l.x);
-          split_bf16x2(v[j][2], v[j][3], h.y, l.y);
-          split_bf16x2(v[j][4], v[j][5], h.z, l.z);
-          split_bf16x2(v[j][6], v[j][7], h.w, l.w);
+          split_f16x2(v[j][0] * sc, v[j][1] * sc, h.x, l.x);
+          split_f16x2(v[j][2] * sc, v[j][3] * sc, h.y, l.y);
+          split_f16x2(v[j][4] * sc, v[j][5] * sc, h.z, l.z);
+          split_f16x2(v[j][6] * sc, v[j][7] * sc, h.w, l.w);
           *reinterpret_cast<uint4*>(st + ta * 16) = h;               // (b * CIB + ci) * 16
           *reinterpret_cast<uint4*>(st + Cfg::A_BYTES + ta * 16) = l;
         }
@@ -763,6 +769,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     const int r = (warp - 4) * 32 + lane;   // TMEM lane = accumulator row; warp 4 + i reads lane quadrant i
     const int kx = r / CIB, ci = cib * CIB + r % CIB;
     float* pr = a.partials + (int64_t)region * a.region_stride;
+    const float us = pow2f(max(-126, -(scale_exp_from_amax(__ldg(a.amax)) + scale_exp_from_amax(__ldg(a.amax + 1)))));
 #pragma unroll 1
     for (int g = 0; g < 9; ++g) {
       float v16[16];
@@ -772,7 +779,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int co = cob * 16 + c;
-          if (co < pC) pr[((int64_t)(pg0 + co) * (a.H1 + a.H2) + hg0 + ci) * 27 + g * 3 + kx] = ntl > 0 ? v16[c] : 0.f;
+          if (co < pC) pr[((int64_t)(pg0 + co) * (a.H1 + a.H2) + hg0 + ci) * 27 + g * 3 + kx] = ntl > 0 ? v16[c] * us : 0.f;
         }
       }
     }

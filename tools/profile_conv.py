@@ -22,29 +22,39 @@ for _ in range(reps):
     y = ops.conv3d(x1, w, b, x2=x2)
     y.backward(torch.ones_like(y))
 torch.cuda.synchronize()
-# timing without a profiler attached (meaningless under ncu)
+# timing without a profiler attached (meaningless under ncu): NT calls back to back between two events, so that the
+# host-side cost of a call (allocation, ctypes, tensor-map encoding: ~0.1 ms) hides behind the previous call's kernels
+NT = int(os.environ.get("DA_NT", "6"))
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-y = None
-ev[0].record(); y = ops.conv3d(x1, w, b, x2=x2); ev[1].record()
-gy = torch.ones_like(y)
+dbg = os.environ.get("DA_UMMA_DEBUG") == "1"
+if dbg:
+    import ctypes
+    from deepatlas_b200 import _lib
+    buf = (ctypes.c_int64 * 11)()
+    _lib.call("da_umma_debug_read", ctypes.cast(buf, ctypes.c_void_p))   # clear what the warm-up left
+ys = []
+ev[0].record()
+for _ in range(NT):
+    ys.append(ops.conv3d(x1, w, b, x2=x2))
+ev[1].record()
 torch.cuda.synchronize()
 fwd_counters = None
-if os.environ.get("DA_UMMA_DEBUG") == "1":
-    import ctypes
-    from deepatlas_b200 import _lib
-    buf = (ctypes.c_int64 * 11)()
+if dbg:
     _lib.call("da_umma_debug_read", ctypes.cast(buf, ctypes.c_void_p))   # reads and clears: what follows belongs to the backward pass
     fwd_counters = list(buf)
-ev[2].record(); y.backward(gy); ev[3].record()
+gy = torch.ones_like(ys[0])
+torch.cuda.synchronize()
+ev[2].record()
+for y in ys:
+    y.backward(gy)
+ev[3].record()
 torch.cuda.synchronize()
 fl = 2.0 * 27 * (C1 + C2) * Cout * D * H * W
-print(f"shape {C1}+{C2}->{Cout} @{D}x{H}x{W}: fwd {ev[0].elapsed_time(ev[1]):.3f} ms ({fl / ev[0].elapsed_time(ev[1]) / 1e9:.1f} TFLOP/s), "
-      f"{'bwd' if xg else 'wgrad'} {ev[2].elapsed_time(ev[3]):.3f} ms ({(2 if xg else 1) * fl / ev[2].elapsed_time(ev[3]) / 1e9:.1f} TFLOP/s)")
+tf, tb = ev[0].elapsed_time(ev[1]) / NT, ev[2].elapsed_time(ev[3]) / NT
+print(f"shape {C1}+{C2}->{Cout} @{D}x{H}x{W}: fwd {tf:.3f} ms ({fl / tf / 1e9:.1f} TFLOP/s), "
+      f"{'bwd' if xg else 'wgrad'} {tb:.3f} ms ({(2 if xg else 1) * fl / tb / 1e9:.1f} TFLOP/s)")
 
-if os.environ.get("DA_UMMA_DEBUG") == "1":
-    import ctypes
-    from deepatlas_b200 import _lib
-    buf = (ctypes.c_int64 * 11)()
+if dbg:
     _lib.call("da_umma_debug_read", ctypes.cast(buf, ctypes.c_void_p))
     if not xg:   # weight gradient alone: the counters are those of conv3d_wgrad_umma16_kernel
         mw, mt, braw, bempty, btot, tmaw, tiles, nct = list(buf)[:8]
