@@ -672,9 +672,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
                                        float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  float acc = 0.f;
-  for (int r = 0; r < nregions; ++r) acc += partials[(int64_t)r * count + i];
-  out[i] = acc;
+  double acc = 0.0;   // <= 148 partials per element: fp64 costs nothing here and keeps cancelling sums clean
+  for (int r = 0; r < nregions; ++r) acc += (double)partials[(int64_t)r * count + i];
+  out[i] = (float)acc;
 }
 
 // per-channel sum over N and space (bias gradient):  out[c] = sum_{n,v} x[n][c][v]

@@ -392,7 +392,7 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
       tco[j] = (tb >> 4) & 15; tkz[j] = tb >> 8;
     }
     int q = -1, k = 0;
-    float bsum = 0.f;  // bias gradient: the kz = 1 task holds every dY value of the tile exactly once (rows 1..4)
+    double bsum = 0.0;  // bias gradient: the kz = 1 task holds every dY value of the tile exactly once (rows 1..4); fp64 across tiles
     for (int u = region; u < a.nunits; u += R) {
       const int zb = (u / a.ncols) * a.zlen, ze = min(a.D, zb + a.zlen);
       for (int z = zb; z < ze; ++z, ++k) {
@@ -405,7 +405,7 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
         const float* p = rawY + ((q - tkz[j]) % WV_YS) * (WV_RAW_BYTES / 4) + tco[j] * 96 + tx;  // plane z - kz + 1
 #pragma unroll
         for (int r = 0; r < 6; ++r) v[j][r] = p[r * 16];
-        if (tkz[j] == 1) bsum += (v[j][1] + v[j][2]) + (v[j][3] + v[j][4]);
+        if (tkz[j] == 1) bsum += (double)((v[j][1] + v[j][2]) + (v[j][3] + v[j][4]));
       }
       if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
       uint8_t* st = smem + s * WU_STAGE_BYTES + 2 * WU_A_BYTES;
@@ -436,7 +436,7 @@ conv3d_wgrad_umma_tma_kernel(const __grid_constant__ CUtensorMap map_h1, const _
       for (int o = 8; o >= 1; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
       const int co = (tp < 128) ? tco[1] : tco[0];
       if (tx == 0 && (tp < 128 || tp >= 256) && cob * 16 + co < pC)
-        a.bias_partials[(int64_t)region * (a.P1 + a.P2) + pg0 + cob * 16 + co] = bsum;
+        a.bias_partials[(int64_t)region * (a.P1 + a.P2) + pg0 + cob * 16 + co] = (float)bsum;
     }
   } else {
     // =============================== A producers: (xc, ci) fixed per (thread, j) ===============================
@@ -668,7 +668,10 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     const int tb = threadIdx.x - 64;
     const int p = tb & 7, co = (tb >> 3) & 15, kz = tb >> 7;
     int q = -1, k = 0;
-    float bsum = 0.f;  // bias gradient: the kz = 1 tasks see every dY value of the tile exactly once (rows 1..4)
+    // bias gradient: the kz = 1 tasks see every dY value of the tile exactly once (rows 1..4).  The gradient of a
+    // translation-invariant loss sums to ~0 over the volume (flow.bias): fp64 across the thread's tiles keeps the
+    // cancellation from amplifying fp32 round-off (one DADD per tile)
+    double bsum = 0.0;
     const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax + 1)));
     long long d_raw = 0, d_empty = 0;
     const long long d_begin = DBG ? clock64() : 0;
@@ -684,7 +687,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
         float2 v[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) v[r] = *reinterpret_cast<const float2*>(src + r * 256);
-        if (kz == 1) bsum += ((v[1].x + v[1].y) + (v[2].x + v[2].y)) + ((v[3].x + v[3].y) + (v[4].x + v[4].y));
+        if (kz == 1) bsum += (double)(((v[1].x + v[1].y) + (v[2].x + v[2].y)) + ((v[3].x + v[3].y) + (v[4].x + v[4].y)));
 #pragma unroll
         for (int r = 0; r < 6; ++r) { v[r].x *= sc; v[r].y *= sc; }
         const long long d1 = DBG ? clock64() : 0;
@@ -714,7 +717,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
       bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
       bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
       bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
-      if (p == 0 && cob * 16 + co < pC) a.bias_partials[(int64_t)region * (a.P1 + a.P2) + pg0 + cob * 16 + co] = bsum;
+      if (p == 0 && cob * 16 + co < pC) a.bias_partials[(int64_t)region * (a.P1 + a.P2) + pg0 + cob * 16 + co] = (float)bsum;
     }
   } else {
     // =============================== A producers: task = (block b, ci) ===============================

@@ -141,11 +141,11 @@ def unet_forward(x, sd: SD, bn: bool, training=True, stats_out=None):
     return F.conv3d(d1, sd["dc0.weight"], sd.get("dc0.bias"))
 
 
-def identity_transform(size: Sequence[int], dtype=torch.float32) -> torch.Tensor:
+def identity_transform(size: Sequence[int], dtype=torch.float32, device=None) -> torch.Tensor:
     """get_identity_transform (lib/utils.py:89-102): 3xDxHxW, channel 0 = x (W axis), 1 = y (H),
     2 = z (D); values k/(n-1)*2-1.  The reference builds it in float32 (arange().float())."""
     D, H, W = size
-    ax = [torch.arange(0, n).float() / (n - 1) * 2.0 - 1 for n in (D, H, W)]
+    ax = [torch.arange(0, n, device=device).float() / (n - 1) * 2.0 - 1 for n in (D, H, W)]
     zz, yy, xx = torch.meshgrid(ax, indexing="ij")
     return torch.stack([xx, yy, zz]).to(dtype)
 
@@ -177,7 +177,7 @@ def voxelmorph_forward(source, target, sd: SD):
     d4 = _vm_block(torch.cat((d3, x2), 1), sd, "decoders.3", 1)
     d5 = _vm_block(F.interpolate(d4, size=x1.shape[2:]), sd, "decoders.4", 1)
     disp = F.conv3d(torch.cat((d5, x1), 1), sd["flow.weight"], sd["flow.bias"], padding=1)
-    deform = disp + identity_transform(source.shape[2:], dtype=disp.dtype)
+    deform = disp + identity_transform(source.shape[2:], dtype=disp.dtype, device=disp.device)
     return disp, warp(source, deform), deform
 
 
@@ -190,7 +190,7 @@ def mask_to_one_hot(mask, n_classes: int, dtype=torch.float32):
     """lib/transforms.py:675-689 (float32 zeros + scatter_ of ones along dim 1)."""
     shape = list(mask.shape)
     shape[1] = n_classes
-    return torch.zeros(shape, dtype=dtype).scatter_(1, mask.long(), 1)
+    return torch.zeros(shape, dtype=dtype, device=mask.device).scatter_(1, mask.long(), 1)
 
 
 def dice_multiclass(source, target, n_class: int, weight_type="Simple", no_bg=False,
@@ -216,7 +216,7 @@ def dice_multiclass(source, target, n_class: int, weight_type="Simple", no_bg=Fa
         tmp = torch.where(torch.isinf(w), torch.ones_like(w), w)
         w = torch.where(torch.isinf(w), torch.ones_like(w) * tmp.max(dim=1, keepdim=True)[0], w)
     elif weight_type == "Uniform":
-        w = torch.ones(B, C - int(no_bg), dtype=source.dtype)
+        w = torch.ones(B, C - int(no_bg), dtype=source.dtype, device=source.device)
     else:
         raise ValueError(weight_type)
     w = w / w.max()
@@ -229,7 +229,7 @@ def lncc(I, J, filter_size=9, eps=1e-6):
     """VoxelMorphLNCC.forward (lib/loss.py:597-617): five valid box-filter sums via F.conv3d with
     a ones kernel, then the reference's cancellation-form cross/variance expressions."""
     n = filter_size ** 3
-    k = torch.ones(1, 1, filter_size, filter_size, filter_size, dtype=I.dtype)
+    k = torch.ones(1, 1, filter_size, filter_size, filter_size, dtype=I.dtype, device=I.device)
     Is, Js = F.conv3d(I, k), F.conv3d(J, k)
     I2s, J2s, IJs = F.conv3d(I * I, k), F.conv3d(J * J, k), F.conv3d(I * J, k)
     Im, Jm = Is / n, Js / n
@@ -242,11 +242,11 @@ def lncc(I, J, filter_size=9, eps=1e-6):
 def bending_energy(u, spacing=(1.0, 1.0, 1.0), normalize=True):
     """BendingEnergyLoss.forward, norm='L2' (lib/loss.py:687-730).  Note the per-CHANNEL scale:
     ``spatial_dims`` (D,H,W)/min multiplies the (B,3) per-channel means (reference quirk, kept)."""
-    sp = torch.tensor(spacing, dtype=torch.float32)
+    sp = torch.tensor(spacing, dtype=torch.float32, device=u.device)
     if normalize:
         sp = sp / sp.min()
     sp = sp.to(u.dtype)
-    dims = torch.tensor(u.shape[2:], dtype=torch.float32)
+    dims = torch.tensor(u.shape[2:], dtype=torch.float32, device=u.device)
     if normalize:
         dims = dims / dims.min()
     dims = dims.to(u.dtype)

@@ -95,7 +95,7 @@ def rel_err_quantile(a, b, frac=1e-4):
     return float(d.kthvalue(k).values / max(float(b.abs().max()), 1e-30))
 
 
-def check_grads_vs_truth(ours, ref32, truth64, tol, slack=3.0, floor=1e-3):
+def check_grads_vs_truth(ours, ref32, truth64, tol, slack=3.0, floor=1e-3, strict=True):
     """Gradient parity on the precision ladder: fp64 oracle = truth, fp32 oracle = the
     reference's own behaviour.  Each of OUR gradients must be within max(tol, slack * reference-fp32 error) of
     the truth, errors normalised by max(||truth_k||_inf, floor * max_k ||truth_k||_inf) so that analytically-zero
@@ -109,7 +109,8 @@ def check_grads_vs_truth(ours, ref32, truth64, tol, slack=3.0, floor=1e-3):
         e_ours = float((ours[k].detach().double().cpu() - t).abs().max()) / scale
         e_ref = float((ref32[k].detach().double() - t).abs().max()) / scale
         bound = max(tol, slack * e_ref)
-        assert e_ours <= bound, f"grad {k}: ours-vs-fp64 {e_ours:.3e} > bound {bound:.3e} (reference fp32-vs-fp64 {e_ref:.3e})"
+        if strict:   # bench.py reports the worst ratio instead of stopping
+            assert e_ours <= bound, f"grad {k}: ours-vs-fp64 {e_ours:.3e} > bound {bound:.3e} (reference fp32-vs-fp64 {e_ref:.3e})"
         if e_ours / bound > worst[0]:
             worst = (e_ours / bound, k)
         if e_ours > worst_abs[0]:
