@@ -936,9 +936,13 @@ inline bool split_tf32() {
 inline bool fwd_umma_ok(const ConvGeom& g) {
   // one launch covers a block of 16 output channels: below ~50k voxels a launch no longer amortises its fixed cost and
   // the tiled FFMA kernel (one launch per layer) wins (measured on UNet's 32^3 levels)
+  // structural limits of the kernel: 32-bit element offsets (output tensor, eight input channels), fused activation
+  // written as max(r, r * slope)
+  const int64_t V = (int64_t)g.Do * g.Ho * g.Wo;
+  if ((int64_t)g.N * g.Cout * V >= ((int64_t)1 << 32) || 8 * V >= ((int64_t)1 << 31)) return false;
+  if (g.act && !(g.slope >= 0.f && g.slope <= 1.f)) return false;
   if (g_force_direct == 3) return g.stride == 1 && g.pad == 1;  // tests: tensor-core path whatever the size heuristics say
-  return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 &&
-         (int64_t)g.Do * g.Ho * g.Wo >= 65536;
+  return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 && V >= 65536;
 }
 inline int64_t umma_workspace_bytes(int Cin, int Cout) {
   return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + 15) / 16) * UMMA_IMG_BYTES + 256;   // + the max-abs slots
@@ -971,23 +975,28 @@ inline unsigned long long* umma_dbg_buffer() {
 }
 
 template <int MODE>
-int launch_umma_mode(const UmmaArgs& a, cudaStream_t stream) {
+int launch_umma_mode(const UmmaArgs& a, const CUtensorMap& m1, const CUtensorMap& m2, cudaStream_t stream) {
   static DaPerDeviceOnce configured;
   constexpr int SMEM = UmmaCfg<MODE>::SMEM_BYTES;
+  constexpr bool HAS_DBG = MODE == 0 || MODE >= 3;   // cycle counters: the 3xTF32 kernel and the TMA-fed ones
   if (configured.first()) {
     cudaFuncSetAttribute(conv3d_umma_kernel<false, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     cudaFuncSetAttribute(conv3d_umma_kernel<false, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    cudaFuncSetAttribute(conv3d_umma_kernel<true, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    cudaFuncSetAttribute(conv3d_umma_kernel<true, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if constexpr (HAS_DBG) {
+      cudaFuncSetAttribute(conv3d_umma_kernel<true, false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      cudaFuncSetAttribute(conv3d_umma_kernel<true, true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    }
   }
   dim3 grid(a.tiles_x * a.tiles_y, (a.D + a.zg - 1) / a.zg, a.N * a.nco);
-  if (a.dbg) {
-    if (a.accumulate) conv3d_umma_kernel<true, true, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
-    else conv3d_umma_kernel<true, false, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
-  } else {
-    if (a.accumulate) conv3d_umma_kernel<false, true, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
-    else conv3d_umma_kernel<false, false, MODE><<<grid, UM_THREADS, SMEM, stream>>>(a);
+  if constexpr (HAS_DBG) {
+    if (a.dbg) {
+      if (a.accumulate) conv3d_umma_kernel<true, true, MODE><<<grid, UM_THREADS, SMEM, stream>>>(m1, m2, a);
+      else conv3d_umma_kernel<true, false, MODE><<<grid, UM_THREADS, SMEM, stream>>>(m1, m2, a);
+      return da_check_launch("conv3d_umma");
+    }
   }
+  if (a.accumulate) conv3d_umma_kernel<false, true, MODE><<<grid, UM_THREADS, SMEM, stream>>>(m1, m2, a);
+  else conv3d_umma_kernel<false, false, MODE><<<grid, UM_THREADS, SMEM, stream>>>(m1, m2, a);
   return da_check_launch("conv3d_umma");
 }
 
@@ -1040,12 +1049,26 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, int64_t
   // the channel chunks accumulate through the output tensor (serial launches); the output-channel blocks are
   // independent and share each launch (grid.z)
   a.nco = nco; a.img_stride = (int64_t)nk * (UMMA_IMG_BYTES / 4);
+  // TMA-staged input planes (modes 3, 4): 16-byte aligned rows and bases, 8-channel boxes that never straddle the
+  // concatenation; the register-staged modes 1, 2 serve everything else
+  CUtensorMap m1, m2;
+  memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2));
+  bool tma_in = !tf32 && !tma_disabled() && (g.Wi & 3) == 0 && aligned16(x1) && aligned16(x2) && (g.C2 == 0 || (g.C1 & 7) == 0);
+  if (tma_in) {
+    { static int off = -1; if (off < 0) { const char* e = getenv("DA_UMMA_TMA_IN"); off = (e && strcmp(e, "0") == 0) ? 1 : 0; } if (off) tma_in = false; }
+  }
+  if (tma_in) {
+    rc = da_make_volume_map(&m1, x1, g.N, g.C1, g.Di, g.Hi, g.Wi, UM_RAWX, UM_TY + 2, 1, 8);
+    if (!rc && g.C2) rc = da_make_volume_map(&m2, x2, g.N, g.C2, g.Di, g.Hi, g.Wi, UM_RAWX, UM_TY + 2, 1, 8);
+    if (rc) tma_in = false;   // the encoder refused this extent: register-staged path
+  }
   for (int ik = 0; ik < nk; ++ik) {
     a.wimg = wp + (int64_t)ik * (UMMA_IMG_BYTES / 4);
     a.c0 = ik * KC; a.accumulate = ik > 0; a.last = ik == nk - 1;
-    if (tf32) rc = launch_umma_mode<0>(a, stream);
-    else if (ik == nk - 1 && last_nch == 2) rc = launch_umma_mode<2>(a, stream);
-    else rc = launch_umma_mode<1>(a, stream);
+    const bool narrow = ik == nk - 1 && last_nch == 2;
+    if (tf32) rc = launch_umma_mode<0>(a, m1, m2, stream);
+    else if (tma_in) rc = narrow ? launch_umma_mode<4>(a, m1, m2, stream) : launch_umma_mode<3>(a, m1, m2, stream);
+    else rc = narrow ? launch_umma_mode<2>(a, m1, m2, stream) : launch_umma_mode<1>(a, m1, m2, stream);
     if (rc) return rc;
   }
   return DA_OK;

@@ -9,6 +9,14 @@
 //      the channels per MMA.  (bf16 pairs need no scaling but carry 16 bits: weight gradients of the first layers
 //      came out 1e-2 off the fp64 oracle, against 1e-4 for 3xTF32 -- measured, rejected.)
 //   2  3xFP16 with 16 input channels per launch (two K chunks): narrow layers and the remainder of Cin % 32
+//   3, 4  modes 1, 2 with the input planes staged by TMA: the register-staged producers of modes 0-2 hold 56 loads per
+//      thread in flight = 21 KB per SM, and one DRAM round trip per batch made them -- not the tensor pipe -- the
+//      limit of a plane step (4.1k cycles per 16 channels, measured with the cycle counters).  Here a plane is cut
+//      into 16-channel units; raw fp32 units ([16 ch][8 rows][48 x] boxes, zero-filled outside the volume) arrive
+//      through a ring of 3-4 TMA slots (49-74 KB in flight, no registers), the three producer warps only convert
+//      shared memory -> scaled fp16 hi/lo -> shared memory, and the MMAs of a plane run unit by unit (the second unit
+//      accumulates into the same TMEM blocks).  Needs W % 4 == 0, 16-byte aligned tensors and a concatenation boundary
+//      on a multiple of 8 channels; otherwise modes 1, 2 serve.
 //
 // Implicit GEMM, output-stationary in TMEM:
 //   D[f][(kx,co)] = sum_{kz,ky,ci} X[ci][plane zo+kz-1][f + (ky-1)*PX] * W[co][ci][kz][ky][kx]      f = in-plane position
@@ -47,18 +55,28 @@ constexpr int UM_WROWS = 5 * UM_NB;            // weight rows: kz blocks in the 
 static_assert(UM_MT * 128 + 2 * UM_PX <= UM_PFA, "shifted A rows must stay inside the slot");
 static_assert(UM_MT * UM_MSTEP >= UM_TY * UM_PX, "M tiles must cover the output rows");
 
+constexpr int UM_RAWX = 48;                    // TMA modes: raw row = x0-4 .. x0+43 (the inner box coordinate must be 16-byte aligned)
 template <int MODE>
 struct UmmaCfg {
   static constexpr bool BF = MODE != 0;
+  static constexpr bool TMAIN = MODE >= 3;
   static constexpr int EPC = BF ? 8 : 4;                             // input channels per 16-byte K chunk
-  static constexpr int NCH = MODE == 2 ? 2 : 4;                      // K chunks per launch
-  static constexpr int KC = EPC * NCH;                               // input channels per launch: 16, 32, 16
-  static constexpr int SLOT_BYTES = 2 * NCH * UM_PFA * 16;           // hi + lo
-  static constexpr int RING_BYTES = 3 * SLOT_BYTES;
+  static constexpr int NCH = (MODE == 2 || MODE == 4) ? 2 : 4;       // K chunks per launch
+  static constexpr int KC = EPC * NCH;                               // input channels per launch: 16, 32, 16, 32, 16
+  static constexpr int SCH = TMAIN ? 2 : NCH;                        // K chunks per ring slot (TMA modes: one 16-channel unit)
+  static constexpr int NSUB = NCH / SCH;                             // units per plane
+  static constexpr int NRING = (MODE == 3) ? 2 : 3;
+  static constexpr int SLOT_BYTES = 2 * SCH * UM_PFA * 16;           // hi + lo
+  static constexpr int RING_BYTES = NRING * SLOT_BYTES;
+  static constexpr int NRAW = TMAIN ? (MODE == 3 ? 3 : 4) : 0;       // raw fp32 units in flight
+  static constexpr int RAW_SLOT_BYTES = 16 * (UM_TY + 2) * UM_RAWX * 4;   // [16 ch][8 rows][48 x]
+  static constexpr int RAW_BYTES = NRAW * RAW_SLOT_BYTES;
   static constexpr int W_BYTES = 2 * 3 * NCH * UM_WROWS * 16;        // [hi|lo][ky][ci/EPC][row][16 bytes]
-  static constexpr int SMEM_BYTES = RING_BYTES + W_BYTES + 128;
+  static constexpr int SMEM_BYTES = RAW_BYTES + RING_BYTES + W_BYTES + 128;   // raw slots first (TMA destinations: 128-byte aligned)
   static constexpr int TMEM_COLS = 512;
   static_assert(UM_MT * UM_N <= 512, "accumulators exceed TMEM");
+  static_assert(RAW_SLOT_BYTES % 128 == 0 && SLOT_BYTES % 128 == 0, "alignment");
+  static_assert(SMEM_BYTES <= 232448 - 4096, "shared memory (static arrays take ~2.5 KB)");
 };
 constexpr int UMMA_IMG_STRIDE_BYTES = UmmaCfg<0>::W_BYTES;  // 92160: every weight image of a layer sits at this pitch
 
@@ -74,7 +92,7 @@ struct UmmaArgs {
   int accumulate, last;       // add to the existing output; apply bias + activation
   int act; float slope;
   int tiles_x, tiles_y, zg;   // z planes per CTA
-  int flags;                  // debug (DA_UMMA_FLAGS): bit 0 = skip the output stores
+  int flags;                  // debug (DA_UMMA_FLAGS), unused at present
   unsigned long long* dbg;    // optional cycle counters of the MMA warp (DA_UMMA_DEBUG=1): acc wait, plane wait, issue, total, steps
 };
 
@@ -165,6 +183,15 @@ __global__ void __launch_bounds__(256) absmax_kernel(AbsmaxArgs a, float* __rest
     }
   }
 }
+// shared-space accesses with 32-bit addresses (generic pointers cost a register pair per dynamic offset)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -204,17 +231,20 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 template <bool DBG, bool ACC, int MODE>   // cycle counters (DA_UMMA_DEBUG=1); a.accumulate (further input-channel chunks); operand format
-__global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) {
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv3d_umma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2, UmmaArgs a) {
   using Cfg = UmmaCfg<MODE>;
   constexpr int N = UM_N, NCH = Cfg::NCH, NB = UM_NB;
   constexpr bool BF = Cfg::BF;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t plane_full[3], plane_empty[3], acc_full[UM_MT], acc_empty[UM_MT];
+  // plane_full / plane_empty: ring slots (one plane, or one 16-channel unit of a plane in the TMA modes)
+  __shared__ __align__(8) uint64_t plane_full[3], plane_empty[3], acc_full[UM_MT], acc_empty[UM_MT], raw_full[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ float edge_s[2][8][2][16];  // warp-edge rows of the kx fold (static: keeps LDS/STS addressing)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  uint8_t* ring = smem;
-  uint8_t* sw = smem + Cfg::RING_BYTES;
+  uint8_t* rawbuf = smem;
+  uint8_t* ring = smem + Cfg::RAW_BYTES;
+  uint8_t* sw = ring + Cfg::RING_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int tb = blockIdx.x;
@@ -232,12 +262,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(&plane_full[i], UM_NPROD); mbar_init(&plane_empty[i], 1); }
     for (int i = 0; i < UM_MT; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], UM_NEPI / UM_MT); }
+    for (int i = 0; i < 4; ++i) mbar_init(&raw_full[i], 1);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < Cfg::W_BYTES / 16; i += UM_THREADS)
     reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wimg) + i);
   // rows UM_PLANE .. UM_PFA of every chunk are only read by discarded accumulator rows; zero them once (no NaN patterns)
-  for (int i = threadIdx.x; i < 3 * 2 * NCH * (UM_PFA - UM_PLANE); i += UM_THREADS) {
+  for (int i = threadIdx.x; i < Cfg::NRING * 2 * Cfg::SCH * (UM_PFA - UM_PLANE); i += UM_THREADS) {
     const int t = i % (UM_PFA - UM_PLANE), c = i / (UM_PFA - UM_PLANE);
     reinterpret_cast<float4*>(ring)[c * UM_PFA + UM_PLANE + t] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -271,7 +302,74 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     const int tp = threadIdx.x - (UM_NEPI + 32);
     const int grp = tp / TPG, ti = tp - grp * TPG;
     const int cend = min(a.c0 + Cfg::KC, a.C1 + a.C2);
-    if constexpr (!BF) {
+    if constexpr (Cfg::TMAIN) {
+      // unit u = (plane u / NSUB, channels c0 + 16 * (u % NSUB) ..+15).  Thread 0 issues the TMA loads: two boxes of 8
+      // channels per unit, each from the tensor that holds those channels (the host guarantees that no box straddles
+      // the concatenation); everything outside the volume or beyond the channel count arrives as zeros.
+      constexpr int NSUB = Cfg::NSUB, NRAW = Cfg::NRAW, NRING = Cfg::NRING;
+      const int nunits = nsteps * NSUB;
+      auto issue = [&](int u) {
+        const int zi = z0 - 1 + u / NSUB, cu = a.c0 + 16 * (u % NSUB);
+        uint64_t* bar = &raw_full[u % NRAW];
+        float* dst = reinterpret_cast<float*>(rawbuf + (u % NRAW) * Cfg::RAW_SLOT_BYTES);
+        mbar_expect_tx(bar, (uint32_t)Cfg::RAW_SLOT_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = cu + 8 * j;
+          if (c < a.C1 || a.C2 == 0) tma_load_5d(dst + j * (Cfg::RAW_SLOT_BYTES / 8), &map1, bar, X0 - 4, Y0 - 1, zi, c, n);
+          else tma_load_5d(dst + j * (Cfg::RAW_SLOT_BYTES / 8), &map2, bar, X0 - 4, Y0 - 1, zi, c - a.C1, n);
+        }
+      };
+      if (tp == 0) {
+        tma_prefetch_desc(&map1);
+        if (a.C2) tma_prefetch_desc(&map2);
+        for (int u = 0; u < NRAW && u < nunits; ++u) issue(u);
+      }
+      // thread = one 8-channel chunk of the unit (grp) x 7 in-plane positions
+      constexpr int TPG = UM_NPROD / 2, PPT = UM_PLANE / TPG;
+      static_assert(TPG * 2 == UM_NPROD && PPT * TPG == UM_PLANE, "producer mapping must tile the plane exactly");
+      const int grp = tp / TPG, ti = tp - grp * TPG;
+      uint32_t roff[PPT];   // byte offset of the thread's positions in a raw channel: row hy, column 3 + hx (the box starts at x0 - 4)
+#pragma unroll
+      for (int b = 0; b < PPT; ++b) {
+        const int f = ti + TPG * b;
+        const int hy = f / UM_PX, hx = f - hy * UM_PX;
+        roff[b] = (uint32_t)(hy * UM_RAWX + hx + 3) * 4u;
+      }
+      constexpr uint32_t CHB = (UM_TY + 2) * UM_RAWX * 4;   // bytes of one raw channel
+      const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax)));
+      const uint32_t raw_s = smem_u32(rawbuf) + (uint32_t)grp * 8u * CHB;
+      const uint32_t ring_s = smem_u32(ring) + (uint32_t)(grp * UM_PFA + ti) * 16u;
+      for (int u = 0; u < nunits; ++u) {
+        const int rs = u % NRAW, slot = u % NRING;
+        mbar_wait(&raw_full[rs], (u / NRAW) & 1);
+        const uint32_t src = raw_s + (uint32_t)rs * Cfg::RAW_SLOT_BYTES;
+        float v[PPT][8];
+#pragma unroll
+        for (int b = 0; b < PPT; ++b)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[b][e] = lds_f32(src + roff[b] + (uint32_t)e * CHB);
+        if (u >= NRING) mbar_wait(&plane_empty[slot], ((u / NRING) - 1) & 1);
+        const uint32_t dst = ring_s + (uint32_t)slot * Cfg::SLOT_BYTES;
+#pragma unroll
+        for (int b = 0; b < PPT; ++b) {
+          uint4 h, l;
+          split_f16x2(v[b][0] * sc, v[b][1] * sc, h.x, l.x);
+          split_f16x2(v[b][2] * sc, v[b][3] * sc, h.y, l.y);
+          split_f16x2(v[b][4] * sc, v[b][5] * sc, h.z, l.z);
+          split_f16x2(v[b][6] * sc, v[b][7] * sc, h.w, l.w);
+          sts_v4(dst + (uint32_t)(TPG * b) * 16u, h);
+          sts_v4(dst + (uint32_t)(TPG * b + Cfg::SCH * UM_PFA) * 16u, l);
+        }
+        fence_proxy_async();
+        mbar_arrive(&plane_full[slot]);
+        // The raw slot is handed back to the TMA unit only now: the stores above consumed every value loaded from it,
+        // so no shared-memory read of this unit can still be queued when the asynchronous proxy overwrites the slot
+        // (a barrier placed right after the loads let a rare late read lose that race: 1 of ~300 test runs).
+        named_bar_sync(3, UM_NPROD);
+        if (tp == 0 && u + NRAW < nunits) issue(u + NRAW);
+      }
+    } else if constexpr (!BF) {
       int oxy[PPT];
 #pragma unroll
       for (int b = 0; b < PPT; ++b) {
@@ -382,6 +480,51 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     const uint64_t adesc0 = umma_desc(0, A_LBO, 128), bdesc0 = umma_desc(0, B_LBO, 128);
     long long t_acc = 0, t_plane = 0, t_issue = 0;
     const long long t_begin = DBG ? clock64() : 0;
+    if constexpr (Cfg::TMAIN) {
+      // unit by unit: the MMAs of unit u read ring slot u % NRING and weight chunks 2 * (u % NSUB), +1; the accumulator
+      // blocks rotate once per plane, so only the first unit of a plane waits for the epilogue and only the last one
+      // hands the finished block over
+      constexpr int NSUB = Cfg::NSUB, NRING = Cfg::NRING;
+      for (int pi = 0; pi < nsteps; ++pi) {
+        const uint32_t brot = sw_s + (uint32_t)(2 - pi % 3) * (NB * 16);
+        const long long t1 = DBG ? clock64() : 0;
+#pragma unroll 1
+        for (int sub = 0; sub < NSUB; ++sub) {
+          const int u = pi * NSUB + sub, slot = u % NRING;
+          const long long t0 = DBG ? clock64() : 0;
+          mbar_wait(&plane_full[slot], (u / NRING) & 1);
+          if (DBG) t_plane += clock64() - t0;
+          const uint32_t slot_s = ring_s + (uint32_t)slot * Cfg::SLOT_BYTES;
+#pragma unroll 1
+          for (int mt = 0; mt < UM_MT; ++mt) {
+            const long long t2 = DBG ? clock64() : 0;
+            if (sub == 0 && pi > 0) mbar_wait(&acc_empty[mt], (pi - 1) & 1);
+            if (DBG) t_acc += clock64() - t2;
+            tc_fence_after();
+            if (elected) {
+              const uint32_t dcol = tmem + (uint32_t)mt * N;
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t arow = slot_s + (uint32_t)(mt * UM_MSTEP + ky * UM_PX) * 16;
+                const uint32_t wt = brot + (uint32_t)(ky * NCH * UM_WROWS) * 16 + (uint32_t)(2 * sub) * B_LBO;
+                const uint64_t a_hi = umma_desc_at(adesc0, arow);
+                const uint64_t a_lo = umma_desc_at(adesc0, arow + Cfg::SCH * UM_PFA * 16);
+                const uint64_t b_hi = umma_desc_at(bdesc0, wt);
+                const uint64_t b_lo = umma_desc_at(bdesc0, wt + 3 * NCH * UM_WROWS * 16);
+                umma_ss<BF>(dcol, a_hi, b_hi, idesc, 1u);
+                umma_ss<BF>(dcol, a_lo, b_hi, idesc, 1u);
+                umma_ss<BF>(dcol, a_hi, b_lo, idesc, 1u);
+              }
+              if (sub == NSUB - 1) umma_commit(&acc_full[mt]);
+            }
+            __syncwarp();
+          }
+          if (elected) umma_commit(&plane_empty[slot]);
+          __syncwarp();
+        }
+        if (DBG) t_issue += clock64() - t1;
+      }
+    } else
     for (int pi = 0; pi < nsteps; ++pi) {
       const long long t0 = DBG ? clock64() : 0;
       mbar_wait(&plane_full[pi % 3], (pi / 3) & 1);
@@ -443,7 +586,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     float bv[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) bv[c] = (a.last && a.bias && co0 + ch0 + c < a.Cout) ? __ldg(a.bias + co0 + ch0 + c) : 0.f;
-    const bool do_act = a.last && a.act;
+    // fused activation as max(r, r * slope): leaky-ReLU / ReLU for 0 <= slope <= 1 (the host checks), identity at slope 1
+    const float slope_eff = (a.last && a.act) ? a.slope : 1.f;
+    const int nvc = max(0, min(8, a.Cout - co0 - ch0));   // valid output channels of this warp's half block
     // modes 1, 2: the operands were scaled by 2^kx and 2^kw; one exact multiplication undoes it (a combined exponent
     // below -126 means results under 2^-90: flushed to zero)
     float us = 1.f;
@@ -460,7 +605,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
     for (int c = 0; c < 8; ++c) pend[c] = 0.f;
     long long e_wait = 0, e_tmem = 0, e_bar = 0, e_out = 0;
     const long long e_begin = DBG ? clock64() : 0;
-    float* const obase = a.out + ((int64_t)n * a.Cout + co0 + ch0) * V + (int64_t)gy * a.W + gx;
+    // 32-bit element offsets into the output (N * Cout * V < 2^32, checked by the host): one IMAD + one 64-bit LEA per
+    // store instead of a 64-bit multiply-add chain.  Lanes outside the volume wrap around harmlessly: they never store.
+    const uint32_t Vu = (uint32_t)V, HWu = (uint32_t)HW;
+    const uint32_t obase = (uint32_t)(((int64_t)n * a.Cout + co0 + ch0) * V + (int64_t)gy * a.W + gx);
+    const bool st_main = valid && !edge_lane, st_edge = valid && (edge_lo || edge_hi);
     const int nb = edge_lo ? wg - 1 : wg + 1, side = edge_lo ? 0 : 1;   // indices, not pointers: keeps LDS addressing
     float e[8];
     // fetch the neighbouring warp's edge values of step `pstep` (issued early, consumed by store_edges after the TMEM phase)
@@ -473,27 +622,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
         for (int c = 0; c < 8; ++c) e[c] = edge_s[pstep & 1][nb][side][ch0 + c];
       }
     };
-    auto store_edges = [&](float* opp) {
-      if (edge_lo || edge_hi) {
+    auto store_edges = [&](uint32_t opp) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float r = pend[c];
-          if (do_act) r = r > 0.f ? r : r * a.slope;
-          if (valid && co0 + ch0 + c < a.Cout) opp[(int64_t)c * V] = r;
-        }
+      for (int c = 0; c < 8; ++c) {
+        const float r = fmaxf(pend[c], pend[c] * slope_eff);
+        if (st_edge && c < nvc) a.out[opp + (uint32_t)c * Vu] = r;
       }
-      __syncwarp();
     };
     for (int pi = 0; pi < nsteps; ++pi) {
       const int ol = pi - 2;                 // output plane completed by this step (local index), if >= 0
       const int blk = (pi + 1) % 3;          // = (pi - 2) mod 3
       const bool live = ol >= 0;             // ol < zcount always (nsteps = zcount + 2)
-      float* op = obase + (int64_t)(z0 + ol) * HW;
+      const uint32_t op = obase + (uint32_t)(z0 + ol) * HWu;
       if (ol > 0) fetch_edges(pi - 1);       // the previous plane's edge rows: their neighbours' values are a step old
-      // the previous chunks' partial output does not depend on this step's MMAs: fetch it before waiting for them
+      // the previous chunks' partial output does not depend on this step's MMAs: fetch it (+ the bias) before waiting
       float old[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) old[c] = (ACC && live && valid && co0 + ch0 + c < a.Cout) ? __ldcg(op + (int64_t)c * V) : 0.f;
+      for (int c = 0; c < 8; ++c) old[c] = ((ACC && live && valid && c < nvc) ? __ldcg(a.out + (op + (uint32_t)c * Vu)) : 0.f) + bv[c];
       const long long e0 = DBG ? clock64() : 0;
       mbar_wait(&acc_full[mt], pi & 1);
       const long long e1 = DBG ? clock64() : 0;
@@ -516,7 +661,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
       if (DBG) { e_wait += e1 - e0; e_tmem += clock64() - e1; }
       if (!live) continue;          // uniform over the CTA
       const long long e3 = DBG ? clock64() : 0;
-      if (ol > 0) store_edges(op - HW);
+      if (ol > 0) store_edges(op - HWu);
       if (lane == 31) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) edge_s[pi & 1][wg][0][ch0 + c] = BF ? v[0][c] * us : v[0][c];
@@ -533,12 +678,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
         if (lane == 0) left = 0.f;      // wrapped around: the true neighbour lives in another warp (added by store_edges)
         if (lane == 31) right = 0.f;
         float r = v[1][c] + left + right;
-        if constexpr (BF) r *= us;
-        r += old[c] + bv[c];
+        if constexpr (BF) r = fmaf(r, us, old[c]);
+        else r += old[c];
         pend[c] = r;
-        if (do_act) r = r > 0.f ? r : r * a.slope;
-        if (valid && !edge_lane && co0 + ch0 + c < a.Cout && !(a.flags & 1)) op[(int64_t)c * V] = r;
-        if ((a.flags & 1) && r == 1.2345e33f) op[(int64_t)c * V] = r;  // debug: keep the dependency, drop the store
+        r = fmaxf(r, r * slope_eff);
+        if (st_main && c < nvc) a.out[op + (uint32_t)c * Vu] = r;
       }
       if (DBG) e_out += clock64() - e3;
     }
@@ -547,7 +691,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) conv3d_umma_kernel(UmmaArgs a) 
 #pragma unroll
       for (int c = 0; c < 8; ++c) pend[c] += e[c];
     }
-    store_edges(obase + (int64_t)(z0 + nsteps - 3) * HW);
+    store_edges(obase + (uint32_t)(z0 + nsteps - 3) * HWu);
     if (DBG && a.dbg && threadIdx.x == 0) {
       atomicAdd(a.dbg + 9, (unsigned long long)e_bar); atomicAdd(a.dbg + 10, (unsigned long long)e_out);
       atomicAdd(a.dbg + 6, (unsigned long long)e_wait); atomicAdd(a.dbg + 7, (unsigned long long)e_tmem);
