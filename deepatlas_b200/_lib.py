@@ -59,6 +59,10 @@ SIGNATURES = {
     "da_conv3d_fwd": ("pipipippiiiiiiiiifpls", "rc"),
     "da_conv3d_dgrad": ("ppipiiiiiiiiiiipls", "rc"),
     "da_conv3d_wgrad": ("pipipippiiiiiiiipls", "rc"),
+    "da_absmax": ("plplps", "rc"),
+    "da_conv3d_fwd_ex": ("pipipippiiiiiiiiifplspi", "rc"),
+    "da_conv3d_dgrad_ex": ("ppipiiiiiiiiiiiplspi", "rc"),
+    "da_conv3d_wgrad_ex": ("pipipippiiiiiiiiplspipi", "rc"),
     "da_channel_sum_workspace_bytes": ("i", "size"),
     "da_channel_sum": ("piilppls", "rc"),
     # bn / act / pool / upsample

@@ -1001,8 +1001,11 @@ int launch_umma_mode(const UmmaArgs& a, const CUtensorMap& m1, const CUtensorMap
 }
 
 // weight source indexing arguments as for repack(); wp must hold umma_workspace_bytes(Cin, Cout)
+// amax_x: optional device slot with an upper bound of max|x1, x2| (valid) or to be filled here (!valid); null: a
+// workspace slot is used
 int run_conv_umma(const float* x1, const float* x2, const float* weight, int64_t wcount, float* wp, const float* bias, float* out,
-                  const ConvGeom& g, int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream) {
+                  const ConvGeom& g, int d1, int a_is_dim0, int flip, int b_off, cudaStream_t stream, float* amax_x = nullptr,
+                  int amax_x_valid = 0) {
   const int Cin = g.C1 + g.C2;
   constexpr int CB = UM_CB;
   const bool tf32 = split_tf32();
@@ -1018,14 +1021,20 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, int64_t
     // 3xFP16: per-tensor power-of-two scales from max|input| (both sources) and max|weight| (the whole tensor: every
     // output-channel block and a data gradient's channel slice share one scale)
     const int64_t V = (int64_t)g.Di * g.Hi * g.Wi;
-    rc = run_absmax(x1, (int64_t)g.N * g.C1 * V, 0, x2, (int64_t)g.N * g.C2 * V, 0, weight, wcount, 1, nullptr, 0, 0, amax, stream);
+    const bool have_x = amax_x && amax_x_valid;
+    rc = run_absmax(have_x ? nullptr : x1, (int64_t)g.N * g.C1 * V, 0, have_x ? nullptr : x2, (int64_t)g.N * g.C2 * V, 0, weight, wcount, 1,
+                    nullptr, 0, 0, amax, stream);
     if (rc) return rc;
-    umma_prep_weights16_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, reinterpret_cast<uint16_t*>(wp), d1, a_is_dim0, flip, Cin, g.Cout, b_off, last_nch, amax);
+    if (amax_x && !amax_x_valid) {   // hand the freshly computed bound to the caller's slot
+      cudaError_t e = cudaMemcpyAsync(amax_x, amax, sizeof(float), cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) { da_set_error("conv3d: amax copy failed: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    umma_prep_weights16_kernel<<<dim3(45, nk, nco), 256, 0, stream>>>(weight, reinterpret_cast<uint16_t*>(wp), d1, a_is_dim0, flip, Cin, g.Cout, b_off, last_nch, amax + 1);
   }
   rc = da_check_launch("umma_prep_weights");
   if (rc) return rc;
   UmmaArgs a;
-  a.amax = amax;
+  a.amax_x = (amax_x && amax_x_valid) ? amax_x : amax; a.amax_w = amax + 1;
   a.dbg = umma_dbg_buffer();
   { static int fl = -1; if (fl < 0) { const char* e = getenv("DA_UMMA_FLAGS"); fl = e ? atoi(e) : 0; } a.flags = fl; }
   a.x1 = x1; a.x2 = x2; a.C1 = g.C1; a.C2 = g.C2; a.bias = bias; a.out = out;
@@ -1190,9 +1199,54 @@ DA_API int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
 // weight: transposed==0 -> nn.Conv3d layout (Cout, C1+C2, k,k,k); transposed==1 -> nn.ConvTranspose3d layout
 // (C1+C2, Cout, k,k,k), only k3 s1 p1 (equivalent to a conv with the flipped kernel).
 // bias nullable.  act: 0 none, 1 leaky-relu(slope) fused (slope 0 = ReLU).  out [N,Cout,Do,Ho,Wo].
+DA_API int da_conv3d_fwd_ex(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed, const float* bias,
+                            float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride, int pad, int act, float slope,
+                            void* workspace, int64_t workspace_bytes, cudaStream_t stream, float* amax_x, int amax_x_valid);
+DA_API int da_conv3d_dgrad_ex(const float* dy, const float* weight, int transposed, float* dx, int N, int Cin_total, int ci_off, int Cdx,
+                              int Cout, int Di, int Hi, int Wi, int ks, int stride, int pad, void* workspace, int64_t workspace_bytes,
+                              cudaStream_t stream, float* amax_dy, int amax_dy_valid);
+DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed, float* grad_weight,
+                              float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride, int pad, void* workspace,
+                              int64_t workspace_bytes, cudaStream_t stream, float* amax_x, int amax_x_valid, float* amax_dy,
+                              int amax_dy_valid);
+
+namespace {
+// fills the caller's max-abs slot when the chosen kernel did not need it itself (the _ex contract: a slot passed with
+// valid = 0 always holds the bound afterwards)
+inline int fill_amax_slot(float* slot, const float* p1, int64_t n1, const float* p2, int64_t n2, cudaStream_t stream) {
+  float* tmp = slot;   // run_absmax zeroes four floats: go through the slot only if it is the head of such a block
+  cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(float), stream);
+  if (e != cudaSuccess) { da_set_error("absmax: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+  AbsmaxArgs a;
+  a.p[0] = p1; a.n[0] = p1 ? n1 : 0; a.slot[0] = 0; a.p[1] = p2; a.n[1] = p2 ? n2 : 0; a.slot[1] = 0;
+  a.p[2] = nullptr; a.n[2] = 0; a.slot[2] = 0; a.p[3] = nullptr; a.n[3] = 0; a.slot[3] = 0;
+  int64_t nb = da_cdiv(a.n[0] + a.n[1], 256 * 16);
+  if (nb > 8 * DA_NUM_SMS) nb = 8 * DA_NUM_SMS;
+  if (nb < 1) nb = 1;
+  absmax_kernel<<<(unsigned)nb, 256, 0, stream>>>(a, tmp);
+  return da_check_launch("absmax");
+}
+}  // namespace
+
+DA_API int da_absmax(const float* x1, int64_t n1, const float* x2, int64_t n2, float* out, cudaStream_t stream) {
+  DA_REQUIRE(x1 && out, "da_absmax: null pointer");
+  return fill_amax_slot(out, x1, n1, x2, n2, stream);
+}
+
 DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed,
                          const float* bias, float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride,
                          int pad, int act, float slope, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return da_conv3d_fwd_ex(x1, C1, x2, C2, weight, transposed, bias, out, N, Di, Hi, Wi, Cout, ks, stride, pad, act, slope, workspace,
+                          workspace_bytes, stream, nullptr, 0);
+}
+
+// The same with a caller-owned max-abs slot for the input (one device float: an upper bound of max|x1, x2|).
+// amax_x_valid = 1: the slot already holds the bound (a producer kernel or an earlier call computed it) and the input
+// pass of the tensor-core path is skipped; 0: the slot is filled by this call, whatever kernel runs.
+DA_API int da_conv3d_fwd_ex(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed,
+                            const float* bias, float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride,
+                            int pad, int act, float slope, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
+                            float* amax_x, int amax_x_valid) {
   DA_REQUIRE(x1 && weight && out && workspace, "da_conv3d_fwd: null pointer");
   DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_fwd: unsupported kernel size %d (1 or 3)", ks);
   DA_REQUIRE(stride == 1 || stride == 2, "da_conv3d_fwd: unsupported stride %d", stride);
@@ -1207,9 +1261,17 @@ DA_API int da_conv3d_fwd(const float* x1, int C1, const float* x2, int C2, const
     const int rc1 = run_conv1x1_stream(x1, x2, C1, C2, weight, Cin, 1, bias, out, N, Cout, (int64_t)Di * Hi * Wi, act, slope, stream);
     if (rc1 >= 0) return rc1;
   }
+  if (ks == 3 && aligned16(wp) && fwd_umma_ok(g) && !(split_tf32() && amax_x && !amax_x_valid))
+    return transposed ? run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cout, 1, 1, 0, stream, amax_x, amax_x_valid)
+                      : run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cin, 0, 0, 0, stream, amax_x, amax_x_valid);
+  if (amax_x && !amax_x_valid) {
+    const int64_t Vi = (int64_t)Di * Hi * Wi;
+    const int rca = fill_amax_slot(amax_x, x1, (int64_t)N * C1 * Vi, x2, (int64_t)N * C2 * Vi, stream);
+    if (rca) return rca;
+  }
   if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
-    return transposed ? run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cout, 1, 1, 0, stream)
-                      : run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cin, 0, 0, 0, stream);
+    return transposed ? run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cout, 1, 1, 0, stream, amax_x, 1)
+                      : run_conv_umma(x1, x2, weight, (int64_t)Cin * Cout * 27, wp, bias, out, g, Cin, 0, 0, 0, stream, amax_x, 1);
   if (ks == 3 && aligned16(wp) && fwd_tma_ok(x1, x2, out, g))
     return transposed ? run_conv_tma(x1, x2, weight, wp, bias, out, g, Cin, Cout, 1, 1, 0, stream)
                       : run_conv_tma(x1, x2, weight, wp, bias, out, g, Cout, Cin, 0, 0, 0, stream);
@@ -1248,6 +1310,14 @@ __global__ void __launch_bounds__(256) zero_insert2_kernel(const float* __restri
 DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed, float* dx, int N, int Cin_total,
                            int ci_off, int Cdx, int Cout, int Di, int Hi, int Wi, int ks, int stride, int pad,
                            void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return da_conv3d_dgrad_ex(dy, weight, transposed, dx, N, Cin_total, ci_off, Cdx, Cout, Di, Hi, Wi, ks, stride, pad, workspace,
+                            workspace_bytes, stream, nullptr, 0);
+}
+
+// amax_dy: caller-owned max-abs slot of dy, as amax_x of da_conv3d_fwd_ex
+DA_API int da_conv3d_dgrad_ex(const float* dy, const float* weight, int transposed, float* dx, int N, int Cin_total,
+                              int ci_off, int Cdx, int Cout, int Di, int Hi, int Wi, int ks, int stride, int pad,
+                              void* workspace, int64_t workspace_bytes, cudaStream_t stream, float* amax_dy, int amax_dy_valid) {
   DA_REQUIRE(dy && weight && dx && workspace, "da_conv3d_dgrad: null pointer");
   DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_dgrad: unsupported kernel size %d", ks);
   DA_REQUIRE(stride == 1 || (stride == 2 && ks == 3 && pad == 1 && !transposed), "da_conv3d_dgrad: unsupported stride/kernel");
@@ -1256,6 +1326,11 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
   const int Do = conv_out(Di, ks, stride, pad), Ho = conv_out(Hi, ks, stride, pad), Wo = conv_out(Wi, ks, stride, pad);
   float* wp = (float*)workspace;
   const int Cp = cpad(Cdx);
+  if (amax_dy && !amax_dy_valid) {   // one pass over dy itself (the stride-2 path below would otherwise scan its zero-inserted copy)
+    const int rca = fill_amax_slot(amax_dy, dy, (int64_t)N * Cout * Do * Ho * Wo, nullptr, 0, stream);
+    if (rca) return rca;
+    amax_dy_valid = 1;
+  }
   if (stride == 1) {
     // dgrad = conv of dy (Cout channels) with [co][flip tap][ci]; for a transposed layer: no flip, dims swapped
     ConvGeom g{N, Cout, 0, Do, Ho, Wo, Di, Hi, Wi, Cdx, Cp, 1, ks == 3 ? 1 : 0, 0, 0.f};
@@ -1265,8 +1340,8 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
       if (rc1 >= 0) return rc1;
     }
     if (ks == 3 && aligned16(wp) && fwd_umma_ok(g))
-      return transposed ? run_conv_umma(dy, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cout, 0, 0, ci_off, stream)
-                        : run_conv_umma(dy, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
+      return transposed ? run_conv_umma(dy, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cout, 0, 0, ci_off, stream, amax_dy, amax_dy_valid)
+                        : run_conv_umma(dy, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream, amax_dy, amax_dy_valid);
     if (ks == 3 && aligned16(wp) && fwd_tma_ok(dy, nullptr, dx, g))
       return transposed ? run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cin_total, Cout, 0, 0, ci_off, stream)
                         : run_conv_tma(dy, nullptr, weight, wp, nullptr, dx, g, Cout, Cin_total, 1, 1, ci_off, stream);
@@ -1290,7 +1365,13 @@ DA_API int da_conv3d_dgrad(const float* dy, const float* weight, int transposed,
       zero_insert2_kernel<<<(unsigned)nb, 256, 0, stream>>>(dy, dyz, (int64_t)N * Cout, Do, Ho, Wo);
       int rc = da_check_launch("conv3d_dgrad_s2/zero_insert");
       if (rc) return rc;
-      return run_conv_umma(dyz, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream);
+      if (!amax_dy && !split_tf32()) {   // no caller slot: bound dy (not its 8x larger zero-inserted copy) into a spare workspace float
+        amax_dy = reinterpret_cast<float*>(reinterpret_cast<char*>(wp) + pack - 64);
+        const int rca = fill_amax_slot(amax_dy, dy, (int64_t)N * Cout * Do * Ho * Wo, nullptr, 0, stream);
+        if (rca) return rca;
+        amax_dy_valid = 1;
+      }
+      return run_conv_umma(dyz, nullptr, weight, (int64_t)Cin_total * Cout * 27, wp, nullptr, dx, g, Cin_total, 1, 1, ci_off, stream, amax_dy, amax_dy_valid);
     }
   }
   int rc = repack(weight, wp, Cout, Cin_total, T, 1, 0, Cout, 0, Cdx, ci_off, Cp, stream);
@@ -1314,7 +1395,8 @@ inline bool wgrad_umma_ok(int N, int D, int H, int W) {
 }
 
 int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed, float* grad_weight,
-                   float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, float* partials, int cap, cudaStream_t stream) {
+                   float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, float* partials, int cap, cudaStream_t stream,
+                   float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid) {
   const int Cin = C1 + C2;
   const int64_t count = (int64_t)Cin * Cout * 27;
   const int tiles_x = (Wi + WU_XT - 1) / WU_XT, tiles_y = (Hi + WU_YT - 1) / WU_YT;
@@ -1366,12 +1448,22 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     CUtensorMap mh1, mh2, mp1, mp2;
     if (bf16) {
       // per-tensor scales: slot 0 = halo-side tensors, slot 1 = plain-side tensors; the slots sit behind the partials
+      // (caller-owned slots with valid bounds replace the passes; slots passed as not valid are filled)
       float* amax = partials + (int64_t)cap * count + (int64_t)WG_MAX_REGIONS * (Cin > Cout ? Cin : Cout);
       const int64_t V = (int64_t)Di * Hi * Wi;
-      rc = run_absmax(h1, (int64_t)N * a.H1 * V, 0, h2, (int64_t)N * a.H2 * V, 0, p1, (int64_t)N * a.P1 * V, 1, p2, (int64_t)N * a.P2 * V, 1, amax,
-                      stream);
-      if (rc) return rc;
-      a.amax = amax;
+      float* amax_hs = transposed ? amax_dy : amax_x; const int hs_valid = transposed ? amax_dy_valid : amax_x_valid;
+      float* amax_ps = transposed ? amax_x : amax_dy; const int ps_valid = transposed ? amax_x_valid : amax_dy_valid;
+      const bool have_h = amax_hs && hs_valid, have_p = amax_ps && ps_valid;
+      if (!have_h || !have_p) {
+        rc = run_absmax(have_h ? nullptr : h1, (int64_t)N * a.H1 * V, 0, have_h ? nullptr : h2, (int64_t)N * a.H2 * V, 0,
+                        have_p ? nullptr : p1, (int64_t)N * a.P1 * V, 1, have_p ? nullptr : p2, (int64_t)N * a.P2 * V, 1, amax, stream);
+        if (rc) return rc;
+        cudaError_t e = cudaSuccess;
+        if (amax_hs && !hs_valid) e = cudaMemcpyAsync(amax_hs, amax, sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess && amax_ps && !ps_valid) e = cudaMemcpyAsync(amax_ps, amax + 1, sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        if (e != cudaSuccess) { da_set_error("conv3d_wgrad: amax copy failed: %s", cudaGetErrorString(e)); return (int)e; }
+      }
+      a.amax_h = have_h ? amax_hs : amax; a.amax_p = have_p ? amax_ps : amax + 1;
       rc = da_make_volume_map_xcy(&mh1, h1, N, a.H1, Di, Hi, Wi, WB_XBOX, cib, 4);
       if (!rc) rc = a.H2 ? da_make_volume_map_xcy(&mh2, h2, N, a.H2, Di, Hi, Wi, WB_XBOX, cib, 4) : (mh2 = mh1, 0);
       if (!rc) rc = da_make_volume_map_xcy(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 16, 6);
@@ -1441,6 +1533,16 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
 DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
                            float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                            int stride, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return da_conv3d_wgrad_ex(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, ks, stride, pad, workspace,
+                            workspace_bytes, stream, nullptr, 0, nullptr, 0);
+}
+
+// amax_x / amax_dy: caller-owned max-abs slots of cat(x1, x2) and of dy, as in da_conv3d_fwd_ex.  Here a slot passed as
+// not valid is filled only if the tensor-core kernel runs (nothing downstream of a weight gradient reuses it).
+DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
+                              float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
+                              int stride, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
+                              float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid) {
   DA_REQUIRE(x1 && dy && grad_weight && workspace, "da_conv3d_wgrad: null pointer");
   DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_wgrad: unsupported kernel size %d", ks);
   DA_REQUIRE(!transposed || (ks == 3 && stride == 1 && pad == 1), "da_conv3d_wgrad: transposed only for k3 s1 p1");
@@ -1463,7 +1565,8 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
     const int tpr = (ntiles + nregions - 1) / nregions;
     nregions = (ntiles + tpr - 1) / tpr;
     if (wgrad_umma_ok(N, Di, Hi, Wi))
-      return run_wgrad_umma(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, partials, cap, stream);
+      return run_wgrad_umma(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, partials, cap, stream, amax_x,
+                            amax_x_valid, amax_dy, amax_dy_valid);
     float* bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
     static DaPerDeviceOnce configured;
     if (configured.first()) {

@@ -65,10 +65,14 @@ struct UmmaCfg {
   static constexpr int KC = EPC * NCH;                               // input channels per launch: 16, 32, 16, 32, 16
   static constexpr int SCH = TMAIN ? 2 : NCH;                        // K chunks per ring slot (TMA modes: one 16-channel unit)
   static constexpr int NSUB = NCH / SCH;                             // units per plane
-  static constexpr int NRING = (MODE == 3) ? 2 : 3;
+#ifndef DA_M3_RING
+#define DA_M3_RING 2
+#define DA_M3_RAW 3
+#endif
+  static constexpr int NRING = (MODE == 3) ? DA_M3_RING : 3;
   static constexpr int SLOT_BYTES = 2 * SCH * UM_PFA * 16;           // hi + lo
   static constexpr int RING_BYTES = NRING * SLOT_BYTES;
-  static constexpr int NRAW = TMAIN ? (MODE == 3 ? 3 : 4) : 0;       // raw fp32 units in flight
+  static constexpr int NRAW = TMAIN ? (MODE == 3 ? DA_M3_RAW : 4) : 0;       // raw fp32 units in flight
   static constexpr int RAW_SLOT_BYTES = 16 * (UM_TY + 2) * UM_RAWX * 4;   // [16 ch][8 rows][48 x]
   static constexpr int RAW_BYTES = NRAW * RAW_SLOT_BYTES;
   static constexpr int W_BYTES = 2 * 3 * NCH * UM_WROWS * 16;        // [hi|lo][ky][ci/EPC][row][16 bytes]
@@ -84,7 +88,8 @@ struct UmmaArgs {
   const float* x1; const float* x2; int C1, C2;
   const float* wimg;          // prepared weight image of (co block 0, this channel chunk); block ib is img_stride floats further
                               // (fp32 hi/lo in mode 0, scaled fp16 hi/lo otherwise)
-  const float* amax;          // modes 1, 2: device pointer to {max|input|, max|weight|} (absmax_kernel), which fix the scales
+  const float* amax_x;        // modes 1-4: device pointers to an upper bound of max|input| and to max|weight| (absmax_kernel),
+  const float* amax_w;        // which fix the power-of-two scales of the two operands
   int64_t img_stride; int nco; // output-channel blocks of the layer = blockIdx.z % nco
   const float* bias; float* out;
   int N, D, H, W, Cout;
@@ -337,7 +342,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
         roff[b] = (uint32_t)(hy * UM_RAWX + hx + 3) * 4u;
       }
       constexpr uint32_t CHB = (UM_TY + 2) * UM_RAWX * 4;   // bytes of one raw channel
-      const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax)));
+      const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax_x)));
       const uint32_t raw_s = smem_u32(rawbuf) + (uint32_t)grp * 8u * CHB;
       const uint32_t ring_s = smem_u32(ring) + (uint32_t)(grp * UM_PFA + ti) * 16u;
       for (int u = 0; u < nunits; ++u) {
@@ -428,7 +433,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
       constexpr int BATCH = 7, NBATCH = PPT / BATCH;   // 56 loads in flight per thread
       static_assert(NBATCH * BATCH == PPT, "load batches must tile the thread's positions");
       const int Vi = (int)V;   // 8 * V < 2^31 (checked by the host): 32-bit element offsets, no per-channel pointers
-      const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax)));
+      const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax_x)));
       for (int pi = 0; pi < nsteps; ++pi) {
         const int slot = pi % 3, use = pi / 3;
         if (use > 0) mbar_wait(&plane_empty[slot], (use - 1) & 1);
@@ -592,7 +597,7 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
     // modes 1, 2: the operands were scaled by 2^kx and 2^kw; one exact multiplication undoes it (a combined exponent
     // below -126 means results under 2^-90: flushed to zero)
     float us = 1.f;
-    if constexpr (BF) us = pow2f(max(-126, -(scale_exp_from_amax(__ldg(a.amax)) + scale_exp_from_amax(__ldg(a.amax + 1)))));
+    if constexpr (BF) us = pow2f(max(-126, -(scale_exp_from_amax(__ldg(a.amax_x)) + scale_exp_from_amax(__ldg(a.amax_w)))));
     // The kx fold needs row f-1 (tap 0) and f+1 (tap 2).  Inside a warp they come by shuffle; the two rows at the warp's
     // ends need the neighbouring warp's edge values, which travel through shared memory.  A store -> barrier -> load
     // chain inside the step cost 1k of its 4.7k cycles (shared memory is saturated by the MMA operand fetch, every round
@@ -741,12 +746,12 @@ __global__ void umma_prep_weights_kernel(const float* __restrict__ src, float* _
 // be a 16-channel one, last_nch = 2):  [hi|lo][ky][ci/8][row = t*48 + kx*16 + co][8 halves], image (ib, ik) at
 // dst + (ib * nk + ik) * UMMA_IMG_STRIDE_BYTES.  Chunk ik starts at input channel 32 * ik.  amax[1] = max|weight|.
 __global__ void umma_prep_weights16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int d1, int a_is_dim0, int flip,
-                                           int A, int B, int b_off, int last_nch, const float* __restrict__ amax) {
+                                           int A, int B, int b_off, int last_nch, const float* __restrict__ amax_w) {
   const int ik = blockIdx.y, c0 = ik * 32, co0 = blockIdx.z * UM_CB;
   const int nch = (ik == (int)gridDim.y - 1) ? last_nch : 4;
   dst += (int64_t)(blockIdx.z * gridDim.y + ik) * (UMMA_IMG_STRIDE_BYTES / 2);
   const int half = 3 * nch * UM_WROWS * 8;   // elements of the hi (or lo) part
-  const float sc = pow2f(scale_exp_from_amax(__ldg(amax + 1)));
+  const float sc = pow2f(scale_exp_from_amax(__ldg(amax_w)));
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x) {
     const int e = i & 7;
     int r = i >> 3;

@@ -272,7 +272,8 @@ struct WgUmmaTmaArgs {
   int tiles_x, tiles_y;
   int ncols, zlen, nunits;  // work unit = (column, z segment of zlen planes); unit u -> CTA u % gridDim.y
   float* bias_partials;     // nullable: [region][P1+P2] sums of the plain-side tensor (= bias gradient when that is dY)
-  const float* amax;        // 3xFP16 kernel: device pointer to {max|halo-side tensors|, max|plain-side tensors|} (absmax_kernel)
+  const float* amax_h;      // 3xFP16 kernel: device pointers to upper bounds of max|halo-side tensors| and
+  const float* amax_p;      // max|plain-side tensors| (absmax_kernel), which fix the power-of-two scales
   unsigned long long* dbg;  // optional cycle counters (DA_UMMA_DEBUG=1, 3xFP16 kernel): MMA warp waiting for operands / total,
                             // B producer warp waiting for raw tiles / for a free stage / total, TMA thread waiting, tiles
 };
@@ -672,7 +673,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     // translation-invariant loss sums to ~0 over the volume (flow.bias): fp64 across the thread's tiles keeps the
     // cancellation from amplifying fp32 round-off (one DADD per tile)
     double bsum = 0.0;
-    const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax + 1)));
+    const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax_p)));
     long long d_raw = 0, d_empty = 0;
     const long long d_begin = DBG ? clock64() : 0;
     for (int u = region; u < a.nunits; u += R) {
@@ -726,7 +727,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     constexpr int NT = 17 * CIB;                       // blocks 0..16 carry data (rows t <= 2 of pairs 0..7)
     constexpr int TPT = (NT + 32 * Cfg::NAW - 1) / (32 * Cfg::NAW);
     const int ta0 = (warp - 14) * 32 + lane;
-    const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax)));
+    const float sc = pow2f(scale_exp_from_amax(__ldg(a.amax_h)));
     for (int k = 0; k < ntl; ++k) {
       const int s = k & 1, use = k >> 1;
       mbar_wait(&rawfull[k % WB_NR], (k / WB_NR) & 1);
@@ -772,7 +773,7 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
     const int r = (warp - 4) * 32 + lane;   // TMEM lane = accumulator row; warp 4 + i reads lane quadrant i
     const int kx = r / CIB, ci = cib * CIB + r % CIB;
     float* pr = a.partials + (int64_t)region * a.region_stride;
-    const float us = pow2f(max(-126, -(scale_exp_from_amax(__ldg(a.amax)) + scale_exp_from_amax(__ldg(a.amax + 1)))));
+    const float us = pow2f(max(-126, -(scale_exp_from_amax(__ldg(a.amax_h)) + scale_exp_from_amax(__ldg(a.amax_p)))));
 #pragma unroll 1
     for (int g = 0; g < 9; ++g) {
       float v16[16];

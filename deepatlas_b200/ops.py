@@ -402,9 +402,13 @@ class Conv3dFunction(torch.autograd.Function):
         out = torch.empty((N, Cout, Do, Ho, Wo), dtype=torch.float32, device=x1.device)
         nb = _lib.size("da_conv3d_pack_bytes", Cin, Cout, ks)
         ws = _ws(nb, x1.device)
-        _lib.call("da_conv3d_fwd", _p(x1), C1, _p(x2), C2, _p(weight), int(transposed), _p(bias), _p(out), N, Di,
+        # max|input|: the tensor-core kernels scale their fp16 operand pairs by it; computed once here (the call fills
+        # the slot) and reused by the weight gradient in backward
+        amax_x = torch.empty((1,), dtype=torch.float32, device=x1.device)
+        _lib.call("da_conv3d_fwd_ex", _p(x1), C1, _p(x2), C2, _p(weight), int(transposed), _p(bias), _p(out), N, Di,
                   Hi, Wi, Cout, ks, stride, pad, 0 if slope is None else 1, 0.0 if slope is None else float(slope),
-                  _p(ws), nb, _stream())
+                  _p(ws), nb, _stream(), _p(amax_x), 0)
+        ctx.amax_x = amax_x
         ctx.save_for_backward(x1, x2, weight, out if slope is not None else None)
         ctx.cfg = (bool(transposed), ks, stride, pad, slope, bias is not None, Cout)
         return out
@@ -425,21 +429,25 @@ class Conv3dFunction(torch.autograd.Function):
         dx1 = dx2 = dw = db = None
         nb = _lib.size("da_conv3d_dgrad_workspace_bytes", N, Cin, Cout, Di, Hi, Wi, ks, stride)
         ws = _ws(nb, dy.device)
+        amax_dy = torch.empty((1,), dtype=torch.float32, device=dy.device)   # filled by the first call that takes it
+        dy_valid = 0
         if ctx.needs_input_grad[0]:
             dx1 = torch.empty_like(x1)
-            _lib.call("da_conv3d_dgrad", _p(dy), _p(weight), int(transposed), _p(dx1), N, Cin, 0, C1, Cout, Di, Hi,
-                      Wi, ks, stride, pad, _p(ws), nb, st)
+            _lib.call("da_conv3d_dgrad_ex", _p(dy), _p(weight), int(transposed), _p(dx1), N, Cin, 0, C1, Cout, Di, Hi,
+                      Wi, ks, stride, pad, _p(ws), nb, st, _p(amax_dy), dy_valid)
+            dy_valid = 1
         if x2 is not None and ctx.needs_input_grad[1]:
             dx2 = torch.empty_like(x2)
-            _lib.call("da_conv3d_dgrad", _p(dy), _p(weight), int(transposed), _p(dx2), N, Cin, C1, C2, Cout, Di, Hi,
-                      Wi, ks, stride, pad, _p(ws), nb, st)
+            _lib.call("da_conv3d_dgrad_ex", _p(dy), _p(weight), int(transposed), _p(dx2), N, Cin, C1, C2, Cout, Di, Hi,
+                      Wi, ks, stride, pad, _p(ws), nb, st, _p(amax_dy), dy_valid)
+            dy_valid = 1
         if ctx.needs_input_grad[2] or (has_bias and ctx.needs_input_grad[3]):
             dw = torch.empty_like(weight)
             db = torch.empty((Cout,), dtype=torch.float32, device=dy.device) if has_bias else None
             nbw = _lib.size("da_conv3d_wgrad_workspace_bytes", Cin, Cout, ks)
             wsw = _ws(nbw, dy.device)
-            _lib.call("da_conv3d_wgrad", _p(x1), C1, _p(x2), C2, _p(dy), int(transposed), _p(dw), _p(db), N, Di, Hi,
-                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, st)
+            _lib.call("da_conv3d_wgrad_ex", _p(x1), C1, _p(x2), C2, _p(dy), int(transposed), _p(dw), _p(db), N, Di, Hi,
+                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, st, _p(ctx.amax_x), 1, _p(amax_dy), dy_valid)
         return dx1, dx2, dw, db, None, None, None, None
 
 

@@ -132,6 +132,22 @@ int da_conv3d_dgrad(const float* dy, const float* weight, int transposed, float*
 int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
                     float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                     int stride, int pad, void* workspace, int64_t workspace_bytes, da_stream_t stream);
+/* The three calls above with caller-owned max-abs slots (one device float each, an upper bound of max|tensor|): the
+ * tensor-core kernels scale their fp16 operand pairs per tensor by a power of two derived from it.  valid = 1: the slot
+ * already holds the bound (da_absmax, an earlier _ex call on the same tensor, or a producer kernel); valid = 0: this
+ * call fills it (da_conv3d_wgrad_ex: only when its tensor-core kernel runs).  NULL slots = the plain calls. */
+int da_absmax(const float* x1, int64_t n1, const float* x2, int64_t n2, float* out, da_stream_t stream); /* out[0] = max(|x1|, |x2|); x2 may be NULL */
+int da_conv3d_fwd_ex(const float* x1, int C1, const float* x2, int C2, const float* weight, int transposed,
+                     const float* bias, float* out, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride,
+                     int pad, int act, float slope, void* workspace, int64_t workspace_bytes,
+                     da_stream_t stream, float* amax_x, int amax_x_valid);
+int da_conv3d_dgrad_ex(const float* dy, const float* weight, int transposed, float* dx, int N, int Cin_total,
+                       int ci_off, int Cdx, int Cout, int Di, int Hi, int Wi, int ks, int stride, int pad,
+                       void* workspace, int64_t workspace_bytes, da_stream_t stream, float* amax_dy, int amax_dy_valid);
+int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
+                       float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
+                       int stride, int pad, void* workspace, int64_t workspace_bytes, da_stream_t stream,
+                       float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid);
 int64_t da_channel_sum_workspace_bytes(int C);
 int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* workspace, int64_t workspace_bytes,
                    da_stream_t stream);

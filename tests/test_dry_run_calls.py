@@ -95,4 +95,4 @@ def test_hot_path_argument_lists(dry):
     batch = make_synthetic_pair((16, 16, 16), 4, seed=230, device="cpu")
     loss, _ = model.joint_loss(*batch)
     loss.backward()
-    assert "da_conv3d_fwd" in dry and "da_warp_dice_sums_bwd" in dry and "da_lncc_bwd" in dry
+    assert "da_conv3d_fwd_ex" in dry and "da_conv3d_wgrad_ex" in dry and "da_warp_dice_sums_bwd" in dry and "da_lncc_bwd" in dry
