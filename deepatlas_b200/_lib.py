@@ -37,6 +37,10 @@ SIGNATURES = {
     "da_softmax_dice_fwd": ("ppiiilpppls", "rc"),
     "da_softmax_dice_bwd": ("ppiiilppppps", "rc"),
     "da_softmax_bwd": ("pppiils", "rc"),
+    "da_head_dice_supported": ("iil", "size"),
+    "da_head_dice_workspace_bytes": ("iil", "size"),
+    "da_head_dice_fwd": ("ppppiiiilpppls", "rc"),
+    "da_head_dice_bwd": ("ppppiiiilpppppppls", "rc"),
     "da_argmax_counts": ("ppiiilpps", "rc"),
     # lncc
     "da_lncc_coef_bytes": ("iiiiii", "size"),

@@ -48,21 +48,34 @@ class JointModel(nn.Module):
     def joint_loss(self, I_m, S_m, I_t, S_t):
         """I_*: (1,1,D,H,W) fp32 images; S_*: (1,D,H,W) integer label maps (uint8 is read directly)."""
         lam = self.lambdas
-        P_m = self.seg(I_m)
-        P_t = self.seg(I_t)
-        disp, I_w, phi = self.reg(I_m, I_t)
-        # softmax(P_m) has two consumers (supervised Dice, anatomy term): one pass yields the Dice sums AND the
-        # probabilities, and one backward pass takes both gradients (no separate softmax, no sum of two 629 MB gradients)
-        if os.environ.get("DA_JOINT_UNFUSED") == "1":   # A/B switch: separate softmax and Dice passes
-            sup_m, prob_m = self.sup_dice(P_m, S_m), ops.softmax(P_m)
+        mode = os.environ.get("DA_JOINT_UNFUSED", "0")   # A/B switch: 1 = separate softmax and Dice passes, 2 = unfused head
+        fuse_head = mode == "0" and hasattr(self.seg, "forward_features") and not getattr(self.seg, "res", False)
+        if fuse_head:
+            # the class head, softmax and the Dice sums as one kernel each way: the 32-class logits (629 MB per volume at
+            # 160x192x160) and their gradient never reach HBM; for the moving image the same pass writes the
+            # probabilities that the anatomy term warps, and the backward takes both of their gradients
+            F_m = self.seg.forward_features(I_m)
+            F_t = self.seg.forward_features(I_t)
+            disp, I_w, phi = self.reg(I_m, I_t)
+            sup_m, prob_m = self.sup_dice.forward_head(F_m, self.seg.head, S_m, want_probs=True)
+            sup_t, _ = self.sup_dice.forward_head(F_t, self.seg.head, S_t)
         else:
-            sup_m, prob_m = self.sup_dice.forward_with_probs(P_m, S_m)
+            P_m = self.seg(I_m)
+            P_t = self.seg(I_t)
+            disp, I_w, phi = self.reg(I_m, I_t)
+            # softmax(P_m) has two consumers (supervised Dice, anatomy term): one pass yields the Dice sums AND the
+            # probabilities, and one backward pass takes both gradients (no separate softmax, no sum of two gradients)
+            if mode == "1":
+                sup_m, prob_m = self.sup_dice(P_m, S_m), ops.softmax(P_m)
+            else:
+                sup_m, prob_m = self.sup_dice.forward_with_probs(P_m, S_m)
+            sup_t = self.sup_dice(P_t, S_t)
         parts = {
             "sim": self.sim_loss(I_w, I_t),
             "reg": self.reg_loss(disp),
             # dice(grid_sample(softmax(P_m), phi), onehot(S_t)): warp and Dice sums fused, labels stand for the one-hot
             "ana": self.ana_dice.forward_warped(prob_m, phi, S_t),
-            "sup": sup_m + self.sup_dice(P_t, S_t),
+            "sup": sup_m + sup_t,
         }
         loss = lam["sim"] * parts["sim"] + lam["reg"] * parts["reg"] + lam["ana"] * parts["ana"] + lam["sup"] * parts["sup"]
         return loss, parts

@@ -53,6 +53,31 @@ class DiceLossMultiClass(nn.Module):
         sums, probs = ops.softmax_dice(source, target)
         return self._closing(sums), probs
 
+    def forward_head(self, features, head, target, want_probs=False):
+        """``forward(head(features), target)`` (and ``softmax(head(features))`` with ``want_probs``) for a softmax=True
+        loss, a 1x1x1 convolution ``head`` (unets.py:250) and a label-mask target, without materialising the logits:
+        head, softmax and Dice sums run as one kernel each way.  Falls back to the separate calls where the fused kernel
+        does not apply (head inputs != 16, more than 32 classes, an odd voxel count, a soft target)."""
+        if not self.softmax:
+            raise ValueError("forward_head needs softmax=True (the head produces logits)")
+        N, K = features.shape[:2]
+        V = features[0, 0].numel()
+        C = head.weight.shape[0]
+        fused = (not target.is_floating_point() and target.dim() == features.dim() - 1 and tuple(head.weight.shape[2:]) == (1, 1, 1)
+                 and ops.head_dice_supported(K, C, V))
+        if not fused:
+            logits = head(features)
+            if want_probs:
+                return self.forward_with_probs(logits, target)
+            return self.forward(logits, target), None
+        assert features.shape[0] == target.shape[0] and tuple(features.shape[-3:]) == tuple(target.shape[-3:])
+        if self.weight_type not in ("Simple", "Volume", "Uniform"):
+            raise ValueError("Class weighting type {} does not exists!".format(self.weight_type))
+        if self.n_class is None:
+            self.n_class = C
+        sums, probs = ops.head_softmax_dice(features, head.weight, head.bias, target, want_probs)
+        return self._closing(sums), probs
+
     def forward_warped(self, source, deform_field, target):
         """``forward(grid_sample(source, deform_field), target)`` for a label-mask ``target`` and probability ``source``
         (the anatomy term of the joint step, same F.grid_sample call as voxel_morph.py:90-91) without materialising the

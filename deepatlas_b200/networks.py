@@ -200,7 +200,23 @@ def UNet_generator(encoders, decoders, act="ReLU", upsample=False, maxpool=True,
         def weights_init(self):
             self.apply(init_conv_weights)
 
+        @property
+        def head(self):
+            """The 1x1x1 class head (unets.py:250): the last module of the last decoder block."""
+            return list(self.decoders.children())[-1][-1]   # (the blocks are registered by name, not by index)
+
         def forward(self, x):
+            return self._run(x, False)
+
+        def forward_features(self, x):
+            """Everything of ``forward`` up to (not including) the class head: the head's input, for callers that fuse
+            head + softmax + Dice (``DiceLossMultiClass.forward_head``).  ``head(forward_features(x)) == forward(x)``."""
+            if self.res:
+                raise NotImplementedError("deepatlas_b200: res=True adds the decoder input to the logits (unets.py:275); "
+                                          "the head is not separable")
+            return self._run(x, True)
+
+        def _run(self, x, stop_before_head):
             skips = []
             for i, enc in enumerate(self.encoders):
                 y = x
@@ -214,7 +230,10 @@ def UNet_generator(encoders, decoders, act="ReLU", upsample=False, maxpool=True,
                 x = self.up_samplers[j](x)
                 skip = skips.pop()
                 y = x
+                last = j == len(self.decoders) - 1
                 for k, blk in enumerate(dec):
+                    if stop_before_head and last and k == len(dec) - 1:
+                        return y
                     y = blk(y, skip) if k == 0 else blk(y)  # first conv reads cat(x, skip) as two sources
                 x = ops.add(y, x) if self.res else y                      # unets.py:275
             return x

@@ -215,6 +215,70 @@ def softmax_dice(logits, target):
     return SoftmaxDiceFunction.apply(logits, target)
 
 
+def head_dice_supported(K: int, C: int, V: int) -> bool:
+    return bool(_lib.size("da_head_dice_supported", int(K), int(C), int(V)))
+
+
+class HeadSoftmaxDiceFunction(torch.autograd.Function):
+    """(sums[N,3,C], probs or None) of softmax(conv1x1(feat, weight, bias)) against a label ``target``: the U-Net's
+    1x1x1 class head (unets.py:250) fused with softmax and the Dice sums (loss.py:427-476), so that neither the logits
+    nor their gradient are written to HBM.  The backward recomputes the logits from the 16 features and forms the
+    feature, weight and bias gradients in one pass."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, target, want_probs: bool):
+        feat = _f32(feat, "features")
+        weight = _f32(weight, "weight")
+        bias = _f32(bias, "bias") if bias is not None else None
+        N, K = feat.shape[:2]
+        C = weight.shape[0]
+        V = feat[0, 0].numel()
+        if weight.numel() != C * K:
+            raise ValueError("head_dice: weight must be (C, K, 1, 1, 1)")
+        if not target.is_cuda or target.is_floating_point():
+            raise RuntimeError("deepatlas_b200: head_dice needs a CUDA label target")
+        if target.dtype not in _KIND:
+            target = target.long()
+        target = target.contiguous()
+        if target.numel() != N * V:
+            raise ValueError("dice: label target must have N*D*H*W elements")
+        kind = _KIND[target.dtype]
+        sums = torch.empty((N, 3, C), dtype=torch.float32, device=feat.device)
+        probs = torch.empty((N, C) + tuple(feat.shape[2:]), dtype=torch.float32, device=feat.device) if want_probs else None
+        nb = _lib.size("da_head_dice_workspace_bytes", N, C, V)
+        ws = _ws(nb, feat.device)
+        _lib.call("da_head_dice_fwd", _p(feat), _p(weight), _p(bias), _p(target), kind, N, K, C, V, _p(sums), _p(probs), _p(ws),
+                  nb, _stream())
+        ctx.save_for_backward(feat, weight, bias, target)
+        ctx.kind = kind
+        if probs is None:
+            ctx.mark_non_differentiable()
+            return sums, None
+        return sums, probs
+
+    @staticmethod
+    def backward(ctx, g, gp):
+        feat, weight, bias, target = ctx.saved_tensors
+        N, K = feat.shape[:2]
+        C = weight.shape[0]
+        V = feat[0, 0].numel()
+        g = torch.zeros((N, 3, C), device=feat.device) if g is None else _f32(g, "grad_sums")
+        gS, gI = g[:, 0].contiguous(), g[:, 2].contiguous()
+        gp = _f32(gp, "grad_probs") if gp is not None else None
+        gfeat = torch.empty_like(feat)
+        gw = torch.empty_like(weight)
+        gb = torch.empty_like(bias) if bias is not None else None
+        nb = _lib.size("da_head_dice_workspace_bytes", N, C, V)
+        ws = _ws(nb, feat.device)
+        _lib.call("da_head_dice_bwd", _p(feat), _p(weight), _p(bias), _p(target), ctx.kind, N, K, C, V, _p(gS), _p(gI), _p(gp),
+                  _p(gfeat), _p(gw), _p(gb), _p(ws), nb, _stream())
+        return gfeat, gw, gb, None, None
+
+
+def head_softmax_dice(feat, weight, bias, target, want_probs=False):
+    return HeadSoftmaxDiceFunction.apply(feat, weight, bias, target, want_probs)
+
+
 class WarpedDiceSumsFunction(torch.autograd.Function):
     """sums[N,3,C] of dice(grid_sample(prob, phi), onehot(labels)) without materialising the warped map: the anatomy
     term of the joint step; see csrc/warp_dice.cu for the structure of the backward."""

@@ -259,6 +259,19 @@ int da_softmax_dice_fwd(const float* logits, const void* target, int target_kind
                         float* probs, void* workspace, int64_t workspace_bytes, da_stream_t stream);
 int da_softmax_dice_bwd(const float* logits, const void* target, int target_kind, int N, int C, int64_t V, const float* gS,
                         const float* gT, const float* gI, const float* grad_probs, float* grad_logits, da_stream_t stream);
+/* The U-Net's 1x1x1 class head (lib/network_factory/unets.py:250, Conv3d(16, C, 1)) fused with softmax + the Dice sums
+ * (lib/loss.py:427-476): the logits and their gradient never reach HBM.  feat [N,16,V]; weight [C,16], bias [C]
+ * nullable; label target (kinds 0, 1, 3).  Forward: sums [N,3,C], probs [N,C,V] nullable (a second consumer of the
+ * probabilities).  Backward: gS, gI [N,C]; grad_probs nullable; grad_feat [N,16,V], grad_weight [C,16], grad_bias [C]
+ * nullable.  da_head_dice_supported: K == 16, C <= 32, V even (callers take the unfused calls otherwise). */
+int64_t da_head_dice_supported(int K, int C, int64_t V); /* 1 or 0 */
+int64_t da_head_dice_workspace_bytes(int N, int C, int64_t V);
+int da_head_dice_fwd(const float* feat, const float* weight, const float* bias, const void* target, int target_kind, int N,
+                     int K, int C, int64_t V, float* sums, float* probs, void* workspace, int64_t workspace_bytes,
+                     da_stream_t stream);
+int da_head_dice_bwd(const float* feat, const float* weight, const float* bias, const void* target, int target_kind, int N,
+                     int K, int C, int64_t V, const float* gS, const float* gI, const float* grad_probs, float* grad_feat,
+                     float* grad_weight, float* grad_bias, void* workspace, int64_t workspace_bytes, da_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -346,3 +346,61 @@ def test_softmax_dice_with_probs_equals_the_two_pass_form(cuda, C, dtype):
     xd = x.to(cuda).requires_grad_(True)
     crit(xd, t).backward()
     assert rel_err(xc.grad, xd.grad) < 1e-6
+
+
+@pytest.mark.parametrize("C", [4, 32])
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.int64])
+@pytest.mark.parametrize("size", [(9, 10, 12), (8, 6, 67 * 2)])
+def test_head_softmax_dice_vs_oracle(cuda, C, dtype, size):
+    """1x1x1 head + softmax + Dice as one kernel each way (DiceLossMultiClass.forward_head) against the CPU oracle's
+    conv3d -> DiceLossMultiClass(softmax=True) in fp32 and fp64, with a second consumer of the probabilities:
+    loss, probabilities, feature / weight / bias gradients."""
+    import torch.nn.functional as F
+
+    import deepatlas_b200 as da
+    from deepatlas_b200 import networks as M
+    from oracle import ref_port as P
+    g = _g()
+    N, K = 2, 16
+    feat = torch.randn((N, K) + size, generator=g)
+    w = torch.randn((C, K, 1, 1, 1), generator=g) * 0.4
+    b = torch.randn((C,), generator=g) * 0.2
+    t = torch.randint(0, C, (N,) + size, generator=g)
+    cot = torch.randn((N, C) + size, generator=g) * 0.01
+
+    def oracle(dt):
+        f_, w_, b_ = (x.to(dt).clone().requires_grad_(True) for x in (feat, w, b))
+        logits = F.conv3d(f_, w_, b_)
+        loss = P.dice_multiclass(logits, t, n_class=C, weight_type="Uniform", softmax=True, eps=1e-6)
+        probs = torch.softmax(logits, dim=1)
+        (3.0 * loss + (probs * cot.to(dt)).sum()).backward()
+        return loss.detach(), probs.detach(), f_.grad, w_.grad, b_.grad
+
+    head = M._Conv1x1(K, C, kernel_size=1, stride=1, padding=0, bias=True).to(cuda)
+    with torch.no_grad():
+        head.weight.copy_(w.to(cuda))
+        head.bias.copy_(b.to(cuda))
+    fg = feat.to(cuda).requires_grad_(True)
+    crit = da.get_loss_function("dice")(n_class=C, weight_type="Uniform", softmax=True, eps=1e-6)
+    from deepatlas_b200 import ops
+    assert ops.head_dice_supported(K, C, feat[0, 0].numel())
+    loss, probs = crit.forward_head(fg, head, t.to(dtype).to(cuda), want_probs=True)
+    (3.0 * loss + (probs * cot.to(cuda)).sum()).backward()
+    r32, r64 = oracle(torch.float32), oracle(torch.float64)
+    ours = (loss, probs, fg.grad, head.weight.grad, head.bias.grad)
+    for name, o, a32, a64 in zip(("loss", "probs", "dfeat", "dweight", "dbias"), ours, r32, r64):
+        assert rel_err(o, a64) < max(TOL, 3 * rel_err(a32, a64)), name
+    # without the second consumer: the probabilities are not written, the backward takes the Dice part only
+    fg2 = feat.to(cuda).requires_grad_(True)
+    head.zero_grad()
+    loss2, none = crit.forward_head(fg2, head, t.to(dtype).to(cuda))
+    assert none is None and rel_err(loss2, r64[0]) < TOL
+    loss2.backward()
+    f_, w_, b_ = (x.double().clone().requires_grad_(True) for x in (feat, w, b))
+    P.dice_multiclass(F.conv3d(f_, w_, b_), t, n_class=C, weight_type="Uniform", softmax=True, eps=1e-6).backward()
+    for name, o, a64 in (("dfeat", fg2.grad, f_.grad), ("dweight", head.weight.grad, w_.grad), ("dbias", head.bias.grad, b_.grad)):
+        assert rel_err(o, a64) < TOL, name
+    # and it equals the unfused path of the same package (separate head, softmax-Dice calls)
+    fg3 = feat.to(cuda).requires_grad_(True)
+    loss3 = crit(head(fg3), t.to(dtype).to(cuda))
+    assert rel_err(loss3, loss2) < 1e-5
