@@ -666,6 +666,7 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restr
 #include "conv3d_tma.inc.cuh"
 #include "conv3d_umma.inc.cuh"
 #include "conv3d_wgrad_umma.inc.cuh"
+#include "conv3d_smallcin.inc.cuh"
 
 // out[i] = sum_r partials[r][i]  (fixed order)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
@@ -675,6 +676,26 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
   double acc = 0.0;   // <= 148 partials per element: fp64 costs nothing here and keeps cancelling sums clean
   for (int r = 0; r < nregions; ++r) acc += (double)partials[(int64_t)r * count + i];
   out[i] = (float)acc;
+}
+
+// the same with one warp per element (lanes stride over the regions, xor-butterfly fold: still a fixed order): small
+// counts, where a thread per element leaves the GPU empty and walks up to 592 regions serially
+__global__ void __launch_bounds__(256) reduce_partials_warp_kernel(const float* __restrict__ partials, int nregions, int64_t count,
+                                                                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= count) return;
+  double acc = 0.0;
+  for (int r = lane; r < nregions; r += 32) acc += (double)partials[(int64_t)r * count + i];
+  acc = warp_sum(acc);
+  if (lane == 0) out[i] = (float)acc;
+}
+
+inline void launch_reduce_partials(const float* partials, int nregions, int64_t count, float* out, cudaStream_t stream) {
+  if (nregions >= 16 && count <= 32768)
+    reduce_partials_warp_kernel<<<(unsigned)da_cdiv(count, 8), 256, 0, stream>>>(partials, nregions, count, out);
+  else
+    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, out);
 }
 
 // per-channel sum over N and space (bias gradient):  out[c] = sum_{n,v} x[n][c][v]
@@ -1192,7 +1213,9 @@ DA_API int64_t da_conv3d_dgrad_workspace_bytes(int N, int Cin, int Cout, int Di,
 DA_API int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks) {
   const int64_t count = (int64_t)Cin * Cout * ks * ks * ks;
   const int m = Cin > Cout ? Cin : Cout;
-  return (int64_t)sizeof(float) * ((int64_t)wg_region_cap(count) * count + (int64_t)WG_MAX_REGIONS * m) + 512;
+  const int64_t gen = (int64_t)sizeof(float) * ((int64_t)wg_region_cap(count) * count + (int64_t)WG_MAX_REGIONS * m) + 512;
+  const int64_t sc = (ks == 3 && Cin <= SC_MAX_CIN) ? (int64_t)sizeof(float) * SC_REGIONS * (count + Cout) + 512 : 0;   // input layers
+  return gen > sc ? gen : sc;
 }
 
 // Forward.  x1 [N,C1,Di,Hi,Wi], x2 [N,C2,...] or null (C2=0): the conv sees cat(x1,x2) along channels.
@@ -1517,11 +1540,11 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     }
   }
   if (rc) return rc;
-  reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+  launch_reduce_partials(partials, nregions, count, grad_weight, stream);
   rc = da_check_launch("conv3d_wgrad_umma/reduce");
   if (!rc && grad_bias) {
     if (bias_partials) {
-      reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, nregions, Cout, grad_bias);
+      launch_reduce_partials(bias_partials, nregions, Cout, grad_bias, stream);
       rc = da_check_launch("conv3d_wgrad_umma/bias-reduce");
     } else {
       rc = run_channel_sum(dy, N, Cout, (int64_t)Di * Hi * Wi, grad_bias, partials + (int64_t)nregions * count, stream);
@@ -1552,6 +1575,23 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
   float* partials = (float*)workspace;
   const int64_t count = (int64_t)Cin * Cout * T;
   const int cap = wg_region_cap(count);
+  if (ks == 3 && stride == 1 && pad == 1 && !transposed && Cin <= SC_MAX_CIN && g_force_direct <= 0 &&
+      (int64_t)N * Di * Hi * ((Wi + 31) / 32) < ((int64_t)1 << 30)) {
+    // input layers (automatic selection only): exact-FFMA kernel, one partial row per block
+    const int nxc = (Wi + 31) / 32;
+    const int64_t units = (int64_t)N * Di * Hi * nxc;
+    const int nregions = (int)(units < SC_REGIONS ? units : SC_REGIONS);
+    float* bias_partials = grad_bias ? partials + (int64_t)nregions * count : nullptr;
+    conv3d_wgrad_smallcin_kernel<<<dim3(nregions, (Cout + SC_COB - 1) / SC_COB), 96 * Cin, 0, stream>>>(
+        x1, x2, C1, C2, dy, partials, bias_partials, N, Di, Hi, Wi, Cout, count);
+    int rc = da_check_launch("conv3d_wgrad_smallcin");
+    if (rc) return rc;
+    launch_reduce_partials(partials, nregions, count, grad_weight, stream);
+    rc = da_check_launch("conv3d_wgrad_smallcin/reduce");
+    if (rc || !grad_bias) return rc;
+    launch_reduce_partials(bias_partials, nregions, Cout, grad_bias, stream);
+    return da_check_launch("conv3d_wgrad_smallcin/bias-reduce");
+  }
   if (ks == 3 && stride == 1 && pad == 1 && !force_direct()) {
     // tiled kernel: regions of 4x8x32 tiles; bias gradient folded in (non-transposed layers)
     const int tiles_x = (Wi + TX - 1) / TX, tiles_y = (Hi + TY - 1) / TY, tiles_z = (Di + TZ - 1) / TZ;
@@ -1603,12 +1643,12 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
       if (!rc && C2) rc = launch_t(dy, Cout, 0, Cout, x2, C2, C1, nullptr);
     }
     if (rc) return rc;
-    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+    launch_reduce_partials(partials, nregions, count, grad_weight, stream);
     rc = da_check_launch("conv3d_wgrad/reduce");
     if (rc) return rc;
     if (grad_bias) {
       if (bias_partials) {
-        reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, nregions, Cout, grad_bias);
+        launch_reduce_partials(bias_partials, nregions, Cout, grad_bias, stream);
         rc = da_check_launch("conv3d_wgrad/bias-reduce");
       } else {
         rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);
@@ -1651,10 +1691,10 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
     int rc = launch_s2(x1, C1, 0, bias_partials);
     if (!rc && C2) rc = launch_s2(x2, C2, C1, nullptr);
     if (rc) return rc;
-    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+    launch_reduce_partials(partials, nregions, count, grad_weight, stream);
     rc = da_check_launch("conv3d_wgrad_s2/reduce");
     if (!rc && grad_bias) {
-      reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, nregions, Cout, grad_bias);
+      launch_reduce_partials(bias_partials, nregions, Cout, grad_bias, stream);
       rc = da_check_launch("conv3d_wgrad_s2/bias-reduce");
     }
     return rc;
@@ -1674,7 +1714,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
     int rc = launch1(x1, C1, 0);
     if (!rc && C2) rc = launch1(x2, C2, C1);
     if (rc) return rc;
-    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, grad_weight);
+    launch_reduce_partials(partials, nregions, count, grad_weight, stream);
     rc = da_check_launch("conv1x1_wgrad/reduce");
     if (!rc && grad_bias) rc = run_channel_sum(dy, N, Cout, Vk1, grad_bias, partials + (int64_t)nregions * count, stream);
     return rc;
@@ -1705,7 +1745,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
     if (!rc && C2) rc = launch(dy, Cout, 0, Cout, x2, C2, C1);
   }
   if (rc) return rc;
-  reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
+  launch_reduce_partials((const float*)workspace, nregions, count, grad_weight, stream);
   rc = da_check_launch("conv3d_wgrad/reduce");
   if (rc) return rc;
   if (grad_bias) rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);

@@ -7,6 +7,7 @@
 // (= four adjacent output voxels -> float4 stores) and four output channels; the weight layout
 // (Cin,Cout,2,2,2) is already [ci][co][pos], so no repack is needed.
 #include "common.cuh"
+#include <stdlib.h>
 #include "tma.cuh"
 
 namespace {
@@ -327,12 +328,23 @@ __global__ void dc_reduce_partials_kernel(const float* __restrict__ partials, in
   out[i] = acc;
 }
 
-constexpr int DC_MAX_REGIONS = 64;
+constexpr int DC_MAX_REGIONS = 444;   // three blocks per SM of the tensor-core weight gradient
 inline int dc_region_cap(int64_t count) {
   int64_t r = ((int64_t)16 << 20) / (count > 0 ? count : 1);
   if (r > DC_MAX_REGIONS) r = DC_MAX_REGIONS;
   if (r < 4) r = 4;
   return (int)r;
+}
+
+#include "deconv_mma.inc.cuh"
+
+inline bool dm_aligned8(const void* p) { return (((uintptr_t)p) & 7) == 0; }
+// tensor-core kernels: 32 or 64 input channels (the U-Net's up-samplers); everything else keeps the FFMA kernels.
+// DA_DECONV_MMA=0 switches them off (A/B timing).
+inline bool dm_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DA_DECONV_MMA"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
 }
 
 }  // namespace
@@ -343,13 +355,28 @@ extern "C" int da_channel_sum(const float* x, int N, int C, int64_t V, float* ou
 
 DA_API int64_t da_deconv_k2s2_wgrad_workspace_bytes(int Cin, int Cout) {
   const int64_t count = (int64_t)Cin * Cout * 8;
-  return (int64_t)sizeof(float) * dc_region_cap(count) * count + 256 + da_channel_sum_workspace_bytes(Cout);
+  return (int64_t)sizeof(float) * ((int64_t)dc_region_cap(count) * count + (int64_t)DC_MAX_REGIONS * Cout) + 256 +
+         da_channel_sum_workspace_bytes(Cout);
 }
 
 // x [N,Cin,D,H,W]; weight (Cin,Cout,2,2,2); out [N,Cout,2D,2H,2W]
 DA_API int da_deconv_k2s2_fwd(const float* x, const float* weight, const float* bias, float* out, int N, int Cin, int Cout,
                               int D, int H, int W, cudaStream_t stream) {
   DA_REQUIRE(x && weight && out, "da_deconv_k2s2_fwd: null pointer");
+  if (dm_enabled() && (Cin == 32 || Cin == 64) && Cout % 32 == 0 && dm_aligned8(out)) {
+    static DaPerDeviceOnce configured;
+    if (configured.first()) {
+      cudaFuncSetAttribute(deconv_k2s2_fwd_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 264 * 4);
+      cudaFuncSetAttribute(deconv_k2s2_fwd_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 264 * 4);
+    }
+    const int64_t nt = da_cdiv((int64_t)D * H * W, 32);
+    int64_t nbx = da_cdiv(nt, DM_FWD_THREADS / 32);
+    if (nbx > 3 * DA_NUM_SMS) nbx = 3 * DA_NUM_SMS;
+    dim3 grid((unsigned)nbx, Cout / 32, N);
+    if (Cin == 32) deconv_k2s2_fwd_mma_kernel<32><<<grid, DM_FWD_THREADS, 32 * 264 * 4, stream>>>(x, weight, bias, out, Cout, D, H, W);
+    else deconv_k2s2_fwd_mma_kernel<64><<<grid, DM_FWD_THREADS, 64 * 264 * 4, stream>>>(x, weight, bias, out, Cout, D, H, W);
+    return da_check_launch("da_deconv_k2s2_fwd/mma");
+  }
   const int64_t pairs = (int64_t)D * H * ((W + 1) / 2);
   dim3 grid((unsigned)da_cdiv(pairs, DC_THREADS), (Cout + 3) / 4, N);
   deconv_k2s2_fwd_kernel<<<grid, DC_THREADS, 0, stream>>>(x, weight, bias, out, Cin, Cout, D, H, W);
@@ -359,6 +386,22 @@ DA_API int da_deconv_k2s2_fwd(const float* x, const float* weight, const float* 
 DA_API int da_deconv_k2s2_dgrad(const float* dy, const float* weight, float* dx, int N, int Cin, int Cout, int D, int H, int W,
                                 cudaStream_t stream) {
   DA_REQUIRE(dy && weight && dx, "da_deconv_k2s2_dgrad: null pointer");
+  const int64_t dm_smem = (int64_t)Cin * (8 * Cout + 4) * 4;
+  if (dm_enabled() && (Cin == 32 || Cin == 64) && Cout % 4 == 0 && dm_smem <= 200 * 1024) {
+    static DaPerDeviceOnce configured;
+    if (configured.first()) {
+      cudaFuncSetAttribute(deconv_k2s2_dgrad_mma_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(deconv_k2s2_dgrad_mma_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }
+    const int mt = Cin == 32 ? 2 : 1;
+    int64_t nbx = da_cdiv(da_cdiv((int64_t)D * H * W, 16 * mt), DM_DGRAD_THREADS / 32);
+    const int per_sm = dm_smem > 100 * 1024 ? 1 : 2;
+    if (nbx > per_sm * DA_NUM_SMS) nbx = per_sm * DA_NUM_SMS;
+    dim3 grid((unsigned)nbx, 1, N);
+    if (Cin == 32) deconv_k2s2_dgrad_mma_kernel<32, 2><<<grid, DM_DGRAD_THREADS, dm_smem, stream>>>(dy, weight, dx, Cout, D, H, W);
+    else deconv_k2s2_dgrad_mma_kernel<64, 1><<<grid, DM_DGRAD_THREADS, dm_smem, stream>>>(dy, weight, dx, Cout, D, H, W);
+    return da_check_launch("da_deconv_k2s2_dgrad/mma");
+  }
   const int64_t pairs = (int64_t)D * H * ((W + 1) / 2);
   // few channels per block only where that is needed to fill the GPU (small volumes)
   const int64_t nbx = da_cdiv(pairs, DC_THREADS);
@@ -378,6 +421,28 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
   if (workspace_bytes < da_deconv_k2s2_wgrad_workspace_bytes(Cin, Cout)) { da_set_error("da_deconv_k2s2_wgrad: workspace too small"); return DA_ERR_WORKSPACE; }
   const int64_t count = (int64_t)Cin * Cout * 8;
   const int cap = dc_region_cap(count);
+  if (dm_enabled() && (Cin == 32 || Cin == 64) && Cout % 32 == 0 && W % 8 == 0) {
+    const int64_t nsteps = (int64_t)N * D * H * (W / 8);
+    const int gy = Cout / 32;
+    int64_t nregions = (Cin == 32 ? 3 : 1) * DA_NUM_SMS / gy;   // 128-thread blocks: three per SM; 256-thread: one
+    if (nregions > cap) nregions = cap;
+    if (nregions > nsteps) nregions = nsteps;
+    if (nregions < 1) nregions = 1;
+    const int64_t spr = da_cdiv(nsteps, nregions);
+    nregions = da_cdiv(nsteps, spr);
+    float* partials = (float*)workspace;
+    float* bias_partials = grad_bias ? partials + (int64_t)cap * count : nullptr;
+    dim3 grid((unsigned)nregions, gy);
+    if (Cin == 32) deconv_k2s2_wgrad_mma_kernel<32><<<grid, 128, 0, stream>>>(x, dy, partials, bias_partials, N, Cout, D, H, W, (int)spr);
+    else deconv_k2s2_wgrad_mma_kernel<64><<<grid, 256, 0, stream>>>(x, dy, partials, bias_partials, N, Cout, D, H, W, (int)spr);
+    int rc = da_check_launch("da_deconv_k2s2_wgrad/mma");
+    if (rc) return rc;
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, (int)nregions, count, grad_weight);
+    rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
+    if (rc || !grad_bias) return rc;
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, (int)nregions, Cout, grad_bias);
+    return da_check_launch("da_deconv_k2s2_wgrad/bias-reduce");
+  }
   if ((W & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0 && da_get_encode_tiled() != nullptr) {
     DeconvWgArgs a;
     a.partials = (float*)workspace; a.Cin = Cin; a.Cout = Cout; a.N = N; a.D = D; a.H = H; a.W = W;

@@ -103,15 +103,17 @@ __global__ void __launch_bounds__(DICE_THREADS) dice_sums_kernel(const float* __
   }
 }
 
-__global__ void dice_finalize_kernel(const float* __restrict__ partials, int nblocks, int C3,
-                                     float* __restrict__ sums) {
-  const int n = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride over the blocks' partial rows, fixed-order fp64 fold
+__global__ void __launch_bounds__(256) dice_finalize_kernel(const float* __restrict__ partials, int nblocks, int C3,
+                                                            float* __restrict__ sums) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= C3) return;
   const float* p = partials + (int64_t)n * nblocks * C3 + i;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += (double)p[(int64_t)b * C3];
-  sums[(int64_t)n * C3 + i] = (float)acc;
+  for (int b = lane; b < nblocks; b += 32) acc += (double)p[(int64_t)b * C3];
+  acc = warp_sum(acc);
+  if (lane == 0) sums[(int64_t)n * C3 + i] = (float)acc;
 }
 
 template <int CP>
@@ -285,8 +287,8 @@ DA_API int da_dice_sums_fwd(const float* source, const void* target, int target_
 #undef CALL
   int rc = da_check_launch("da_dice_sums_fwd");
   if (rc) return rc;
-  dim3 g2((3 * C + 127) / 128, N);
-  dice_finalize_kernel<<<g2, 128, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
+  dim3 g2((3 * C + 7) / 8, N);
+  dice_finalize_kernel<<<g2, 256, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
   return da_check_launch("da_dice_sums_fwd/finalize");
 }
 
@@ -306,8 +308,8 @@ DA_API int da_softmax_dice_fwd(const float* logits, const void* target, int targ
 #undef CALL
   int rc = da_check_launch("da_softmax_dice_fwd");
   if (rc) return rc;
-  dim3 g2((3 * C + 127) / 128, N);
-  dice_finalize_kernel<<<g2, 128, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
+  dim3 g2((3 * C + 7) / 8, N);
+  dice_finalize_kernel<<<g2, 256, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
   return da_check_launch("da_softmax_dice_fwd/finalize");
 }
 

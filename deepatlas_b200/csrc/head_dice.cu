@@ -136,14 +136,17 @@ __global__ void __launch_bounds__(HD_THREADS) head_dice_fwd_kernel(const float* 
   }
 }
 
-__global__ void hd_finalize_sums_kernel(const float* __restrict__ partials, int nblocks, int C3, float* __restrict__ sums) {
-  const int n = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride over the blocks' partial rows, fixed-order fp64 fold
+__global__ void __launch_bounds__(256) hd_finalize_sums_kernel(const float* __restrict__ partials, int nblocks, int C3,
+                                                               float* __restrict__ sums) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= C3) return;
   const float* p = partials + (int64_t)n * nblocks * C3 + i;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += (double)p[(int64_t)b * C3];
-  sums[(int64_t)n * C3 + i] = (float)acc;
+  for (int b = lane; b < nblocks; b += 32) acc += (double)p[(int64_t)b * C3];
+  acc = warp_sum(acc);
+  if (lane == 0) sums[(int64_t)n * C3 + i] = (float)acc;
 }
 
 // Backward.  Dynamic shared memory: sdl [CP][PITCH] (logit gradients of the block's 256 voxels), sf [K][PITCH] (their
@@ -274,17 +277,19 @@ __global__ void __launch_bounds__(HD_THREADS) head_dice_bwd_kernel(const float* 
     out[i] = (red[i] + red[HD_WPART + i]) + (red[2 * HD_WPART + i] + red[3 * HD_WPART + i]);
 }
 
-// grad_weight [C][K], grad_bias [C] (nullable) = fixed-order fp64 sums over the blocks' partial rows
-__global__ void hd_finalize_wgrad_kernel(const float* __restrict__ wpart, int nrows, int C, float* __restrict__ gw,
-                                         float* __restrict__ gb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// grad_weight [C][K], grad_bias [C] (nullable) = fixed-order fp64 sums over the blocks' partial rows (warp per element)
+__global__ void __launch_bounds__(256) hd_finalize_wgrad_kernel(const float* __restrict__ wpart, int nrows, int C,
+                                                                float* __restrict__ gw, float* __restrict__ gb) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= HD_WPART) return;
   const bool is_b = i >= HD_CP * HD_K;
   const int c = is_b ? i - HD_CP * HD_K : i / HD_K;
   if (c >= C || (is_b && !gb)) return;
   double acc = 0.0;
-  for (int r = 0; r < nrows; ++r) acc += (double)wpart[(int64_t)r * HD_WPART + i];
-  if (is_b) gb[c] = (float)acc; else gw[i] = (float)acc;
+  for (int r = lane; r < nrows; r += 32) acc += (double)wpart[(int64_t)r * HD_WPART + i];
+  acc = warp_sum(acc);
+  if (lane == 0) { if (is_b) gb[c] = (float)acc; else gw[i] = (float)acc; }
 }
 
 inline int hd_blocks(int64_t V) {
@@ -320,8 +325,8 @@ DA_API int da_head_dice_fwd(const float* feat, const float* weight, const float*
   else head_dice_fwd_kernel<false><<<grid, HD_THREADS, 0, stream>>>(feat, weight, bias, target, target_kind, C, V, (float*)workspace, nullptr);
   int rc = da_check_launch("da_head_dice_fwd");
   if (rc) return rc;
-  dim3 g2((3 * C + 127) / 128, N);
-  hd_finalize_sums_kernel<<<g2, 128, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
+  dim3 g2((3 * C + 7) / 8, N);
+  hd_finalize_sums_kernel<<<g2, 256, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
   return da_check_launch("da_head_dice_fwd/finalize");
 }
 
@@ -352,6 +357,6 @@ DA_API int da_head_dice_bwd(const float* feat, const float* weight, const float*
                                                                            grad_feat, (float*)workspace);
   int rc = da_check_launch("da_head_dice_bwd");
   if (rc) return rc;
-  hd_finalize_wgrad_kernel<<<(HD_WPART + 127) / 128, 128, 0, stream>>>((const float*)workspace, N * nb, C, grad_weight, grad_bias);
+  hd_finalize_wgrad_kernel<<<(HD_WPART + 7) / 8, 256, 0, stream>>>((const float*)workspace, N * nb, C, grad_weight, grad_bias);
   return da_check_launch("da_head_dice_bwd/finalize");
 }

@@ -295,7 +295,9 @@ def test_upsample_nearest(cuda, sin, sout):
 
 
 @pytest.mark.parametrize("Cin,Cout,size", [(8, 8, (4, 5, 6)), (32, 32, (6, 6, 8)), (6, 10, (3, 4, 5)), (64, 64, (5, 6, 5)),
-                                           (12, 20, (3, 6, 40)), (32, 32, (4, 10, 36))])  # last two: TMA-tiled weight gradient, ragged groups / tiles
+                                           (12, 20, (3, 6, 40)), (32, 32, (4, 10, 36)),  # these two: TMA-tiled weight gradient, ragged groups / tiles
+                                           # tensor-core (mma.sync 3xTF32) kernels: 32 / 64 input channels, W % 8 == 0 for the weight gradient
+                                           (64, 64, (3, 4, 16)), (32, 64, (3, 5, 24)), (64, 32, (2, 3, 8)), (32, 32, (7, 9, 40))])
 def test_deconv_k2s2(cuda, Cin, Cout, size):
     from deepatlas_b200 import ops
     g = _g()

@@ -1,0 +1,6 @@
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_extra.py -q -m gpu -x --tb=short 2>&1 | grep -v "^$" | tail -8
+timeout 900 python -m pytest tests/test_gpu_nets.py tests/test_gpu_golden.py tests/test_gpu_zz_training.py -q -m gpu -x --tb=short 2>&1 | grep -v "^$" | tail -8
+DA_ONLY="1->" timeout 300 python tools/layer_times.py
+DA_ONLY="1+1" timeout 300 python tools/layer_times.py
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-torch-cuda > gpurun_out/bench_r2_g.json 2> gpurun_out/bench_r2_g.err; tail -c 300 gpurun_out/bench_r2_g.err; python -c "
+import json;d=json.loads(open('gpurun_out/bench_r2_g.json').read().strip().splitlines()[-1]);print(d['ms_per_step'],d['value'],d['e2e'],d['loss'])"
