@@ -325,11 +325,27 @@ def run_ours(args, wl):
     # ---- end to end: host buffers in, loss scalar out, every step ---------------------------------------
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Through the package's own input stage (deepatlas_b200/input_stage.py, what a training loop uses): every step's
+    # host buffers go through pinned staging and an async copy on a side stream, one step ahead of the arithmetic
+    # (the first step's copy cannot overlap anything and is inside the timed region too); the loss is read back to the
+    # host every step, as the reference's loop does (models/segmentation.py:157).
+    from deepatlas_b200.input_stage import DeviceInputStage
+    samples = [(host[i], host[i + 1]) for i in range(0, len(host), 2)]
+    stage = DeviceInputStage(dev, depth=2 * len(samples))
+
+    def submit_all():
+        for img, seg in samples:
+            stage.submit(img, seg)
+
     f0.record()
     last = None
-    for _ in range(args.steps):
-        batch = [t.to(dev, non_blocking=True) for t in host]
-        last = float(step(batch).item())
+    submit_all()
+    for k in range(args.steps):
+        batch = [t for _ in samples for t in stage.get()]
+        loss_k = step(batch)          # asynchronous launches
+        if k + 1 < args.steps:
+            submit_all()              # the next step's staging + copies run while this step computes
+        last = float(loss_k.item())
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps

@@ -72,8 +72,10 @@ SIGNATURES = {
     # bn / act / pool / upsample
     "da_bn_workspace_bytes": ("i", "size"),
     "da_bn_stats": ("piilffpppppls", "rc"),
+    "da_bn_stats_ex": ("piilffppppppifppls", "rc"),
     "da_bn_act_fwd": ("pppppiilifps", "rc"),
     "da_bn_act_bwd": ("ppppppiiliifppppls", "rc"),
+    "da_bn_act_bwd_ex": ("ppppppiiliifpppppls", "rc"),
     "da_act_bwd": ("ppflps", "rc"),
     "da_maxpool2_fwd": ("ppliiis", "rc"),
     "da_maxpool2_bwd": ("pppliiis", "rc"),

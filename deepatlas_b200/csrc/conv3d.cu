@@ -1579,7 +1579,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
       (int64_t)N * Di * Hi * ((Wi + 31) / 32) < ((int64_t)1 << 30)) {
     // input layers (automatic selection only): exact-FFMA kernel, one partial row per block
     const int nxc = (Wi + 31) / 32;
-    const int64_t units = (int64_t)N * Di * Hi * nxc;
+    const int64_t units = (int64_t)N * Di * ((Hi + SC_YSEG - 1) / SC_YSEG) * nxc;
     const int nregions = (int)(units < SC_REGIONS ? units : SC_REGIONS);
     float* bias_partials = grad_bias ? partials + (int64_t)nregions * count : nullptr;
     conv3d_wgrad_smallcin_kernel<<<dim3(nregions, (Cout + SC_COB - 1) / SC_COB), 96 * Cin, 0, stream>>>(

@@ -19,13 +19,31 @@ constexpr int BN_SPLITS = DA_BN_SPLITS;  // blocks per channel for the statistic
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) { return (act && z <= 0.f) ? z * slope : z; }
 __device__ __forceinline__ float act_grad(float z, int act, float slope) { return (act && z <= 0.f) ? slope : 1.f; }
 
-// partials [C][BN_SPLITS][2] (sum, sumsq) in fp64.  vec: V % 4 == 0 and 16-byte aligned base -> 16-byte loads, four
+// block-wide min or max (valid in thread 0); red: BN_THREADS / 32 floats
+__device__ __forceinline__ float block_minmax(float v, bool is_max, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, w) : fminf(v, w);
+  }
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  if (lane == 0) red[wp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < BN_THREADS / 32; ++i) v = is_max ? fmaxf(v, red[i]) : fminf(v, red[i]);
+  }
+  return v;
+}
+
+// partials [C][BN_SPLITS][4] (sum, sumsq, min, max) in fp64.  vec: V % 4 == 0 and 16-byte aligned base -> 16-byte loads, four
 // independent ones in flight per thread (a scalar one-load-per-iteration loop left half of the HBM bandwidth unused)
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t V, int vec,
                                                               double* __restrict__ partials) {
   __shared__ double red[BN_THREADS / 32];
+  __shared__ float redm[2][BN_THREADS / 32];
   const int c = blockIdx.x, s = blockIdx.y;
   double a1 = 0, a2 = 0;
+  float vmin = INFINITY, vmax = -INFINITY;   // value range of the channel: bounds the layer's output (bn_finalize_kernel)
   for (int n = 0; n < N; ++n) {
     const float* p = x + ((int64_t)n * C + c) * V;
     if (vec) {
@@ -39,6 +57,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
         const float4 v = __ldg(p4 + i);
         f1 += (v.x + v.y) + (v.z + v.w);
         f2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, f2))));
+        vmin = fminf(fminf(vmin, fminf(v.x, v.y)), fminf(v.z, v.w));
+        vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
         if (++k == 8) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
       }
       a1 += (double)f1; a2 += (double)f2;
@@ -50,6 +70,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
       for (int64_t i = lo + threadIdx.x; i < hi; i += BN_THREADS) {
         const float v = p[i];
         f1 += v; f2 = fmaf(v, v, f2);
+        vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
         if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
       }
       a1 += (double)f1; a2 += (double)f2;
@@ -57,31 +78,60 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
   }
   const double b1 = block_sum<double, BN_THREADS / 32>(a1, red);
   const double b2 = block_sum<double, BN_THREADS / 32>(a2, red);
+  const float m0 = block_minmax(vmin, false, redm[0]), m1 = block_minmax(vmax, true, redm[1]);
   if (threadIdx.x == 0) {
-    partials[((int64_t)c * BN_SPLITS + s) * 2 + 0] = b1;
-    partials[((int64_t)c * BN_SPLITS + s) * 2 + 1] = b2;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 0] = b1;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 1] = b2;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 2] = (double)m0;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 3] = (double)m1;
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ partials, int C, double M, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0, s2 = 0;
-  for (int s = 0; s < BN_SPLITS; ++s) {
-    s1 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 0];
-    s2 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 1];
+// one block; amax_y (nullable): upper bound of max|act(gamma * xhat + beta)| over the whole tensor, from the channels'
+// value ranges -- the next convolution's tensor-core path scales its fp16 operand pairs by it and skips its own pass
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ partials, int C, double M, float eps, float momentum,
+                                                          float* __restrict__ mean, float* __restrict__ invstd,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int act, float slope, float* __restrict__ amax_y) {
+  __shared__ float redb[4];
+  float bound = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0, s2 = 0, lo = INFINITY, hi = -INFINITY;
+    for (int s = 0; s < BN_SPLITS; ++s) {
+      const double* q = partials + ((int64_t)c * BN_SPLITS + s) * 4;
+      s1 += q[0];
+      s2 += q[1];
+      lo = fmin(lo, q[2]);
+      hi = fmax(hi, q[3]);
+    }
+    const double mu = s1 / M;
+    double var = s2 / M - mu * mu;
+    if (var < 0) var = 0;
+    const double is = 1.0 / sqrt(var + (double)eps);
+    mean[c] = (float)mu;
+    invstd[c] = (float)is;
+    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
+    if (running_var) {
+      const double unbiased = M > 1 ? var * M / (M - 1) : var;
+      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
+    // act(gamma * xhat + beta) is monotone in xhat: its extreme magnitudes sit at the ends of the channel's value range
+    const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
+    double y0 = ga * (lo - mu) * is + be, y1 = ga * (hi - mu) * is + be;
+    if (act && y0 <= 0) y0 *= (double)slope;
+    if (act && y1 <= 0) y1 *= (double)slope;
+    bound = fmaxf(bound, (float)(fmax(fabs(y0), fabs(y1)) * 1.00001));   // (+ the apply pass's fp32 round-off)
   }
-  const double mu = s1 / M;
-  double var = s2 / M - mu * mu;
-  if (var < 0) var = 0;
-  mean[c] = (float)mu;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
-  if (running_var) {
-    const double unbiased = M > 1 ? var * M / (M - 1) : var;
-    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+  if (amax_y) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+    if ((threadIdx.x & 31) == 0) redb[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) bound = fmaxf(bound, redb[i]);
+      amax_y[0] = bound;
+    }
   }
 }
 
@@ -121,6 +171,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
   const int c = blockIdx.x, s = blockIdx.y;
   const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
   double a1 = 0, a2 = 0;
+  float mg = 0.f, mx = 0.f;   // max|dy|, max|xhat| of the channel: bound the layer's input gradient (bn_bwd_finalize_kernel)
+  __shared__ float redm[2][BN_THREADS / 32];
   for (int n = 0; n < N; ++n) {
     const int64_t base = ((int64_t)n * C + c) * V;
     if (vec) {
@@ -138,6 +190,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
         const float g2 = dv.z * act_grad(xh2 * ga + be, act, slope), g3 = dv.w * act_grad(xh3 * ga + be, act, slope);
         f1 += (g0 + g1) + (g2 + g3);
         f2 = fmaf(g0, xh0, fmaf(g1, xh1, fmaf(g2, xh2, fmaf(g3, xh3, f2))));
+        mg = fmaxf(fmaxf(mg, fmaxf(fabsf(dv.x), fabsf(dv.y))), fmaxf(fabsf(dv.z), fabsf(dv.w)));
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(xh0), fabsf(xh1))), fmaxf(fabsf(xh2), fabsf(xh3)));
         if (++k == 8) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
       }
       a1 += (double)f1; a2 += (double)f2;
@@ -150,6 +204,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
         const float xh = (x[base + i] - mu) * is;
         const float g = dy[base + i] * act_grad(xh * ga + be, act, slope);
         f1 += g; f2 = fmaf(g, xh, f2);
+        mg = fmaxf(mg, fabsf(dy[base + i])); mx = fmaxf(mx, fabsf(xh));
         if (++k == 32) { a1 += (double)f1; a2 += (double)f2; f1 = f2 = 0.f; k = 0; }
       }
       a1 += (double)f1; a2 += (double)f2;
@@ -157,25 +212,50 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
   }
   const double b1 = block_sum<double, BN_THREADS / 32>(a1, red);
   const double b2 = block_sum<double, BN_THREADS / 32>(a2, red);
+  const float m0 = block_minmax(mg, true, redm[0]), m1 = block_minmax(mx, true, redm[1]);
   if (threadIdx.x == 0) {
-    partials[((int64_t)c * BN_SPLITS + s) * 2 + 0] = b1;
-    partials[((int64_t)c * BN_SPLITS + s) * 2 + 1] = b2;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 0] = b1;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 1] = b2;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 2] = (double)m0;
+    partials[((int64_t)c * BN_SPLITS + s) * 4 + 3] = (double)m1;
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partials, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ s12) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0, s2 = 0;
-  for (int s = 0; s < BN_SPLITS; ++s) {
-    s1 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 0];
-    s2 += partials[((int64_t)c * BN_SPLITS + s) * 2 + 1];
+// one block; amax_dx (nullable): upper bound of max|dx| over the whole tensor,
+//   |dx| <= |gamma invstd| (max|g| + |s1| / M + max|xhat| |s2| / M)   with |g| <= |dy| (slopes <= 1)
+__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __restrict__ partials, int C, float* __restrict__ dgamma,
+                                                              float* __restrict__ dbeta, float* __restrict__ s12,
+                                                              const float* __restrict__ invstd, const float* __restrict__ gamma, double invM,
+                                                              int training, float* __restrict__ amax_dx) {
+  __shared__ float redb[4];
+  float bound = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0, s2 = 0, mg = 0, mx = 0;
+    for (int s = 0; s < BN_SPLITS; ++s) {
+      const double* q = partials + ((int64_t)c * BN_SPLITS + s) * 4;
+      s1 += q[0];
+      s2 += q[1];
+      mg = fmax(mg, q[2]);
+      mx = fmax(mx, q[3]);
+    }
+    if (dbeta) dbeta[c] = (float)s1;
+    if (dgamma) dgamma[c] = (float)s2;
+    s12[2 * c] = (float)s1;
+    s12[2 * c + 1] = (float)s2;
+    const double k = fabs((gamma ? (double)gamma[c] : 1.0) * (double)invstd[c]);
+    const double b = training ? k * (mg + fabs(s1) * invM + mx * fabs(s2) * invM) : k * mg;
+    bound = fmaxf(bound, (float)(b * 1.00001));
   }
-  if (dbeta) dbeta[c] = (float)s1;
-  if (dgamma) dgamma[c] = (float)s2;
-  s12[2 * c] = (float)s1;
-  s12[2 * c + 1] = (float)s2;
+  if (amax_dx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
+    if ((threadIdx.x & 31) == 0) redb[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) bound = fmaxf(bound, redb[i]);
+      amax_dx[0] = bound;
+    }
+  }
 }
 
 // dx = gamma*invstd*(g - s1/M - xhat*s2/M)   (training)  |  gamma*invstd*g   (eval)
@@ -341,19 +421,32 @@ inline int ew_grid(int64_t total, int per_block = 256) {
 
 }  // namespace
 
-DA_API int64_t da_bn_workspace_bytes(int C) { return (int64_t)sizeof(double) * C * BN_SPLITS * 2 + (int64_t)sizeof(float) * 2 * C + 256; }
+DA_API int64_t da_bn_workspace_bytes(int C) { return (int64_t)sizeof(double) * C * BN_SPLITS * 4 + (int64_t)sizeof(float) * 2 * C + 256; }
 
 // Training-mode statistics: mean/invstd [C] out; running stats (nullable) updated in place with `momentum`
 // (unbiased variance), as nn.BatchNorm3d does.
+DA_API int da_bn_stats_ex(const float* x, int N, int C, int64_t V, float eps, float momentum, float* mean, float* invstd,
+                          float* running_mean, float* running_var, const float* gamma, const float* beta, int act, float slope,
+                          float* amax_y, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 DA_API int da_bn_stats(const float* x, int N, int C, int64_t V, float eps, float momentum, float* mean, float* invstd,
                        float* running_mean, float* running_var, void* workspace, int64_t workspace_bytes,
                        cudaStream_t stream) {
+  return da_bn_stats_ex(x, N, C, V, eps, momentum, mean, invstd, running_mean, running_var, nullptr, nullptr, 0, 0.f, nullptr,
+                        workspace, workspace_bytes, stream);
+}
+
+// The same; with amax_y (one device float) it also leaves max|act(gamma * xhat + beta)| (up to round-off, from above),
+// the magnitude of the layer's output that da_bn_act_fwd is about to write (gamma / beta / act / slope as passed there):
+// the consumer's da_conv3d_fwd_ex takes it as a valid max-abs slot.
+DA_API int da_bn_stats_ex(const float* x, int N, int C, int64_t V, float eps, float momentum, float* mean, float* invstd,
+                          float* running_mean, float* running_var, const float* gamma, const float* beta, int act, float slope,
+                          float* amax_y, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   DA_REQUIRE(x && mean && invstd && workspace, "da_bn_stats: null pointer");
   if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_stats: workspace too small"); return DA_ERR_WORKSPACE; }
   dim3 grid(C, BN_SPLITS);
   bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, ((V & 3) == 0 && aligned16(x)) ? 1 : 0, (double*)workspace);
-  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean,
-                                                        invstd, running_mean, running_var);
+  bn_finalize_kernel<<<1, 128, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean, invstd,
+                                            running_mean, running_var, gamma, beta, act, slope, amax_y);
   return da_check_launch("da_bn_stats", 2);
 }
 
@@ -366,20 +459,33 @@ DA_API int da_bn_act_fwd(const float* x, const float* mean, const float* invstd,
   return da_check_launch("da_bn_act_fwd");
 }
 
+DA_API int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                            const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
+                            float* dgamma, float* dbeta, float* amax_dx, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 DA_API int da_bn_act_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
                          float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return da_bn_act_bwd_ex(dy, x, mean, invstd, gamma, beta, N, C, V, training, act, slope, dx, dgamma, dbeta, nullptr, workspace,
+                          workspace_bytes, stream);
+}
+
+// The same; amax_dx (one device float, nullable) receives an upper bound of max|dx| (a valid max-abs slot for the
+// da_conv3d_dgrad_ex / _wgrad_ex calls that consume dx).
+DA_API int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                            const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
+                            float* dgamma, float* dbeta, float* amax_dx, void* workspace, int64_t workspace_bytes,
+                            cudaStream_t stream) {
   DA_REQUIRE(dy && x && mean && invstd && dx && workspace, "da_bn_act_bwd: null pointer");
   if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_act_bwd: workspace too small"); return DA_ERR_WORKSPACE; }
   double* partials = (double*)workspace;
-  float* s12 = (float*)(partials + (int64_t)C * BN_SPLITS * 2);
+  float* s12 = (float*)(partials + (int64_t)C * BN_SPLITS * 4);
   dim3 g1(C, BN_SPLITS);
   const int vec = ((V & 3) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) ? 1 : 0;
+  const double invM = 1.0 / ((double)N * (double)V);
   bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, vec, partials);
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, stream>>>(partials, C, dgamma, dbeta, s12);
+  bn_bwd_finalize_kernel<<<1, 128, 0, stream>>>(partials, C, dgamma, dbeta, s12, invstd, gamma, invM, training, amax_dx);
   dim3 g2(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
-  bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)(1.0 / ((double)N * (double)V)),
-                                            training, act, slope, vec, dx);
+  bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)invM, training, act, slope, vec, dx);
   return da_check_launch("da_bn_act_bwd", 3);
 }
 

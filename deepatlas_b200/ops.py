@@ -36,6 +36,24 @@ def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+# Max-abs bounds travel with the tensors they describe: a producer that knows an upper bound of max|t| (batch norm, from
+# the value ranges its statistics pass sees anyway; max-pooling and nearest up-sampling, which only select values)
+# attaches it as ``t._da_amax`` (a one-element device tensor), and the convolutions' tensor-core path, which scales its
+# fp16 operand pairs by such a bound, then skips its own pass over the tensor.  Any op that makes a new tensor drops it.
+def _get_amax(t):
+    a = getattr(t, "_da_amax", None)
+    if a is None or getattr(t, "_da_amax_version", None) != t._version:
+        return None
+    return a
+
+
+def _set_amax(t, a):
+    if a is not None:
+        t._da_amax = a
+        t._da_amax_version = t._version
+    return t
+
+
 def _check_device(t: torch.Tensor, name: str):
     """Kernels launch on the CURRENT device's current stream (``_stream()``): a tensor living on another GPU would be
     dereferenced in the wrong context.  Fail loudly instead; ``with torch.cuda.device(t.device):`` is the fix."""
@@ -468,10 +486,15 @@ class Conv3dFunction(torch.autograd.Function):
         ws = _ws(nb, x1.device)
         # max|input|: the tensor-core kernels scale their fp16 operand pairs by it; computed once here (the call fills
         # the slot) and reused by the weight gradient in backward
-        amax_x = torch.empty((1,), dtype=torch.float32, device=x1.device)
+        a1 = _get_amax(x1)
+        a2 = _get_amax(x2) if x2 is not None else None
+        if a1 is not None and (x2 is None or a2 is not None):
+            amax_x, x_valid = (a1 if x2 is None else torch.maximum(a1, a2)), 1   # a producer's bound: no pass over the input
+        else:
+            amax_x, x_valid = torch.empty((1,), dtype=torch.float32, device=x1.device), 0
         _lib.call("da_conv3d_fwd_ex", _p(x1), C1, _p(x2), C2, _p(weight), int(transposed), _p(bias), _p(out), N, Di,
                   Hi, Wi, Cout, ks, stride, pad, 0 if slope is None else 1, 0.0 if slope is None else float(slope),
-                  _p(ws), nb, _stream(), _p(amax_x), 0)
+                  _p(ws), nb, _stream(), _p(amax_x), x_valid)
         ctx.amax_x = amax_x
         ctx.save_for_backward(x1, x2, weight, out if slope is not None else None)
         ctx.cfg = (bool(transposed), ks, stride, pad, slope, bias is not None, Cout)
@@ -493,8 +516,10 @@ class Conv3dFunction(torch.autograd.Function):
         dx1 = dx2 = dw = db = None
         nb = _lib.size("da_conv3d_dgrad_workspace_bytes", N, Cin, Cout, Di, Hi, Wi, ks, stride)
         ws = _ws(nb, dy.device)
-        amax_dy = torch.empty((1,), dtype=torch.float32, device=dy.device)   # filled by the first call that takes it
-        dy_valid = 0
+        amax_dy = _get_amax(dy)   # the producer's bound (batch-norm backward), else filled by the first call that takes it
+        dy_valid = 1
+        if amax_dy is None:
+            amax_dy, dy_valid = torch.empty((1,), dtype=torch.float32, device=dy.device), 0
         if ctx.needs_input_grad[0]:
             dx1 = torch.empty_like(x1)
             _lib.call("da_conv3d_dgrad_ex", _p(dy), _p(weight), int(transposed), _p(dx1), N, Cin, 0, C1, Cout, Di, Hi,
@@ -539,9 +564,12 @@ class BnActFunction(torch.autograd.Function):
             mean = torch.empty((C,), dtype=torch.float32, device=dev)
             invstd = torch.empty((C,), dtype=torch.float32, device=dev)
             ws = _ws(nb, dev)
-            _lib.call("da_bn_stats", _p(x), N, C, V, float(eps), float(momentum), _p(mean), _p(invstd),
-                      _p(running_mean), _p(running_var), _p(ws), nb, st)
+            amax_y = torch.empty((1,), dtype=torch.float32, device=dev)
+            _lib.call("da_bn_stats_ex", _p(x), N, C, V, float(eps), float(momentum), _p(mean), _p(invstd),
+                      _p(running_mean), _p(running_var), _p(gamma), _p(beta), 0 if slope is None else 1,
+                      0.0 if slope is None else float(slope), _p(amax_y), _p(ws), nb, st)
         else:
+            amax_y = None
             mean = running_mean.detach().float().contiguous()
             invstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
         y = torch.empty_like(x)
@@ -549,10 +577,12 @@ class BnActFunction(torch.autograd.Function):
                   0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(y), st)
         ctx.save_for_backward(x, mean, invstd, gamma, beta)
         ctx.cfg = (bool(training), slope)
-        return y
+        if amax_y is not None:
+            ctx.mark_non_differentiable(amax_y)
+        return y, amax_y   # (the bound is attached to y by bn_act(): attributes set here do not reach the tensor apply() returns)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _g_amax=None):
         x, mean, invstd, gamma, beta = ctx.saved_tensors
         training, slope = ctx.cfg
         dy = _f32(dy, "grad_out")
@@ -563,14 +593,17 @@ class BnActFunction(torch.autograd.Function):
         db = torch.empty_like(mean)
         nb = _lib.size("da_bn_workspace_bytes", C)
         ws = _ws(nb, x.device)
-        _lib.call("da_bn_act_bwd", _p(dy), _p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), N, C, V, int(training),
-                  0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(dx), _p(dg), _p(db),
+        amax_dx = torch.empty((1,), dtype=torch.float32, device=x.device)
+        _lib.call("da_bn_act_bwd_ex", _p(dy), _p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), N, C, V, int(training),
+                  0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(dx), _p(dg), _p(db), _p(amax_dx),
                   _p(ws), nb, _stream())
+        _set_amax(dx, amax_dx)
         return dx, (dg if gamma is not None else None), (db if beta is not None else None), None, None, None, None, None, None
 
 
 def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, slope=None):
-    return BnActFunction.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, slope)
+    y, amax = BnActFunction.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, slope)
+    return _set_amax(y, amax)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -593,11 +626,11 @@ class MaxPool2Function(torch.autograd.Function):
         dy = _f32(dy, "grad_out")
         dx = torch.empty_like(x)
         _lib.call("da_maxpool2_bwd", _p(dy), _p(x), _p(dx), N * C, D, H, W, _stream())
-        return dx
+        return _set_amax(dx, _get_amax(dy))   # dy values or zeros
 
 
 def maxpool2(x):
-    return MaxPool2Function.apply(x)
+    return _set_amax(MaxPool2Function.apply(x), _get_amax(x))   # a maximum of input values: the input's bound holds
 
 
 class UpsampleNearestFunction(torch.autograd.Function):
@@ -623,7 +656,7 @@ class UpsampleNearestFunction(torch.autograd.Function):
 def upsample_nearest(x, size: Sequence[int]):
     if tuple(x.shape[2:]) == tuple(size):
         return x
-    return UpsampleNearestFunction.apply(x, tuple(size))
+    return _set_amax(UpsampleNearestFunction.apply(x, tuple(size)), _get_amax(x))   # copies of input values
 
 
 class DeconvK2S2Function(torch.autograd.Function):

@@ -166,6 +166,17 @@ int da_bn_act_bwd(const float* dy, const float* x, const float* mean, const floa
                   const float* gamma, const float* beta, int N, int C, int64_t V, int training, int act,
                   float slope, float* dx, float* dgamma, float* dbeta, void* workspace,
                   int64_t workspace_bytes, da_stream_t stream);
+/* da_bn_stats / da_bn_act_bwd with one more output: an upper bound of max|.| of the tensor the layer is about to write
+ * (amax_y: the activated output of da_bn_act_fwd with the same gamma / beta; amax_dx: the input gradient), derived from
+ * per-channel value ranges gathered by the statistics passes.  One device float each, nullable; a consumer convolution
+ * passes it to da_conv3d_*_ex as a valid max-abs slot and skips its own pass over the tensor. */
+int da_bn_stats_ex(const float* x, int N, int C, int64_t V, float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, const float* gamma, const float* beta, int act, float slope,
+                   float* amax_y, void* workspace, int64_t workspace_bytes, da_stream_t stream);
+int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                     const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
+                     float* dgamma, float* dbeta, float* amax_dx, void* workspace, int64_t workspace_bytes,
+                     da_stream_t stream);
 int da_act_bwd(const float* dy, const float* y, float slope, int64_t total, float* dx, da_stream_t stream);
 int da_maxpool2_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, da_stream_t stream);
 int da_maxpool2_bwd(const float* dy, const float* x, float* dx, int64_t NC, int D, int H, int W,

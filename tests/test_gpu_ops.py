@@ -365,3 +365,44 @@ def test_eval_argmax_and_dice_bit_exact(cuda, C, size, dtype):
     ok = ~torch.isnan(ref_dice)
     assert torch.equal(got[ok], ref_dice[ok])
     assert int(counts[:, 0].sum()) == 2 * logits[0, 0].numel() and int(counts[:, 0, 2].sum()) == 0
+
+
+@pytest.mark.parametrize("slope", [None, 0.0, 0.01])
+def test_bn_act_output_bounds(cuda, slope):
+    """The max-abs bounds batch norm attaches to its output and to its input gradient (consumed by the convolutions'
+    tensor-core path instead of a pass over the tensor) are true upper bounds, and tight: the forward one is the exact
+    maximum up to round-off, the backward one a triangle inequality."""
+    from deepatlas_b200 import ops
+    g = _g()
+    C, size = 6, (9, 10, 12)
+    x = (torch.randn((2, C) + size, generator=g) * 3 + 1).to(cuda).requires_grad_(True)
+    ga = (torch.randn(C, generator=g)).to(cuda).requires_grad_(True)
+    be = (torch.randn(C, generator=g)).to(cuda).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=cuda), torch.ones(C, device=cuda)
+    y = ops.bn_act(x, ga, be, rm, rv, training=True, slope=slope)
+    a = ops._get_amax(y)
+    assert a is not None
+    ymax = float(y.detach().abs().max())
+    assert ymax <= float(a) <= ymax * 1.001
+    p = ops.maxpool2(y)
+    assert ops._get_amax(p) is a
+    seen = {}
+
+    class Probe(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return t * 1.0
+
+        @staticmethod
+        def backward(ctx, gt):
+            seen["amax"], seen["max"] = ops._get_amax(gt), float(gt.abs().max())
+            return gt
+
+    xp = Probe.apply(x)
+    y2 = ops.bn_act(xp, ga, be, rm, rv, training=True, slope=slope)
+    (y2 * torch.randn(y2.shape, generator=g).to(cuda)).sum().backward()
+    assert seen["amax"] is not None
+    assert seen["max"] <= float(seen["amax"]) <= 4 * seen["max"]
+    with torch.no_grad():
+        y.add_(1.0)   # an in-place change invalidates the bound
+    assert ops._get_amax(y) is None

@@ -1,6 +1,6 @@
 """Per-layer timing of every k3 convolution of the C4 joint step through the C ABI (forward, data gradient(s), weight
 gradient; preallocated buffers, no autograd): where the convolution time of a step goes, layer by layer.
-Env: DA_SIZE="160,192,160", DA_NT repeats, DA_ONLY=substring filter on the layer name."""
+Env: DA_SIZE="160,192,160", DA_NT repeats, DA_ONLY=substring filter on the layer name, DA_IMPL=da_set_conv_impl code."""
 import ctypes
 import os
 import sys
@@ -14,6 +14,8 @@ D0, H0, W0 = (int(v) for v in os.environ.get("DA_SIZE", "160,192,160").split(","
 NT = int(os.environ.get("DA_NT", "4"))
 ONLY = os.environ.get("DA_ONLY", "")
 dev = torch.device("cuda:0")
+if os.environ.get("DA_IMPL"):   # 0 auto, 1 direct, 2 tiled FFMA, 3 tensor cores forced
+    _lib.call("da_set_conv_impl", int(os.environ["DA_IMPL"]))
 P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
 
 # (name, C1, C2, Cout, level of the INPUT (0 = full), stride, needs dx, multiplicity per step)
