@@ -40,7 +40,7 @@ SIGNATURES = {
     "da_head_dice_supported": ("iil", "size"),
     "da_head_dice_workspace_bytes": ("iil", "size"),
     "da_head_dice_fwd": ("ppppiiiilpppls", "rc"),
-    "da_head_dice_bwd": ("ppppiiiilpppppppls", "rc"),
+    "da_head_dice_bwd": ("ppppiiiilppppppipls", "rc"),
     "da_argmax_counts": ("ppiiilpps", "rc"),
     # lncc
     "da_lncc_coef_bytes": ("iiiiii", "size"),
@@ -66,7 +66,7 @@ SIGNATURES = {
     "da_absmax": ("plplps", "rc"),
     "da_conv3d_fwd_ex": ("pipipippiiiiiiiiifplspi", "rc"),
     "da_conv3d_dgrad_ex": ("ppipiiiiiiiiiiiplspi", "rc"),
-    "da_conv3d_wgrad_ex": ("pipipippiiiiiiiiplspipi", "rc"),
+    "da_conv3d_wgrad_ex": ("pipipippiiiiiiiiplspipii", "rc"),
     "da_channel_sum_workspace_bytes": ("i", "size"),
     "da_channel_sum": ("piilppls", "rc"),
     # bn / act / pool / upsample
@@ -75,7 +75,7 @@ SIGNATURES = {
     "da_bn_stats_ex": ("piilffppppppifppls", "rc"),
     "da_bn_act_fwd": ("pppppiilifps", "rc"),
     "da_bn_act_bwd": ("ppppppiiliifppppls", "rc"),
-    "da_bn_act_bwd_ex": ("ppppppiiliifpppppls", "rc"),
+    "da_bn_act_bwd_ex": ("ppppppiiliifppppipls", "rc"),
     "da_act_bwd": ("ppflps", "rc"),
     "da_maxpool2_fwd": ("ppliiis", "rc"),
     "da_maxpool2_bwd": ("pppliiis", "rc"),
@@ -86,6 +86,7 @@ SIGNATURES = {
     "da_deconv_k2s2_fwd": ("ppppiiiiiis", "rc"),
     "da_deconv_k2s2_dgrad": ("pppiiiiiis", "rc"),
     "da_deconv_k2s2_wgrad": ("ppppiiiiiipls", "rc"),
+    "da_deconv_k2s2_wgrad_ex": ("ppppiiiiiiipls", "rc"),
     # remaining registry losses
     "da_pair_moments_workspace_bytes": ("i", "size"),
     "da_pair_moments_fwd": ("ppilppls", "rc"),

@@ -669,11 +669,12 @@ __global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restr
 #include "conv3d_smallcin.inc.cuh"
 
 // out[i] = sum_r partials[r][i]  (fixed order)
+// accumulate: out[i] += the sum (a parameter gradient that already holds an earlier contribution of the same step)
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
-                                       float* __restrict__ out) {
+                                       float* __restrict__ out, int accumulate) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  double acc = 0.0;   // <= 148 partials per element: fp64 costs nothing here and keeps cancelling sums clean
+  double acc = accumulate ? (double)out[i] : 0.0;   // <= 148 partials per element: fp64 costs nothing here and keeps cancelling sums clean
   for (int r = 0; r < nregions; ++r) acc += (double)partials[(int64_t)r * count + i];
   out[i] = (float)acc;
 }
@@ -681,21 +682,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 // the same with one warp per element (lanes stride over the regions, xor-butterfly fold: still a fixed order): small
 // counts, where a thread per element leaves the GPU empty and walks up to 592 regions serially
 __global__ void __launch_bounds__(256) reduce_partials_warp_kernel(const float* __restrict__ partials, int nregions, int64_t count,
-                                                                   float* __restrict__ out) {
+                                                                   float* __restrict__ out, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= count) return;
   double acc = 0.0;
   for (int r = lane; r < nregions; r += 32) acc += (double)partials[(int64_t)r * count + i];
   acc = warp_sum(acc);
-  if (lane == 0) out[i] = (float)acc;
+  if (lane == 0) out[i] = (float)(accumulate ? acc + (double)out[i] : acc);
 }
+
+// set by da_conv3d_wgrad_ex for the duration of the call: the gradient outputs are added to instead of overwritten
+thread_local int g_grad_accumulate = 0;
+struct GradAccumulateScope {
+  explicit GradAccumulateScope(int a) { g_grad_accumulate = a; }
+  ~GradAccumulateScope() { g_grad_accumulate = 0; }
+};
 
 inline void launch_reduce_partials(const float* partials, int nregions, int64_t count, float* out, cudaStream_t stream) {
   if (nregions >= 16 && count <= 32768)
-    reduce_partials_warp_kernel<<<(unsigned)da_cdiv(count, 8), 256, 0, stream>>>(partials, nregions, count, out);
+    reduce_partials_warp_kernel<<<(unsigned)da_cdiv(count, 8), 256, 0, stream>>>(partials, nregions, count, out, g_grad_accumulate);
   else
-    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, out);
+    reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, out, g_grad_accumulate);
 }
 
 // per-channel sum over N and space (bias gradient):  out[c] = sum_{n,v} x[n][c][v]
@@ -731,18 +739,18 @@ __global__ void __launch_bounds__(256) channel_sum_partial_kernel(const float* _
   const double t = block_sum<double, 8>(acc, red);
   if (threadIdx.x == 0) part[(int64_t)c * CS_SPLITS + sp] = t;
 }
-__global__ void channel_sum_final_kernel(const double* __restrict__ part, int C, float* __restrict__ out) {
+__global__ void channel_sum_final_kernel(const double* __restrict__ part, int C, float* __restrict__ out, int accumulate) {
   const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double a = part[(int64_t)c * CS_SPLITS + lane] + part[(int64_t)c * CS_SPLITS + 32 + lane];
   a = warp_sum(a);
-  if (lane == 0) out[c] = (float)a;
+  if (lane == 0) out[c] = (float)(accumulate ? a + (double)out[c] : a);
 }
 inline int64_t channel_sum_scratch_bytes(int C) { return (int64_t)sizeof(double) * C * CS_SPLITS + 256; }
-inline int run_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* scratch, cudaStream_t stream) {
+inline int run_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* scratch, cudaStream_t stream, int accumulate = 0) {
   double* part = (double*)(((uintptr_t)scratch + 15) & ~(uintptr_t)15);
   channel_sum_partial_kernel<<<dim3(C, CS_SPLITS), 256, 0, stream>>>(x, N, C, V, part);
-  channel_sum_final_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, C, out);
+  channel_sum_final_kernel<<<(C + 7) / 8, 256, 0, stream>>>(part, C, out, accumulate);
   return da_check_launch("channel_sum", 2);
 }
 
@@ -963,7 +971,10 @@ inline bool fwd_umma_ok(const ConvGeom& g) {
   if ((int64_t)g.N * g.Cout * V >= ((int64_t)1 << 32) || 8 * V >= ((int64_t)1 << 31)) return false;
   if (g.act && !(g.slope >= 0.f && g.slope <= 1.f)) return false;
   if (g_force_direct == 3) return g.stride == 1 && g.pad == 1;  // tests: tensor-core path whatever the size heuristics say
-  return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 && V >= 65536;
+  // (measured, round 2: with at most four 32-channel launches per layer the tensor path also wins on a 20x24x20 level --
+  // 64 -> 64: 0.060 ms against 0.111 ms for the FFMA kernel)
+  const bool big = V >= 65536 || (V >= 8192 && g.C1 + g.C2 <= 128 && g.Cout <= 64);
+  return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 && big;
 }
 inline int64_t umma_workspace_bytes(int Cin, int Cout) {
   return (int64_t)((Cout + UM_CB - 1) / UM_CB) * ((Cin + 15) / 16) * UMMA_IMG_BYTES + 256;   // + the max-abs slots
@@ -1231,7 +1242,7 @@ DA_API int da_conv3d_dgrad_ex(const float* dy, const float* weight, int transpos
 DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed, float* grad_weight,
                               float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks, int stride, int pad, void* workspace,
                               int64_t workspace_bytes, cudaStream_t stream, float* amax_x, int amax_x_valid, float* amax_dy,
-                              int amax_dy_valid);
+                              int amax_dy_valid, int accumulate);
 
 namespace {
 // fills the caller's max-abs slot when the chosen kernel did not need it itself (the _ex contract: a slot passed with
@@ -1410,11 +1421,13 @@ DA_API int da_conv3d_dgrad_ex(const float* dy, const float* weight, int transpos
 // Weight gradient (+ optional bias gradient).  grad_weight has the layer's own layout
 // ((Cout,Cin,k^3), or (Cin,Cout,k^3) when transposed).  x2 may be null.
 // tcgen05 weight gradient (conv3d_wgrad_umma_kernel): k3 s1 p1 layers whose volume amortises the per-CTA TMEM read-out
-inline bool wgrad_umma_ok(int N, int D, int H, int W) {
+inline bool wgrad_umma_ok(int N, int D, int H, int W, int Cin, int Cout) {
   if (g_force_direct == 3) return true;
   const char* e = getenv("DA_WGRAD_UMMA");
   if (e && strcmp(e, "0") == 0) return false;
-  return umma_enabled() && !force_direct() && W >= 16 && (int64_t)N * D * H * W >= 65536;
+  const int64_t V = (int64_t)N * D * H * W;
+  const bool big = V >= 65536 || (V >= 8192 && Cin <= 128 && Cout <= 64);   // as fwd_umma_ok
+  return umma_enabled() && !force_direct() && W >= 16 && big;
 }
 
 int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed, float* grad_weight,
@@ -1547,7 +1560,7 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
       launch_reduce_partials(bias_partials, nregions, Cout, grad_bias, stream);
       rc = da_check_launch("conv3d_wgrad_umma/bias-reduce");
     } else {
-      rc = run_channel_sum(dy, N, Cout, (int64_t)Di * Hi * Wi, grad_bias, partials + (int64_t)nregions * count, stream);
+      rc = run_channel_sum(dy, N, Cout, (int64_t)Di * Hi * Wi, grad_bias, partials + (int64_t)nregions * count, stream, g_grad_accumulate);
     }
   }
   return rc;
@@ -1557,16 +1570,19 @@ DA_API int da_conv3d_wgrad(const float* x1, int C1, const float* x2, int C2, con
                            float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                            int stride, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   return da_conv3d_wgrad_ex(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, ks, stride, pad, workspace,
-                            workspace_bytes, stream, nullptr, 0, nullptr, 0);
+                            workspace_bytes, stream, nullptr, 0, nullptr, 0, 0);
 }
 
 // amax_x / amax_dy: caller-owned max-abs slots of cat(x1, x2) and of dy, as in da_conv3d_fwd_ex.  Here a slot passed as
 // not valid is filled only if the tensor-core kernel runs (nothing downstream of a weight gradient reuses it).
+// accumulate = 1: the results are ADDED to grad_weight / grad_bias (a parameter used twice in a step, or a gradient
+// bucket that already holds this step's earlier contributions) -- folded into the fixed-order region reduce.
 DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
                               float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                               int stride, int pad, void* workspace, int64_t workspace_bytes, cudaStream_t stream,
-                              float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid) {
+                              float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid, int accumulate) {
   DA_REQUIRE(x1 && dy && grad_weight && workspace, "da_conv3d_wgrad: null pointer");
+  GradAccumulateScope accumulate_scope(accumulate ? 1 : 0);   // grad_weight / grad_bias are added to, not overwritten
   DA_REQUIRE(ks == 1 || ks == 3, "da_conv3d_wgrad: unsupported kernel size %d", ks);
   DA_REQUIRE(!transposed || (ks == 3 && stride == 1 && pad == 1), "da_conv3d_wgrad: transposed only for k3 s1 p1");
   const int Cin = C1 + C2, T = ks * ks * ks;
@@ -1604,7 +1620,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
     if (nregions < 1) nregions = 1;
     const int tpr = (ntiles + nregions - 1) / nregions;
     nregions = (ntiles + tpr - 1) / tpr;
-    if (wgrad_umma_ok(N, Di, Hi, Wi))
+    if (wgrad_umma_ok(N, Di, Hi, Wi, Cin, Cout))
       return run_wgrad_umma(x1, C1, x2, C2, dy, transposed, grad_weight, grad_bias, N, Di, Hi, Wi, Cout, partials, cap, stream, amax_x,
                             amax_x_valid, amax_dy, amax_dy_valid);
     float* bias_partials = (grad_bias && !transposed) ? partials + (int64_t)nregions * count : nullptr;
@@ -1651,7 +1667,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
         launch_reduce_partials(bias_partials, nregions, Cout, grad_bias, stream);
         rc = da_check_launch("conv3d_wgrad/bias-reduce");
       } else {
-        rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);
+        rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream, g_grad_accumulate);
       }
     }
     return rc;
@@ -1716,7 +1732,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
     if (rc) return rc;
     launch_reduce_partials(partials, nregions, count, grad_weight, stream);
     rc = da_check_launch("conv1x1_wgrad/reduce");
-    if (!rc && grad_bias) rc = run_channel_sum(dy, N, Cout, Vk1, grad_bias, partials + (int64_t)nregions * count, stream);
+    if (!rc && grad_bias) rc = run_channel_sum(dy, N, Cout, Vk1, grad_bias, partials + (int64_t)nregions * count, stream, g_grad_accumulate);
     return rc;
   }
   const int64_t total_rows = (int64_t)N * Do * Ho * ((Wo + 31) / 32);
@@ -1748,7 +1764,7 @@ DA_API int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, 
   launch_reduce_partials((const float*)workspace, nregions, count, grad_weight, stream);
   rc = da_check_launch("conv3d_wgrad/reduce");
   if (rc) return rc;
-  if (grad_bias) rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream);
+  if (grad_bias) rc = run_channel_sum(dy, N, Cout, (int64_t)Do * Ho * Wo, grad_bias, partials + (int64_t)nregions * count, stream, g_grad_accumulate);
   return rc;
 }
 

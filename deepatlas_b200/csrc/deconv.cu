@@ -320,12 +320,18 @@ __global__ void __launch_bounds__(DT_THREADS, 2)
       }
 }
 
-__global__ void dc_reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count, float* __restrict__ out) {
+// accumulate: out[i] += the sum (a parameter gradient that already holds an earlier contribution of the same step)
+__global__ void dc_reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count, float* __restrict__ out,
+                                          int accumulate) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float acc = 0.f;
   for (int r = 0; r < nregions; ++r) acc += partials[(int64_t)r * count + i];
-  out[i] = acc;
+  out[i] = accumulate ? out[i] + acc : acc;
+}
+__global__ void dc_add_kernel(float* __restrict__ out, const float* __restrict__ v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += v[i];
 }
 
 constexpr int DC_MAX_REGIONS = 444;   // three blocks per SM of the tensor-core weight gradient
@@ -415,8 +421,31 @@ DA_API int da_deconv_k2s2_dgrad(const float* dy, const float* weight, float* dx,
   return da_check_launch("da_deconv_k2s2_dgrad");
 }
 
+namespace {
+// bias gradient of the FFMA paths: channel sums of dY (the weight partials at the head of the workspace have been consumed
+// by the reduce on the same stream); accumulating: sums into the workspace tail, then added
+int dc_bias_sum(const float* dy, int N, int Cout, int64_t Vo, float* grad_bias, int accumulate, void* workspace, int64_t workspace_bytes,
+                cudaStream_t stream) {
+  if (!accumulate) return da_channel_sum(dy, N, Cout, Vo, grad_bias, workspace, workspace_bytes, stream);
+  float* tmp = (float*)workspace;   // [Cout] ahead of the channel-sum scratch
+  const int64_t head = 256 * (((int64_t)Cout * 4 + 255) / 256);
+  int rc = da_channel_sum(dy, N, Cout, Vo, tmp, (char*)workspace + head, workspace_bytes - head, stream);
+  if (rc) return rc;
+  dc_add_kernel<<<(Cout + 127) / 128, 128, 0, stream>>>(grad_bias, tmp, Cout);
+  return da_check_launch("da_deconv_k2s2_wgrad/bias-add");
+}
+}  // namespace
+
+DA_API int da_deconv_k2s2_wgrad_ex(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N, int Cin, int Cout,
+                                   int D, int H, int W, int accumulate, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
 DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N, int Cin, int Cout,
                                 int D, int H, int W, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return da_deconv_k2s2_wgrad_ex(x, dy, grad_weight, grad_bias, N, Cin, Cout, D, H, W, 0, workspace, workspace_bytes, stream);
+}
+
+// accumulate = 1: grad_weight / grad_bias += the result (a gradient bucket that already holds earlier contributions)
+DA_API int da_deconv_k2s2_wgrad_ex(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N, int Cin, int Cout,
+                                   int D, int H, int W, int accumulate, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   DA_REQUIRE(x && dy && grad_weight && workspace, "da_deconv_k2s2_wgrad: null pointer");
   if (workspace_bytes < da_deconv_k2s2_wgrad_workspace_bytes(Cin, Cout)) { da_set_error("da_deconv_k2s2_wgrad: workspace too small"); return DA_ERR_WORKSPACE; }
   const int64_t count = (int64_t)Cin * Cout * 8;
@@ -437,10 +466,10 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
     else deconv_k2s2_wgrad_mma_kernel<64><<<grid, 256, 0, stream>>>(x, dy, partials, bias_partials, N, Cout, D, H, W, (int)spr);
     int rc = da_check_launch("da_deconv_k2s2_wgrad/mma");
     if (rc) return rc;
-    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, (int)nregions, count, grad_weight);
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, (int)nregions, count, grad_weight, accumulate);
     rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
     if (rc || !grad_bias) return rc;
-    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, (int)nregions, Cout, grad_bias);
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, (int)nregions, Cout, grad_bias, accumulate);
     return da_check_launch("da_deconv_k2s2_wgrad/bias-reduce");
   }
   if ((W & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0 && da_get_encode_tiled() != nullptr) {
@@ -468,10 +497,10 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
     deconv_k2s2_wgrad_tma_kernel<<<dim3(groups, nregions), DT_THREADS, DT_SMEM_BYTES, stream>>>(mx, mdy, a);
     int rc = da_check_launch("da_deconv_k2s2_wgrad_tma");
     if (rc) return rc;
-    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight, accumulate);
     rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
     if (rc || !grad_bias) return rc;
-    return da_channel_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, workspace, workspace_bytes, stream);
+    return dc_bias_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, accumulate, workspace, workspace_bytes, stream);
   }
   const int64_t total_rows = (int64_t)N * D * H * ((W + 31) / 32);
   int nregions = (int)(total_rows < cap ? total_rows : cap);
@@ -482,9 +511,9 @@ DA_API int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_wei
   deconv_k2s2_wgrad_kernel<<<grid, DW_THREADS, 0, stream>>>(x, dy, (float*)workspace, N, Cin, Cout, D, H, W, rpr, total_rows);
   int rc = da_check_launch("da_deconv_k2s2_wgrad");
   if (rc) return rc;
-  dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight);
+  dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight, accumulate);
   rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
   if (rc || !grad_bias) return rc;
   // the weight partials have been consumed by the reduce above (same stream): reuse the workspace head
-  return da_channel_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, workspace, workspace_bytes, stream);
+  return dc_bias_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, accumulate, workspace, workspace_bytes, stream);
 }

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(HD_THREADS) head_dice_bwd_kernel(const float* 
 
 // grad_weight [C][K], grad_bias [C] (nullable) = fixed-order fp64 sums over the blocks' partial rows (warp per element)
 __global__ void __launch_bounds__(256) hd_finalize_wgrad_kernel(const float* __restrict__ wpart, int nrows, int C,
-                                                                float* __restrict__ gw, float* __restrict__ gb) {
+                                                                float* __restrict__ gw, float* __restrict__ gb, int accumulate) {
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= HD_WPART) return;
@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(256) hd_finalize_wgrad_kernel(const float* __r
   double acc = 0.0;
   for (int r = lane; r < nrows; r += 32) acc += (double)wpart[(int64_t)r * HD_WPART + i];
   acc = warp_sum(acc);
-  if (lane == 0) { if (is_b) gb[c] = (float)acc; else gw[i] = (float)acc; }
+  if (lane == 0) {
+    if (is_b) gb[c] = (float)(accumulate ? acc + (double)gb[c] : acc);
+    else gw[i] = (float)(accumulate ? acc + (double)gw[i] : acc);
+  }
 }
 
 inline int hd_blocks(int64_t V) {
@@ -332,10 +335,11 @@ DA_API int da_head_dice_fwd(const float* feat, const float* weight, const float*
 
 // gS, gI [N,C]: gradients of the loss w.r.t. the S and I sums (T does not depend on the network); grad_probs [N,C,V]
 // nullable (the second consumer's gradient at the probabilities).  grad_feat [N,16,V], grad_weight [C,16], grad_bias [C]
-// nullable.
+// nullable; accumulate = 1: grad_weight / grad_bias += the result.
 DA_API int da_head_dice_bwd(const float* feat, const float* weight, const float* bias, const void* target, int target_kind, int N,
                             int K, int C, int64_t V, const float* gS, const float* gI, const float* grad_probs, float* grad_feat,
-                            float* grad_weight, float* grad_bias, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+                            float* grad_weight, float* grad_bias, int accumulate, void* workspace, int64_t workspace_bytes,
+                            cudaStream_t stream) {
   DA_REQUIRE(feat && weight && target && gS && gI && grad_feat && grad_weight && workspace, "da_head_dice_bwd: null pointer");
   DA_REQUIRE(da_head_dice_supported(K, C, V), "da_head_dice_bwd: unsupported shape (K = %d, C = %d, V = %lld)", K, C, (long long)V);
   DA_REQUIRE(target_kind == 0 || target_kind == 1 || target_kind == 3, "da_head_dice_bwd: label target only");
@@ -357,6 +361,6 @@ DA_API int da_head_dice_bwd(const float* feat, const float* weight, const float*
                                                                            grad_feat, (float*)workspace);
   int rc = da_check_launch("da_head_dice_bwd");
   if (rc) return rc;
-  hd_finalize_wgrad_kernel<<<(HD_WPART + 7) / 8, 256, 0, stream>>>((const float*)workspace, N * nb, C, grad_weight, grad_bias);
+  hd_finalize_wgrad_kernel<<<(HD_WPART + 7) / 8, 256, 0, stream>>>((const float*)workspace, N * nb, C, grad_weight, grad_bias, accumulate);
   return da_check_launch("da_head_dice_bwd/finalize");
 }

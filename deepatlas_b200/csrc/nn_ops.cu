@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __restrict__ partials, int C, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ s12,
                                                               const float* __restrict__ invstd, const float* __restrict__ gamma, double invM,
-                                                              int training, float* __restrict__ amax_dx) {
+                                                              int training, float* __restrict__ amax_dx, int accumulate) {
   __shared__ float redb[4];
   float bound = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __re
       mg = fmax(mg, q[2]);
       mx = fmax(mx, q[3]);
     }
-    if (dbeta) dbeta[c] = (float)s1;
-    if (dgamma) dgamma[c] = (float)s2;
+    if (dbeta) dbeta[c] = (float)(accumulate ? s1 + (double)dbeta[c] : s1);
+    if (dgamma) dgamma[c] = (float)(accumulate ? s2 + (double)dgamma[c] : s2);
     s12[2 * c] = (float)s1;
     s12[2 * c + 1] = (float)s2;
     const double k = fabs((gamma ? (double)gamma[c] : 1.0) * (double)invstd[c]);
@@ -461,19 +461,20 @@ DA_API int da_bn_act_fwd(const float* x, const float* mean, const float* invstd,
 
 DA_API int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                             const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
-                            float* dgamma, float* dbeta, float* amax_dx, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+                            float* dgamma, float* dbeta, float* amax_dx, int accumulate, void* workspace, int64_t workspace_bytes,
+                            cudaStream_t stream);
 DA_API int da_bn_act_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                          const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
                          float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
-  return da_bn_act_bwd_ex(dy, x, mean, invstd, gamma, beta, N, C, V, training, act, slope, dx, dgamma, dbeta, nullptr, workspace,
+  return da_bn_act_bwd_ex(dy, x, mean, invstd, gamma, beta, N, C, V, training, act, slope, dx, dgamma, dbeta, nullptr, 0, workspace,
                           workspace_bytes, stream);
 }
 
 // The same; amax_dx (one device float, nullable) receives an upper bound of max|dx| (a valid max-abs slot for the
-// da_conv3d_dgrad_ex / _wgrad_ex calls that consume dx).
+// da_conv3d_dgrad_ex / _wgrad_ex calls that consume dx); accumulate = 1: dgamma / dbeta += the result.
 DA_API int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                             const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
-                            float* dgamma, float* dbeta, float* amax_dx, void* workspace, int64_t workspace_bytes,
+                            float* dgamma, float* dbeta, float* amax_dx, int accumulate, void* workspace, int64_t workspace_bytes,
                             cudaStream_t stream) {
   DA_REQUIRE(dy && x && mean && invstd && dx && workspace, "da_bn_act_bwd: null pointer");
   if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_act_bwd: workspace too small"); return DA_ERR_WORKSPACE; }
@@ -483,7 +484,7 @@ DA_API int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, 
   const int vec = ((V & 3) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) ? 1 : 0;
   const double invM = 1.0 / ((double)N * (double)V);
   bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, vec, partials);
-  bn_bwd_finalize_kernel<<<1, 128, 0, stream>>>(partials, C, dgamma, dbeta, s12, invstd, gamma, invM, training, amax_dx);
+  bn_bwd_finalize_kernel<<<1, 128, 0, stream>>>(partials, C, dgamma, dbeta, s12, invstd, gamma, invM, training, amax_dx, accumulate);
   dim3 g2(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
   bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)invM, training, act, slope, vec, dx);
   return da_check_launch("da_bn_act_bwd", 3);

@@ -42,7 +42,10 @@ class FlatGradBucket:
     or does not alias its slot), copies such gradients into the bucket and restores the views, so the collective is
     always over the real gradients.  Prefer ``zero()`` / ``zero_grad()`` of the bucket (one memset, views kept)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], inplace: bool = True):
+        """``inplace``: the CUDA backward kernels add parameter gradients straight into the bucket views (ops._grad_dst)
+        instead of returning tensors for autograd to add -- one launch less per parameter and use.  Turn it off for code
+        that calls ``torch.autograd.grad`` on these parameters or hangs hooks on them."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatGradBucket: no trainable parameters")
@@ -54,6 +57,8 @@ class FlatGradBucket:
         for p in self.params:
             n = p.numel()
             v = self.flat[off:off + n].view_as(p)
+            if inplace and dev.type == "cuda":
+                v._da_inplace = True
             self._views.append(v)
             p.grad = v
             off += n

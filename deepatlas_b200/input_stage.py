@@ -71,12 +71,20 @@ class DeviceInputStage:
         ev = slot.get("free")
         if ev is not None:
             ev.synchronize()  # the copy that last read this slot's pinned buffers has finished
-        pi = self._pinned(slot, "image", image)
-        pi.copy_(image)
+        # a tensor that already sits in pinned memory is copied from where it is (no second host copy); the caller
+        # must then leave it alone until the copy has run -- get() of the same sample orders the consumer after it
+        if image.is_pinned() and image.is_contiguous():
+            pi = image
+        else:
+            pi = self._pinned(slot, "image", image)
+            pi.copy_(image)
         ps = None
         if seg is not None:
-            ps = self._pinned(slot, "seg", seg)
-            ps.copy_(seg)
+            if seg.is_pinned() and seg.is_contiguous():
+                ps = seg
+            else:
+                ps = self._pinned(slot, "seg", seg)
+                ps.copy_(seg)
         lo, size = crop_window(image.shape, self.crop_size)
         with torch.cuda.stream(self.stream):
             di = pi.to(self.device, non_blocking=True)

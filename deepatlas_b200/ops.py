@@ -54,6 +54,23 @@ def _set_amax(t, a):
     return t
 
 
+# Parameter gradients written straight into their destination.  A gradient tensor marked ``_da_inplace`` (FlatGradBucket
+# marks its views: ``p.grad`` slices of one flat all-reduce buffer that exist before backward starts) is added to inside
+# the producing backward's own fixed-order reduce kernel (``accumulate = 1``), and autograd is handed ``None`` -- instead of
+# a fresh tensor that autograd then adds to ``p.grad`` with one more kernel per parameter and use (187 launches per joint
+# step).  Opt-in per parameter, because ``torch.autograd.grad`` and parameter hooks expect the tensors.
+def _grad_dst(p, wanted: bool):
+    """``p.grad`` if the gradient of parameter ``p`` is to be accumulated in place, else None."""
+    if not wanted or p is None or not p.is_leaf:
+        return None
+    g = p.grad
+    if g is None or not getattr(g, "_da_inplace", False):
+        return None
+    if g.dtype != torch.float32 or g.device != p.device or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
+
+
 def _check_device(t: torch.Tensor, name: str):
     """Kernels launch on the CURRENT device's current stream (``_stream()``): a tensor living on another GPU would be
     dereferenced in the wrong context.  Fail loudly instead; ``with torch.cuda.device(t.device):`` is the fix."""
@@ -284,12 +301,17 @@ class HeadSoftmaxDiceFunction(torch.autograd.Function):
         gS, gI = g[:, 0].contiguous(), g[:, 2].contiguous()
         gp = _f32(gp, "grad_probs") if gp is not None else None
         gfeat = torch.empty_like(feat)
-        gw = torch.empty_like(weight)
-        gb = torch.empty_like(bias) if bias is not None else None
+        gw_dst = _grad_dst(weight, ctx.needs_input_grad[1])
+        gb_dst = _grad_dst(bias, ctx.needs_input_grad[2]) if bias is not None else None
+        inplace = gw_dst is not None and (bias is None or gb_dst is not None)
+        gw = gw_dst if inplace else torch.empty_like(weight)
+        gb = (gb_dst if inplace else torch.empty_like(bias)) if bias is not None else None
         nb = _lib.size("da_head_dice_workspace_bytes", N, C, V)
         ws = _ws(nb, feat.device)
         _lib.call("da_head_dice_bwd", _p(feat), _p(weight), _p(bias), _p(target), ctx.kind, N, K, C, V, _p(gS), _p(gI), _p(gp),
-                  _p(gfeat), _p(gw), _p(gb), _p(ws), nb, _stream())
+                  _p(gfeat), _p(gw), _p(gb), int(inplace), _p(ws), nb, _stream())
+        if inplace:
+            gw = gb = None
         return gfeat, gw, gb, None, None
 
 
@@ -497,6 +519,7 @@ class Conv3dFunction(torch.autograd.Function):
                   _p(ws), nb, _stream(), _p(amax_x), x_valid)
         ctx.amax_x = amax_x
         ctx.save_for_backward(x1, x2, weight, out if slope is not None else None)
+        ctx.bias_ref = bias   # (only its .grad is looked at in backward)
         ctx.cfg = (bool(transposed), ks, stride, pad, slope, bias is not None, Cout)
         return out
 
@@ -531,12 +554,18 @@ class Conv3dFunction(torch.autograd.Function):
                       Wi, ks, stride, pad, _p(ws), nb, st, _p(amax_dy), dy_valid)
             dy_valid = 1
         if ctx.needs_input_grad[2] or (has_bias and ctx.needs_input_grad[3]):
-            dw = torch.empty_like(weight)
-            db = torch.empty((Cout,), dtype=torch.float32, device=dy.device) if has_bias else None
+            bias = ctx.bias_ref
+            gw_dst = _grad_dst(weight, ctx.needs_input_grad[2])
+            gb_dst = _grad_dst(bias, has_bias and ctx.needs_input_grad[3]) if has_bias else None
+            inplace = gw_dst is not None and (not has_bias or gb_dst is not None)
+            dw = gw_dst if inplace else torch.empty_like(weight)
+            db = (gb_dst if inplace else torch.empty((Cout,), dtype=torch.float32, device=dy.device)) if has_bias else None
             nbw = _lib.size("da_conv3d_wgrad_workspace_bytes", Cin, Cout, ks)
             wsw = _ws(nbw, dy.device)
             _lib.call("da_conv3d_wgrad_ex", _p(x1), C1, _p(x2), C2, _p(dy), int(transposed), _p(dw), _p(db), N, Di, Hi,
-                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, st, _p(ctx.amax_x), 1, _p(amax_dy), dy_valid)
+                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, st, _p(ctx.amax_x), 1, _p(amax_dy), dy_valid, int(inplace))
+            if inplace:
+                dw = db = None   # already added to weight.grad / bias.grad
         return dx1, dx2, dw, db, None, None, None, None
 
 
@@ -589,15 +618,20 @@ class BnActFunction(torch.autograd.Function):
         N, C = x.shape[:2]
         V = x[0, 0].numel()
         dx = torch.empty_like(x)
-        dg = torch.empty_like(mean)
-        db = torch.empty_like(mean)
+        g_dst = _grad_dst(gamma, gamma is not None and ctx.needs_input_grad[1])
+        b_dst = _grad_dst(beta, beta is not None and ctx.needs_input_grad[2])
+        inplace = g_dst is not None and b_dst is not None
+        dg = g_dst if inplace else torch.empty_like(mean)
+        db = b_dst if inplace else torch.empty_like(mean)
         nb = _lib.size("da_bn_workspace_bytes", C)
         ws = _ws(nb, x.device)
         amax_dx = torch.empty((1,), dtype=torch.float32, device=x.device)
         _lib.call("da_bn_act_bwd_ex", _p(dy), _p(x), _p(mean), _p(invstd), _p(gamma), _p(beta), N, C, V, int(training),
                   0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(dx), _p(dg), _p(db), _p(amax_dx),
-                  _p(ws), nb, _stream())
+                  int(inplace), _p(ws), nb, _stream())
         _set_amax(dx, amax_dx)
+        if inplace:
+            dg = db = None   # already added to gamma.grad / beta.grad
         return dx, (dg if gamma is not None else None), (db if beta is not None else None), None, None, None, None, None, None
 
 
@@ -672,6 +706,7 @@ class DeconvK2S2Function(torch.autograd.Function):
         _lib.call("da_deconv_k2s2_fwd", _p(x), _p(weight), _p(bias), _p(out), N, Cin, Cout, D, H, W, _stream())
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         return out
 
     @staticmethod
@@ -686,11 +721,16 @@ class DeconvK2S2Function(torch.autograd.Function):
             dx = torch.empty_like(x)
             _lib.call("da_deconv_k2s2_dgrad", _p(dy), _p(weight), _p(dx), N, Cin, Cout, D, H, W, st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty_like(weight)
-            db = torch.empty((Cout,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            gw_dst = _grad_dst(weight, ctx.needs_input_grad[1])
+            gb_dst = _grad_dst(ctx.bias_ref, ctx.has_bias and ctx.needs_input_grad[2]) if ctx.has_bias else None
+            inplace = gw_dst is not None and (not ctx.has_bias or gb_dst is not None)
+            dw = gw_dst if inplace else torch.empty_like(weight)
+            db = (gb_dst if inplace else torch.empty((Cout,), dtype=torch.float32, device=dy.device)) if ctx.has_bias else None
             nb = _lib.size("da_deconv_k2s2_wgrad_workspace_bytes", Cin, Cout)
             ws = _ws(nb, dy.device)
-            _lib.call("da_deconv_k2s2_wgrad", _p(x), _p(dy), _p(dw), _p(db), N, Cin, Cout, D, H, W, _p(ws), nb, st)
+            _lib.call("da_deconv_k2s2_wgrad_ex", _p(x), _p(dy), _p(dw), _p(db), N, Cin, Cout, D, H, W, int(inplace), _p(ws), nb, st)
+            if inplace:
+                dw = db = None
         return dx, dw, db
 
 

@@ -147,7 +147,8 @@ int da_conv3d_dgrad_ex(const float* dy, const float* weight, int transposed, flo
 int da_conv3d_wgrad_ex(const float* x1, int C1, const float* x2, int C2, const float* dy, int transposed,
                        float* grad_weight, float* grad_bias, int N, int Di, int Hi, int Wi, int Cout, int ks,
                        int stride, int pad, void* workspace, int64_t workspace_bytes, da_stream_t stream,
-                       float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid);
+                       float* amax_x, int amax_x_valid, float* amax_dy, int amax_dy_valid, int accumulate);
+/* (accumulate = 1: grad_weight / grad_bias += the result, inside the fixed-order region reduce.) */
 int64_t da_channel_sum_workspace_bytes(int C);
 int da_channel_sum(const float* x, int N, int C, int64_t V, float* out, void* workspace, int64_t workspace_bytes,
                    da_stream_t stream);
@@ -175,8 +176,8 @@ int da_bn_stats_ex(const float* x, int N, int C, int64_t V, float eps, float mom
                    float* amax_y, void* workspace, int64_t workspace_bytes, da_stream_t stream);
 int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                      const float* beta, int N, int C, int64_t V, int training, int act, float slope, float* dx,
-                     float* dgamma, float* dbeta, float* amax_dx, void* workspace, int64_t workspace_bytes,
-                     da_stream_t stream);
+                     float* dgamma, float* dbeta, float* amax_dx, int accumulate, void* workspace, int64_t workspace_bytes,
+                     da_stream_t stream); /* accumulate = 1: dgamma / dbeta += */
 int da_act_bwd(const float* dy, const float* y, float slope, int64_t total, float* dx, da_stream_t stream);
 int da_maxpool2_fwd(const float* x, float* y, int64_t NC, int D, int H, int W, da_stream_t stream);
 int da_maxpool2_bwd(const float* dy, const float* x, float* dx, int64_t NC, int D, int H, int W,
@@ -196,6 +197,9 @@ int da_deconv_k2s2_dgrad(const float* dy, const float* weight, float* dx, int N,
 int da_deconv_k2s2_wgrad(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N,
                          int Cin, int Cout, int D, int H, int W, void* workspace, int64_t workspace_bytes,
                          da_stream_t stream);
+int da_deconv_k2s2_wgrad_ex(const float* x, const float* dy, float* grad_weight, float* grad_bias, int N, int Cin, int Cout,
+                            int D, int H, int W, int accumulate, void* workspace, int64_t workspace_bytes,
+                            da_stream_t stream); /* accumulate = 1: grad_weight / grad_bias += */
 
 /* ---- remaining entries of the loss registry (lib/loss.py:739-750) ------------------
  * pair moments: replaces the ATen passes of NormalizedCrossCorrelationLoss (lib/loss.py:494-501), nn.MSELoss
@@ -282,7 +286,8 @@ int da_head_dice_fwd(const float* feat, const float* weight, const float* bias, 
                      da_stream_t stream);
 int da_head_dice_bwd(const float* feat, const float* weight, const float* bias, const void* target, int target_kind, int N,
                      int K, int C, int64_t V, const float* gS, const float* gI, const float* grad_probs, float* grad_feat,
-                     float* grad_weight, float* grad_bias, void* workspace, int64_t workspace_bytes, da_stream_t stream);
+                     float* grad_weight, float* grad_bias, int accumulate, void* workspace, int64_t workspace_bytes,
+                     da_stream_t stream); /* accumulate = 1: grad_weight / grad_bias += */
 
 #ifdef __cplusplus
 }

@@ -53,3 +53,30 @@ def test_three_adam_steps_follow_the_oracle(cuda):
     for k in ("encoders.0.0.BN.running_mean", "encoders.0.0.BN.running_var", "decoders.decBlock2.1.BN.running_var"):
         assert rel_err(after[k], sd[k]) < 1e-2, k
     assert int(after["encoders.0.0.BN.num_batches_tracked"]) == steps
+
+
+def test_bucket_inplace_gradients_equal_autograd_accumulation(cuda):
+    """FlatGradBucket(inplace=True): the backward kernels add parameter gradients straight into the bucket views
+    (accumulate = 1 inside their fixed-order reduces, autograd gets None).  Same gradients as the plain path, in which
+    autograd adds returned tensors -- on the joint step, where the segmentation net's parameters are used twice."""
+    from deepatlas_b200.dist import FlatGradBucket
+    from deepatlas_b200.joint import JointModel, make_synthetic_pair
+    n_classes, size = 4, (16, 24, 16)
+    batch = make_synthetic_pair(size, n_classes, seed=231, device=cuda)
+    flats, losses = [], []
+    for inplace in (True, False):
+        torch.manual_seed(230)
+        model = JointModel(n_classes=n_classes).to(cuda)
+        model.weights_init()
+        bucket = FlatGradBucket(model.trainable_parameters(), inplace=inplace)
+        assert all(getattr(p.grad, "_da_inplace", False) == inplace for p in bucket.params)
+        for _ in range(2):   # the second round starts from zero() like a training loop
+            bucket.zero()
+            loss, _ = model.joint_loss(*batch)
+            loss.backward()
+        assert bucket.rebind(copy=True) == 0          # every gradient still lives in its bucket slot
+        flats.append(bucket.flat.clone())
+        losses.append(float(loss))
+    assert losses[0] == losses[1]
+    assert float(flats[0].abs().max()) > 0
+    assert rel_err(flats[0], flats[1]) < 1e-5

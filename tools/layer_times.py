@@ -97,7 +97,7 @@ for name, C1, C2, Cout, lvl, stride, need_dx, mult in LAYERS:
 
     def wgrad():
         _lib.call("da_conv3d_wgrad_ex", P(x1), C1, P(x2), C2, P(dy), 0, P(gw), P(gb), 1, D, H, W, Cout, 3, stride, 1, P(ws), nw, st,
-                  P(ax), 1, P(ady), 1)
+                  P(ax), 1, P(ady), 1, 0)
 
     tf = timeit(fwd)
     td = timeit(dgrad) if need_dx else 0.0
