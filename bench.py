@@ -285,7 +285,8 @@ def run_ours(args, wl):
     model.weights_init()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model.trainable_parameters())
-    opt = torch.optim.Adam(bucket.params, lr=1e-3, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.Adam(bucket.params, lr=1e-3, fused=True, capturable=use_graph)
 
     host = [t.pin_memory() for t in make_synthetic_pair(SIZE, CLASSES, seed=230 + rank)]
     if wl["kind"] == "seg":
@@ -293,12 +294,19 @@ def run_ours(args, wl):
     dev_batch = [t.to(dev) for t in host]
     h2d = sum(t.numel() * t.element_size() for t in host)
 
-    def step(batch):
+    def compute(batch):
         bucket.zero()
         loss, _ = model.joint_loss(*batch)
         loss.backward()
+        return loss.detach()
+
+    def update():
         bucket.allreduce(world)
         opt.step()
+
+    def step(batch):
+        loss = compute(batch)
+        update()
         return loss
 
     def barrier():
@@ -306,8 +314,25 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the whole step as one CUDA graph (deepatlas_b200/graph.py): eager, the host side of a step (about a thousand launches
+    # through Python) is as long as its GPU side; --no-graph times the eager loop
+    gstep, graph_note = None, "eager"
+    run = step
+    if use_graph:
+        from deepatlas_b200.graph import GraphedStep
+        try:
+            if world == 1:
+                gstep = GraphedStep(lambda *b: step(b), dev_batch, warmup=args.warmup)
+                graph_note = "one CUDA graph per step (zero grads, forward, backward, Adam)"
+            else:   # the NCCL all-reduce and the optimizer stay outside the graph (torch's NCCL watchdog, see graph.py)
+                gstep = GraphedStep(lambda *b: compute(b), dev_batch, warmup=args.warmup, eager_tail=update)
+                graph_note = "one CUDA graph per step (zero grads, forward, backward) + eager NCCL all-reduce and Adam"
+            run = lambda batch: gstep(*batch)   # noqa: E731
+        except Exception as e:   # noqa: BLE001  (keep the bench alive: the eager step is the same arithmetic)
+            torch.cuda.synchronize()
+            graph_note = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
     for _ in range(args.warmup):
-        step(dev_batch)
+        run(dev_batch)
     # ---- device-resident timing -------------------------------------------------------------------------
     sampler = ClockSampler(local)
     barrier()
@@ -316,11 +341,13 @@ def run_ours(args, wl):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step(dev_batch)
+        loss = run(dev_batch)
     e1.record()
     barrier()
     clocks = sampler.stop()
-    launches = _lib.size("da_launch_count") - l0
+    launches = _lib.size("da_launch_count") - l0   # (launch calls made by the host: none during graph replays)
+    if gstep is not None:
+        launches = gstep.launches_per_step * args.steps   # library kernels inside the replayed graphs
     ms = e0.elapsed_time(e1) / args.steps
     # ---- end to end: host buffers in, loss scalar out, every step ---------------------------------------
     barrier()
@@ -328,7 +355,7 @@ def run_ours(args, wl):
     # Through the package's own input stage (deepatlas_b200/input_stage.py, what a training loop uses): every step's
     # host buffers go through pinned staging and an async copy on a side stream, one step ahead of the arithmetic
     # (the first step's copy cannot overlap anything and is inside the timed region too); the loss is read back to the
-    # host every step, as the reference's loop does (models/segmentation.py:157).
+    # host every step (the reference's loop logs it every step, models/segmentation.py:157) ...
     from deepatlas_b200.input_stage import DeviceInputStage
     samples = [(host[i], host[i + 1]) for i in range(0, len(host), 2)]
     stage = DeviceInputStage(dev, depth=2 * len(samples))
@@ -337,15 +364,26 @@ def run_ours(args, wl):
         for img, seg in samples:
             stage.submit(img, seg)
 
+    # ... through a pinned buffer, one step behind: step k's loss is copied to the host right after the step on the same
+    # stream and read while step k+1 runs (a blocking .item() per step leaves the GPU idle for the launch latency of the
+    # next 1000-node graph); every step's loss is read inside the timed region, the last one after the loop.
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
     f0.record()
     last = None
     submit_all()
     for k in range(args.steps):
         batch = [t for _ in samples for t in stage.get()]
-        loss_k = step(batch)          # asynchronous launches
+        loss_k = run(batch)           # asynchronous: one graph launch (or the eager launches)
+        loss_host[k % 2].copy_(loss_k, non_blocking=True)
+        loss_ready[k % 2].record()
         if k + 1 < args.steps:
             submit_all()              # the next step's staging + copies run while this step computes
-        last = float(loss_k.item())
+        if k > 0:
+            loss_ready[(k - 1) % 2].synchronize()
+            last = float(loss_host[(k - 1) % 2])
+    loss_ready[(args.steps - 1) % 2].synchronize()
+    last = float(loss_host[(args.steps - 1) % 2])
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps
@@ -448,16 +486,20 @@ def run_ours(args, wl):
                 "config": {"workload": wl["name"], "pairs_per_gpu": 1, "classes": CLASSES,
                            "seg": {"joint": "UNet_light(1,C,bias,BN)", "seg": "UNet(1,C,bias,BN) 32-base", "reg": None}[wl["kind"]],
                            "reg": None if wl["kind"] == "seg" else "VoxelMorphCVPR2018", "optimizer": "Adam(fused)", "parallelism": f"dp{world}",
+                           "step_launch": graph_note,
                            "grad_bucket_bytes": bucket.nbytes,
                            "arithmetic": "fp32 storage and accumulation; k3 convolutions on tcgen05 as 3xFP16 (fp16 hi/lo pairs of operands "
                                          "scaled per tensor by a power of two: fp32-grade products), everything else fp32 CUDA cores",
                            "l2_policy": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": wl["volumes"] * world / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e},
+                        "ms_per_step": ms_e2e, "input_path": "pinned host tensors -> DeviceInputStage (side-stream copy one step ahead, clip on device)",
+                        "loss_readback": "every step through a pinned buffer, read by the host one step behind"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_wgrad": roofline_wgrad, "cpu_baseline": cpu,
                 "torch_cuda_baseline": tcuda, "parity": parity, "peak_mem_gb": peak_mem, "loss": last}
         print(json.dumps(line), flush=True)
     if world > 1:
+        gstep = run = None   # the graph goes before the process group
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
     return 0
@@ -473,6 +515,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-cuda", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the captured CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -170,6 +170,15 @@ class BendingEnergyLoss(nn.Module):
             self.spacing = self.spacing / self.spacing.min()
 
     def _coef(self, shape, device):
+        # cached per (shape, device): built on the host, and a pageable host-to-device copy per step would be a host
+        # synchronisation (and is not capturable in a CUDA graph)
+        key = (tuple(shape), str(device))
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        if key not in cache:
+            cache[key] = self._coef_host(shape).to(device)
+        return cache[key]
+
+    def _coef_host(self, shape):
         # lib/loss.py:694-696,721-729: scale_term[c] = (dims[c]*spacing[c]/denom_term)^2 (per CHANNEL, the
         # reference's quirk), mean over space, mean over (B,3), weights (1,1,1,2,2,2)/9
         B, _, D, H, W = shape
@@ -183,7 +192,7 @@ class BendingEnergyLoss(nn.Module):
         interior = float((D - 2) * (H - 2) * (W - 2))
         scale = ((dims * sp)[:, None] / den[None, :]) ** 2          # (3 channels, 6 terms)
         coef = scale * wt[None, :] / (9.0 * 3.0 * B * interior)
-        return coef.float().to(device)
+        return coef.float()
 
     def forward(self, input):
         sums = ops.bending_sums(input)                               # (B, 3, 6)
