@@ -35,8 +35,11 @@ WORKLOADS = {
                metric="volumes/sec (fwd+bwd) 256x256x256 joint seg+reg"),
     "c3": dict(name="reg_only_160x160x160_fp32", kind="reg", size=(160, 160, 160), classes=2, volumes=2, algo_bytes=5.18e9,
                metric="volumes/sec (fwd+bwd) 160x160x160 registration (VoxelMorph + warp + LNCC + bending)"),
-    "c2": dict(name="seg_only_unet32_128x128x128_c4_fp32", kind="seg", size=(128, 128, 128), classes=4, volumes=1, algo_bytes=20.14e9,
-               metric="volumes/sec (fwd+bwd) 128x128x128 seg-only 32-base UNet"),
+    # BASELINE config #2 is the reduced-precision ("bf16") case: its k3 convolutions run the tensor-core kernels in the
+    # single-pass mode (da_set_conv_split(2): fp16 operands scaled per tensor, fp32 accumulate and storage); --precision fp32
+    # times the exact 3xFP16 path instead
+    "c2": dict(name="seg_only_unet32_128x128x128_c4_f16x1", kind="seg", size=(128, 128, 128), classes=4, volumes=1, algo_bytes=20.14e9,
+               metric="volumes/sec (fwd+bwd) 128x128x128 seg-only 32-base UNet", precision="f16x1"),
 }
 PARITY_SIZE = (80, 96, 80)          # extent of the in-bench parity check against the fp32 / fp64 oracle (CPU leg)
 
@@ -274,6 +277,9 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     _lib.load()
     SIZE, CLASSES = wl["size"], wl["classes"]
+    precision = args.precision or wl.get("precision", "fp32")
+    if precision == "f16x1":
+        _lib.call("da_set_conv_split", 2)
 
     torch.manual_seed(230)
     if wl["kind"] == "joint":
@@ -482,14 +488,20 @@ def run_ours(args, wl):
             tcuda = torch_cuda_baseline(wl)
         line = {"metric": wl["metric"], "value": wl["volumes"] * world / (ms * 1e-3), "unit": "volumes/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if precision == "fp32" else "f16 tensor-core operands (single pass), f32 accumulate / storage / everything else",
+                "data": "synthetic",
                 "config": {"workload": wl["name"], "pairs_per_gpu": 1, "classes": CLASSES,
                            "seg": {"joint": "UNet_light(1,C,bias,BN)", "seg": "UNet(1,C,bias,BN) 32-base", "reg": None}[wl["kind"]],
                            "reg": None if wl["kind"] == "seg" else "VoxelMorphCVPR2018", "optimizer": "Adam(fused)", "parallelism": f"dp{world}",
                            "step_launch": graph_note,
                            "grad_bucket_bytes": bucket.nbytes,
-                           "arithmetic": "fp32 storage and accumulation; k3 convolutions on tcgen05 as 3xFP16 (fp16 hi/lo pairs of operands "
-                                         "scaled per tensor by a power of two: fp32-grade products), everything else fp32 CUDA cores",
+                           "arithmetic": ("fp32 storage and accumulation; k3 convolutions on tcgen05 as 3xFP16 (fp16 hi/lo pairs of operands "
+                                          "scaled per tensor by a power of two: fp32-grade products), k2 s2 deconvolutions on mma.sync as 3xTF32, "
+                                          "everything else fp32 CUDA cores") if precision == "fp32" else
+                                         ("fp32 storage and accumulation; k3 convolutions of the tensor-core levels as ONE fp16 MMA per product "
+                                          "(operands scaled per tensor and rounded to 11 significant bits; declared tolerance 5e-3, "
+                                          "tests/test_gpu_ops.py::test_conv3d_single_pass_mode), deep small levels exact FFMA, everything else fp32"),
                            "l2_policy": "working set per step (>10 GB of activations) far exceeds the 126 MB L2; no flush needed"},
                 "e2e": {"value": wl["volumes"] * world / (ms_e2e * 1e-3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e, "input_path": "pinned host tensors -> DeviceInputStage (side-stream copy one step ahead, clip on device)",
@@ -516,6 +528,8 @@ def main():
     ap.add_argument("--no-torch-cuda", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the captured CUDA graph")
+    ap.add_argument("--precision", default=None, choices=["fp32", "f16x1"],
+                    help="k3 convolutions: fp32-grade 3xFP16 (default, all configs but c2) or the single-pass reduced-precision mode (c2)")
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -962,6 +962,10 @@ inline bool split_tf32() {
   }
   return g_conv_split == 1;
 }
+// da_set_conv_split(2): one MMA per product on the scaled fp16 operands (11 significant bits, fp32 accumulate) -- the
+// reduced-precision mode BASELINE config C2 asks for (its "bf16"; fp16 on per-tensor scaled operands has three more
+// mantissa bits at the same MMA rate).  Everything around the k3 convolutions stays fp32.
+inline int single_pass() { return g_conv_split == 2 ? 1 : 0; }
 inline bool fwd_umma_ok(const ConvGeom& g) {
   // one launch covers a block of 16 output channels: below ~50k voxels a launch no longer amortises its fixed cost and
   // the tiled FFMA kernel (one launch per layer) wins (measured on UNet's 32^3 levels)
@@ -1067,6 +1071,7 @@ int run_conv_umma(const float* x1, const float* x2, const float* weight, int64_t
   if (rc) return rc;
   UmmaArgs a;
   a.amax_x = (amax_x && amax_x_valid) ? amax_x : amax; a.amax_w = amax + 1;
+  a.single_pass = single_pass();
   a.dbg = umma_dbg_buffer();
   { static int fl = -1; if (fl < 0) { const char* e = getenv("DA_UMMA_FLAGS"); fl = e ? atoi(e) : 0; } a.flags = fl; }
   a.x1 = x1; a.x2 = x2; a.C1 = g.C1; a.C2 = g.C2; a.bias = bias; a.out = out;
@@ -1199,7 +1204,7 @@ DA_API int da_umma_debug_read(int64_t* out6) {
 // tests cross-check all of them), 3 = tcgen05 forward/dgrad whenever structurally possible (ignores the size heuristics).  Also settable through the
 // environment variable DA_CONV_IMPL=direct before the first call.
 DA_API int da_set_conv_split(int split) {
-  DA_REQUIRE(split == 0 || split == 1, "da_set_conv_split: split must be 0 (3xFP16) or 1 (3xTF32)");
+  DA_REQUIRE(split >= 0 && split <= 2, "da_set_conv_split: split must be 0 (3xFP16), 1 (3xTF32) or 2 (1xFP16, reduced precision)");
   g_conv_split = split;
   return DA_OK;
 }
@@ -1453,6 +1458,7 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
     // round-robin, so CTAs that run together walk neighbouring columns in lockstep (DRAM pages, L2 lines shared);
     // the segment count minimises rounds x (planes per unit + pipeline fill).
     WgUmmaTmaArgs a;
+    a.single_pass = 0;
     const float* h1 = transposed ? dy : x1; const float* h2 = transposed ? nullptr : x2;
     const float* p1 = transposed ? x1 : dy; const float* p2 = transposed ? x2 : nullptr;
     a.H1 = transposed ? Cout : C1; a.H2 = transposed ? 0 : C2;
@@ -1500,6 +1506,7 @@ int run_wgrad_umma(const float* x1, int C1, const float* x2, int C2, const float
         if (e != cudaSuccess) { da_set_error("conv3d_wgrad: amax copy failed: %s", cudaGetErrorString(e)); return (int)e; }
       }
       a.amax_h = have_h ? amax_hs : amax; a.amax_p = have_p ? amax_ps : amax + 1;
+      a.single_pass = single_pass();
       rc = da_make_volume_map_xcy(&mh1, h1, N, a.H1, Di, Hi, Wi, WB_XBOX, cib, 4);
       if (!rc) rc = a.H2 ? da_make_volume_map_xcy(&mh2, h2, N, a.H2, Di, Hi, Wi, WB_XBOX, cib, 4) : (mh2 = mh1, 0);
       if (!rc) rc = da_make_volume_map_xcy(&mp1, p1, N, a.P1, Di, Hi, Wi, 16, 16, 6);

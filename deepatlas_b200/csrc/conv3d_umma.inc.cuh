@@ -90,6 +90,7 @@ struct UmmaArgs {
                               // (fp32 hi/lo in mode 0, scaled fp16 hi/lo otherwise)
   const float* amax_x;        // modes 1-4: device pointers to an upper bound of max|input| and to max|weight| (absmax_kernel),
   const float* amax_w;        // which fix the power-of-two scales of the two operands
+  int single_pass;            // 1: only the hi x hi MMA (half-precision operands, fp32 accumulate: the reduced-precision mode)
   int64_t img_stride; int nco; // output-channel blocks of the layer = blockIdx.z % nco
   const float* bias; float* out;
   int N, D, H, W, Cout;
@@ -517,8 +518,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
                 const uint64_t b_hi = umma_desc_at(bdesc0, wt);
                 const uint64_t b_lo = umma_desc_at(bdesc0, wt + 3 * NCH * UM_WROWS * 16);
                 umma_ss<BF>(dcol, a_hi, b_hi, idesc, 1u);
-                umma_ss<BF>(dcol, a_lo, b_hi, idesc, 1u);
-                umma_ss<BF>(dcol, a_hi, b_lo, idesc, 1u);
+                if (!a.single_pass) {
+                  umma_ss<BF>(dcol, a_lo, b_hi, idesc, 1u);
+                  umma_ss<BF>(dcol, a_hi, b_lo, idesc, 1u);
+                }
               }
               if (sub == NSUB - 1) umma_commit(&acc_full[mt]);
             }
@@ -556,8 +559,10 @@ conv3d_umma_kernel(const __grid_constant__ CUtensorMap map1, const __grid_consta
               const uint64_t b_hi = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO);
               const uint64_t b_lo = umma_desc_at(bdesc0, wt + (uint32_t)(2 * j2) * B_LBO + 3 * NCH * UM_WROWS * 16);
               umma_ss<BF>(dcol, a_hi, b_hi, idesc, 1u);
-              umma_ss<BF>(dcol, a_lo, b_hi, idesc, 1u);
-              umma_ss<BF>(dcol, a_hi, b_lo, idesc, 1u);
+              if (!a.single_pass) {
+                umma_ss<BF>(dcol, a_lo, b_hi, idesc, 1u);
+                umma_ss<BF>(dcol, a_hi, b_lo, idesc, 1u);
+              }
             }
           }
           umma_commit(&acc_full[mt]);

@@ -274,6 +274,7 @@ struct WgUmmaTmaArgs {
   float* bias_partials;     // nullable: [region][P1+P2] sums of the plain-side tensor (= bias gradient when that is dY)
   const float* amax_h;      // 3xFP16 kernel: device pointers to upper bounds of max|halo-side tensors| and
   const float* amax_p;      // max|plain-side tensors| (absmax_kernel), which fix the power-of-two scales
+  int single_pass;          // 3xFP16 kernel: 1 = only the hi x hi MMA (reduced-precision mode)
   unsigned long long* dbg;  // optional cycle counters (DA_UMMA_DEBUG=1, 3xFP16 kernel): MMA warp waiting for operands / total,
                             // B producer warp waiting for raw tiles / for a free stage / total, TMA thread waiting, tiles
 };
@@ -612,8 +613,10 @@ conv3d_wgrad_umma16_kernel(const __grid_constant__ CUtensorMap map_h1, const __g
           const uint32_t ao = (uint32_t)(4 * q) * Cfg::BLK_BYTES, bo = (uint32_t)(2 * q) * WU_BP;
           umma_f16(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, first ? 0u : 1u);
           first = 0;
-          umma_f16(tmem, umma_desc_at(adesc0, a_lo + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, 1u);
-          umma_f16(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_lo + bo), idesc, 1u);
+          if (!a.single_pass) {
+            umma_f16(tmem, umma_desc_at(adesc0, a_lo + ao), umma_desc_at(bdesc0, b_hi + bo), idesc, 1u);
+            umma_f16(tmem, umma_desc_at(adesc0, a_hi + ao), umma_desc_at(bdesc0, b_lo + bo), idesc, 1u);
+          }
         }
         umma_commit(&empty[s]);
       }

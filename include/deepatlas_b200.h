@@ -118,7 +118,7 @@ int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, int H, 
  * x2 may be NULL with C2 = 0.  act: 0 none, 1 fused leaky-ReLU(slope) (slope 0 = ReLU). */
 int da_umma_debug_read(int64_t* out11); /* debug: cycle counters of the tensor-core conv's MMA warps (DA_UMMA_DEBUG=1) */
 int da_set_conv_impl(int impl); /* 0 = auto (tcgen05 fwd/dgrad/wgrad where they apply), 1 = generic direct kernels, 2 = tiled FFMA only, 3 = tcgen05 forced */
-int da_set_conv_split(int split); /* operand format of the tcgen05 kernels: 0 = 3xFP16 (default: fp16 hi/lo pairs of operands scaled per tensor by a power of two, 22 significant bits, fp32 accumulate), 1 = 3xTF32 (half the MMA rate) */
+int da_set_conv_split(int split); /* operand format of the tcgen05 kernels: 0 = 3xFP16 (default: fp16 hi/lo pairs of operands scaled per tensor by a power of two, 22 significant bits, fp32 accumulate), 1 = 3xTF32 (half the MMA rate), 2 = 1xFP16 (one MMA per product on the scaled fp16 operands, 11 significant bits, fp32 accumulate: the reduced-precision mode of BASELINE config C2; parity tolerance 5e-3 instead of 1e-4) */
 int64_t da_conv3d_pack_bytes(int Cin, int Cout, int ks);
 int64_t da_conv3d_dgrad_workspace_bytes(int N, int Cin, int Cout, int Di, int Hi, int Wi, int ks, int stride); /* >= pack_bytes; stride 2 adds the zero-inserted dy that lets the tcgen05 path run */
 int64_t da_conv3d_wgrad_workspace_bytes(int Cin, int Cout, int ks);

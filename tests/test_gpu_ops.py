@@ -406,3 +406,41 @@ def test_bn_act_output_bounds(cuda, slope):
     with torch.no_grad():
         y.add_(1.0)   # an in-place change invalidates the bound
     assert ops._get_amax(y) is None
+
+
+F16X1_TOL = 5e-3   # declared tolerance of the reduced-precision mode: operands rounded to 11 significant bits, fp32 accumulate
+
+
+@pytest.mark.parametrize("case", [(16, 0, 16, (8, 10, 24)), (32, 16, 16, (6, 9, 40)), (64, 0, 32, (5, 6, 20))])
+def test_conv3d_single_pass_mode(cuda, case):
+    """da_set_conv_split(2): one tcgen05 MMA per product on the scaled fp16 operands (BASELINE config C2's
+    reduced-precision mode).  Forward, data and weight gradients against the fp64 convolution within the declared 5e-3,
+    and measurably different from the default 3xFP16 path (i.e. the mode is really taken)."""
+    from deepatlas_b200 import ops
+    C1, C2, Cout, size = case
+    g = _g()
+    x1 = torch.randn((1, C1) + size, generator=g)
+    x2 = torch.randn((1, C2) + size, generator=g) if C2 else None
+    Cin = C1 + C2
+    w = torch.randn((Cout, Cin, 3, 3, 3), generator=g) * (2.0 / (Cin * 27)) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    cot = torch.randn((1, Cout) + size, generator=g)
+    xx = (torch.cat((x1, x2), 1) if C2 else x1).double().requires_grad_(True)
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    (F.conv3d(xx, wd, bd, padding=1) * cot.double()).sum().backward()
+    truth = (F.conv3d(xx, wd, bd, padding=1).detach(), xx.grad, wd.grad, bd.grad)
+    errs = {}
+    for impl in ("umma", "umma_f16x1"):
+        a1 = x1.to(cuda).requires_grad_(True)
+        a2 = x2.to(cuda).requires_grad_(True) if C2 else None
+        wg, bg = w.to(cuda).requires_grad_(True), b.to(cuda).requires_grad_(True)
+        with conv_impl(impl):
+            y = ops.conv3d(a1, wg, bg, x2=a2, stride=1, pad=1)
+            (y * cot.to(cuda)).sum().backward()
+        gx = torch.cat((a1.grad, a2.grad), 1) if C2 else a1.grad
+        errs[impl] = [rel_err(o, t) for o, t in zip((y, gx, wg.grad, bg.grad), truth)]
+    assert max(errs["umma"][:3]) < TOL, errs
+    assert max(errs["umma_f16x1"]) < F16X1_TOL, errs
+    # half-precision rounding is visible, i.e. the single-pass branch ran (forward and data gradient; the weight gradient
+    # of a narrow volume runs the 3xTF32 kernel, which has no single-pass mode)
+    assert min(errs["umma_f16x1"][:2]) > 1e-5, errs

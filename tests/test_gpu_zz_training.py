@@ -129,14 +129,17 @@ def test_graphed_step_equals_eager(cuda):
                     st["exp_avg"].zero_()
                     st["exp_avg_sq"].zero_()
             assert run.launches_per_step > 100
-        losses = [float(run(*b)) for b in batches]
-        results[mode] = (losses, [p.detach().clone() for p in bucket.params])
-    l_e, p_e = results["eager"]
+        losses, grads = [], None
+        for b in batches:
+            losses.append(float(run(*b)))
+            if grads is None:
+                grads = bucket.flat.clone()   # the first step's gradients (Adam reads the bucket, it does not clear it)
+        results[mode] = (losses, grads)
+    l_e, g_e = results["eager"]
     for mode in ("graph", "graph+tail"):
-        l_g, p_g = results[mode]
+        l_g, g_g = results[mode]
         for a, b in zip(l_e, l_g):
             assert abs(a - b) <= 1e-5 * abs(a), (mode, l_e, l_g)
-        # parameters: Adam's first updates are lr * sign(g), so a parameter whose gradient is pure round-off (a conv bias in
-        # front of a BatchNorm) moves by +-lr at random in both runs; the weights proper agree
-        errs = sorted(rel_err(a, b) for a, b in zip(p_g, p_e) if a.dim() == 5)
-        assert errs[len(errs) // 2] < 1e-3, (mode, errs)
+        assert rel_err(g_g, g_e) < 1e-4, mode
+        # (parameters are not compared: Adam's first updates are lr * sign(g), so every element whose gradient is round-off
+        # -- the anatomy term's scatter kernels add with atomics -- moves by +-lr at random in any two runs)
