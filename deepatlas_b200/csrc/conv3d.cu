@@ -679,17 +679,26 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
   out[i] = (float)acc;
 }
 
-// the same with one warp per element (lanes stride over the regions, xor-butterfly fold: still a fixed order): small
-// counts, where a thread per element leaves the GPU empty and walks up to 592 regions serially
+// small counts (a thread per element leaves the GPU empty and walks up to 592 regions serially): block = 32 consecutive
+// elements (lane = element: coalesced 128-byte rows) x 8 warps that deal the regions among themselves; fixed order
 __global__ void __launch_bounds__(256) reduce_partials_warp_kernel(const float* __restrict__ partials, int nregions, int64_t count,
                                                                    float* __restrict__ out, int accumulate) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= count) return;
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   double acc = 0.0;
-  for (int r = lane; r < nregions; r += 32) acc += (double)partials[(int64_t)r * count + i];
-  acc = warp_sum(acc);
-  if (lane == 0) out[i] = (float)(accumulate ? acc + (double)out[i] : acc);
+  if (i < count) {
+#pragma unroll 4
+    for (int r = wp; r < nregions; r += 8) acc += (double)partials[(int64_t)r * count + i];
+  }
+  red[wp][lane] = acc;
+  __syncthreads();
+  if (wp == 0 && i < count) {
+    double t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    out[i] = (float)(accumulate ? t + (double)out[i] : t);
+  }
 }
 
 // set by da_conv3d_wgrad_ex for the duration of the call: the gradient outputs are added to instead of overwritten
@@ -701,7 +710,7 @@ struct GradAccumulateScope {
 
 inline void launch_reduce_partials(const float* partials, int nregions, int64_t count, float* out, cudaStream_t stream) {
   if (nregions >= 16 && count <= 32768)
-    reduce_partials_warp_kernel<<<(unsigned)da_cdiv(count, 8), 256, 0, stream>>>(partials, nregions, count, out, g_grad_accumulate);
+    reduce_partials_warp_kernel<<<(unsigned)da_cdiv(count, 32), 256, 0, stream>>>(partials, nregions, count, out, g_grad_accumulate);
   else
     reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, nregions, count, out, g_grad_accumulate);
 }

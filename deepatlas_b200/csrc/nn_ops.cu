@@ -38,10 +38,11 @@ __device__ __forceinline__ float block_minmax(float v, bool is_max, float* red) 
 // partials [C][BN_SPLITS][4] (sum, sumsq, min, max) in fp64.  vec: V % 4 == 0 and 16-byte aligned base -> 16-byte loads, four
 // independent ones in flight per thread (a scalar one-load-per-iteration loop left half of the HBM bandwidth unused)
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __restrict__ x, int N, int C, int64_t V, int vec,
-                                                              double* __restrict__ partials) {
+                                                              double* __restrict__ partials, float* __restrict__ amax_slot) {
   __shared__ double red[BN_THREADS / 32];
   __shared__ float redm[2][BN_THREADS / 32];
   const int c = blockIdx.x, s = blockIdx.y;
+  if (amax_slot && c == 0 && s == 0 && threadIdx.x == 0) *amax_slot = 0.f;   // the finalize kernel folds into it with atomicMax
   double a1 = 0, a2 = 0;
   float vmin = INFINITY, vmax = -INFINITY;   // value range of the channel: bounds the layer's output (bn_finalize_kernel)
   for (int n = 0; n < N; ++n) {
@@ -87,34 +88,40 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
   }
 }
 
-// one block; amax_y (nullable): upper bound of max|act(gamma * xhat + beta)| over the whole tensor, from the channels'
+// warp = channel; amax_y (nullable, zeroed by the statistics kernel): upper bound of max|act(gamma * xhat + beta)| over the whole tensor, from the channels'
 // value ranges -- the next convolution's tensor-core path scales its fp16 operand pairs by it and skips its own pass
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ partials, int C, double M, float eps, float momentum,
                                                           float* __restrict__ mean, float* __restrict__ invstd,
                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           int act, float slope, float* __restrict__ amax_y) {
+  static_assert(BN_SPLITS <= 32, "one lane per split");
   __shared__ float redb[4];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float bound = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s1 = 0, s2 = 0, lo = INFINITY, hi = -INFINITY;
-    for (int s = 0; s < BN_SPLITS; ++s) {
-      const double* q = partials + ((int64_t)c * BN_SPLITS + s) * 4;
-      s1 += q[0];
-      s2 += q[1];
-      lo = fmin(lo, q[2]);
-      hi = fmax(hi, q[3]);
+  for (int c = blockIdx.x * nw + wp; c < C; c += gridDim.x * nw) {   // warp = channel, lane = split: fixed-order butterfly folds
+    const bool live = lane < BN_SPLITS;
+    const double* q = partials + ((int64_t)c * BN_SPLITS + (live ? lane : 0)) * 4;
+    double s1 = live ? q[0] : 0.0, s2 = live ? q[1] : 0.0, lo = live ? q[2] : INFINITY, hi = live ? q[3] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
     const double mu = s1 / M;
     double var = s2 / M - mu * mu;
     if (var < 0) var = 0;
     const double is = 1.0 / sqrt(var + (double)eps);
-    mean[c] = (float)mu;
-    invstd[c] = (float)is;
-    if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
-    if (running_var) {
-      const double unbiased = M > 1 ? var * M / (M - 1) : var;
-      running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    if (lane == 0) {
+      mean[c] = (float)mu;
+      invstd[c] = (float)is;
+      if (running_mean) running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mu);
+      if (running_var) {
+        const double unbiased = M > 1 ? var * M / (M - 1) : var;
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+      }
     }
     // act(gamma * xhat + beta) is monotone in xhat: its extreme magnitudes sit at the ends of the channel's value range
     const double ga = gamma ? (double)gamma[c] : 1.0, be = beta ? (double)beta[c] : 0.0;
@@ -123,14 +130,12 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
     if (act && y1 <= 0) y1 *= (double)slope;
     bound = fmaxf(bound, (float)(fmax(fabs(y0), fabs(y1)) * 1.00001));   // (+ the apply pass's fp32 round-off)
   }
-  if (amax_y) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-    if ((threadIdx.x & 31) == 0) redb[threadIdx.x >> 5] = bound;
+  if (amax_y) {   // (every lane of a warp holds the warp's bound)
+    if (lane == 0) redb[wp] = bound;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) bound = fmaxf(bound, redb[i]);
-      amax_y[0] = bound;
+      for (int i = 1; i < nw; ++i) bound = fmaxf(bound, redb[i]);
+      atomicMax(reinterpret_cast<unsigned int*>(amax_y), __float_as_uint(bound));   // non-negative floats order as unsigned ints
     }
   }
 }
@@ -166,9 +171,10 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
                                                                   const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   int N, int C, int64_t V, int act, float slope, int vec,
-                                                                  double* __restrict__ partials) {
+                                                                  double* __restrict__ partials, float* __restrict__ amax_slot) {
   __shared__ double red[BN_THREADS / 32];
   const int c = blockIdx.x, s = blockIdx.y;
+  if (amax_slot && c == 0 && s == 0 && threadIdx.x == 0) *amax_slot = 0.f;   // the finalize kernel folds into it with atomicMax
   const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
   double a1 = 0, a2 = 0;
   float mg = 0.f, mx = 0.f;   // max|dy|, max|xhat| of the channel: bound the layer's input gradient (bn_bwd_finalize_kernel)
@@ -221,39 +227,42 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
   }
 }
 
-// one block; amax_dx (nullable): upper bound of max|dx| over the whole tensor,
+// warp = channel; amax_dx (nullable, zeroed by the statistics kernel): upper bound of max|dx| over the whole tensor,
 //   |dx| <= |gamma invstd| (max|g| + |s1| / M + max|xhat| |s2| / M)   with |g| <= |dy| (slopes <= 1)
 __global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const double* __restrict__ partials, int C, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta, float* __restrict__ s12,
                                                               const float* __restrict__ invstd, const float* __restrict__ gamma, double invM,
                                                               int training, float* __restrict__ amax_dx, int accumulate) {
   __shared__ float redb[4];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float bound = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s1 = 0, s2 = 0, mg = 0, mx = 0;
-    for (int s = 0; s < BN_SPLITS; ++s) {
-      const double* q = partials + ((int64_t)c * BN_SPLITS + s) * 4;
-      s1 += q[0];
-      s2 += q[1];
-      mg = fmax(mg, q[2]);
-      mx = fmax(mx, q[3]);
+  for (int c = blockIdx.x * nw + wp; c < C; c += gridDim.x * nw) {   // warp = channel, lane = split
+    const bool live = lane < BN_SPLITS;
+    const double* q = partials + ((int64_t)c * BN_SPLITS + (live ? lane : 0)) * 4;
+    double s1 = live ? q[0] : 0.0, s2 = live ? q[1] : 0.0, mg = live ? q[2] : 0.0, mx = live ? q[3] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      mg = fmax(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if (dbeta) dbeta[c] = (float)(accumulate ? s1 + (double)dbeta[c] : s1);
-    if (dgamma) dgamma[c] = (float)(accumulate ? s2 + (double)dgamma[c] : s2);
-    s12[2 * c] = (float)s1;
-    s12[2 * c + 1] = (float)s2;
+    if (lane == 0) {
+      if (dbeta) dbeta[c] = (float)(accumulate ? s1 + (double)dbeta[c] : s1);
+      if (dgamma) dgamma[c] = (float)(accumulate ? s2 + (double)dgamma[c] : s2);
+      s12[2 * c] = (float)s1;
+      s12[2 * c + 1] = (float)s2;
+    }
     const double k = fabs((gamma ? (double)gamma[c] : 1.0) * (double)invstd[c]);
     const double b = training ? k * (mg + fabs(s1) * invM + mx * fabs(s2) * invM) : k * mg;
     bound = fmaxf(bound, (float)(b * 1.00001));
   }
   if (amax_dx) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(0xffffffffu, bound, o));
-    if ((threadIdx.x & 31) == 0) redb[threadIdx.x >> 5] = bound;
+    if (lane == 0) redb[wp] = bound;
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int i = 1; i < (int)(blockDim.x >> 5); ++i) bound = fmaxf(bound, redb[i]);
-      amax_dx[0] = bound;
+      for (int i = 1; i < nw; ++i) bound = fmaxf(bound, redb[i]);
+      atomicMax(reinterpret_cast<unsigned int*>(amax_dx), __float_as_uint(bound));
     }
   }
 }
@@ -444,8 +453,8 @@ DA_API int da_bn_stats_ex(const float* x, int N, int C, int64_t V, float eps, fl
   DA_REQUIRE(x && mean && invstd && workspace, "da_bn_stats: null pointer");
   if (workspace_bytes < da_bn_workspace_bytes(C)) { da_set_error("da_bn_stats: workspace too small"); return DA_ERR_WORKSPACE; }
   dim3 grid(C, BN_SPLITS);
-  bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, ((V & 3) == 0 && aligned16(x)) ? 1 : 0, (double*)workspace);
-  bn_finalize_kernel<<<1, 128, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean, invstd,
+  bn_stats_kernel<<<grid, BN_THREADS, 0, stream>>>(x, N, C, V, ((V & 3) == 0 && aligned16(x)) ? 1 : 0, (double*)workspace, amax_y);
+  bn_finalize_kernel<<<(C + 3) / 4, 128, 0, stream>>>((const double*)workspace, C, (double)N * (double)V, eps, momentum, mean, invstd,
                                             running_mean, running_var, gamma, beta, act, slope, amax_y);
   return da_check_launch("da_bn_stats", 2);
 }
@@ -483,8 +492,8 @@ DA_API int da_bn_act_bwd_ex(const float* dy, const float* x, const float* mean, 
   dim3 g1(C, BN_SPLITS);
   const int vec = ((V & 3) == 0 && aligned16(x) && aligned16(dy) && aligned16(dx)) ? 1 : 0;
   const double invM = 1.0 / ((double)N * (double)V);
-  bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, vec, partials);
-  bn_bwd_finalize_kernel<<<1, 128, 0, stream>>>(partials, C, dgamma, dbeta, s12, invstd, gamma, invM, training, amax_dx, accumulate);
+  bn_bwd_stats_kernel<<<g1, BN_THREADS, 0, stream>>>(dy, x, mean, invstd, gamma, beta, N, C, V, act, slope, vec, partials, amax_dx);
+  bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, stream>>>(partials, C, dgamma, dbeta, s12, invstd, gamma, invM, training, amax_dx, accumulate);
   dim3 g2(ew_grid(V, 1024) > 512 ? 512 : ew_grid(V, 1024), C, N);
   bn_act_bwd_kernel<<<g2, 256, 0, stream>>>(dy, x, mean, invstd, gamma, beta, s12, C, V, (float)invM, training, act, slope, vec, dx);
   return da_check_launch("da_bn_act_bwd", 3);
