@@ -320,14 +320,26 @@ __global__ void __launch_bounds__(DT_THREADS, 2)
       }
 }
 
-// accumulate: out[i] += the sum (a parameter gradient that already holds an earlier contribution of the same step)
-__global__ void dc_reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count, float* __restrict__ out,
-                                          int accumulate) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  float acc = 0.f;
-  for (int r = 0; r < nregions; ++r) acc += partials[(int64_t)r * count + i];
-  out[i] = accumulate ? out[i] + acc : acc;
+// out[i] (+)= sum_r partials[r][i], fixed order: block = 32 consecutive elements (coalesced rows) x 8 warps that deal the
+// regions among themselves.  accumulate: a parameter gradient that already holds an earlier contribution of the same step.
+__global__ void __launch_bounds__(256) dc_reduce_partials_kernel(const float* __restrict__ partials, int nregions, int64_t count,
+                                                                 float* __restrict__ out, int accumulate) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (i < count) {
+#pragma unroll 4
+    for (int r = wp; r < nregions; r += 8) acc += (double)partials[(int64_t)r * count + i];
+  }
+  red[wp][lane] = acc;
+  __syncthreads();
+  if (wp == 0 && i < count) {
+    double t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t += red[w][lane];
+    out[i] = (float)(accumulate ? t + (double)out[i] : t);
+  }
 }
 __global__ void dc_add_kernel(float* __restrict__ out, const float* __restrict__ v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,10 +478,10 @@ DA_API int da_deconv_k2s2_wgrad_ex(const float* x, const float* dy, float* grad_
     else deconv_k2s2_wgrad_mma_kernel<64><<<grid, 256, 0, stream>>>(x, dy, partials, bias_partials, N, Cout, D, H, W, (int)spr);
     int rc = da_check_launch("da_deconv_k2s2_wgrad/mma");
     if (rc) return rc;
-    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>(partials, (int)nregions, count, grad_weight, accumulate);
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 32), 256, 0, stream>>>(partials, (int)nregions, count, grad_weight, accumulate);
     rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
     if (rc || !grad_bias) return rc;
-    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 256), 256, 0, stream>>>(bias_partials, (int)nregions, Cout, grad_bias, accumulate);
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(Cout, 32), 256, 0, stream>>>(bias_partials, (int)nregions, Cout, grad_bias, accumulate);
     return da_check_launch("da_deconv_k2s2_wgrad/bias-reduce");
   }
   if ((W & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) == 0 && da_get_encode_tiled() != nullptr) {
@@ -497,7 +509,7 @@ DA_API int da_deconv_k2s2_wgrad_ex(const float* x, const float* dy, float* grad_
     deconv_k2s2_wgrad_tma_kernel<<<dim3(groups, nregions), DT_THREADS, DT_SMEM_BYTES, stream>>>(mx, mdy, a);
     int rc = da_check_launch("da_deconv_k2s2_wgrad_tma");
     if (rc) return rc;
-    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight, accumulate);
+    dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 32), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight, accumulate);
     rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
     if (rc || !grad_bias) return rc;
     return dc_bias_sum(dy, N, Cout, (int64_t)8 * D * H * W, grad_bias, accumulate, workspace, workspace_bytes, stream);
@@ -511,7 +523,7 @@ DA_API int da_deconv_k2s2_wgrad_ex(const float* x, const float* dy, float* grad_
   deconv_k2s2_wgrad_kernel<<<grid, DW_THREADS, 0, stream>>>(x, dy, (float*)workspace, N, Cin, Cout, D, H, W, rpr, total_rows);
   int rc = da_check_launch("da_deconv_k2s2_wgrad");
   if (rc) return rc;
-  dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 256), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight, accumulate);
+  dc_reduce_partials_kernel<<<(unsigned)da_cdiv(count, 32), 256, 0, stream>>>((const float*)workspace, nregions, count, grad_weight, accumulate);
   rc = da_check_launch("da_deconv_k2s2_wgrad/reduce");
   if (rc || !grad_bias) return rc;
   // the weight partials have been consumed by the reduce above (same stream): reuse the workspace head

@@ -76,14 +76,17 @@ __global__ void __launch_bounds__(WD_THREADS) warp_dice_fwd_kernel(const float* 
   }
 }
 
-__global__ void warp_dice_finalize_kernel(const float* __restrict__ partials, int nblocks, int C3, float* __restrict__ sums) {
-  const int n = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride over the blocks' partial rows, fixed-order fp64 fold
+__global__ void __launch_bounds__(256) warp_dice_finalize_kernel(const float* __restrict__ partials, int nblocks, int C3,
+                                                                 float* __restrict__ sums) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= C3) return;
   const float* p = partials + (int64_t)n * nblocks * C3 + i;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += (double)p[(int64_t)b * C3];
-  sums[(int64_t)n * C3 + i] = (float)acc;
+  for (int b = lane; b < nblocks; b += 32) acc += (double)p[(int64_t)b * C3];
+  acc = warp_sum(acc);
+  if (lane == 0) sums[(int64_t)n * C3 + i] = (float)acc;
 }
 
 // grad_prob[c][q] = gS_c * Wsum[q] + gI_c * L_c[q]   (in place on the L accumulator)
@@ -210,21 +213,23 @@ __global__ void __launch_bounds__(256) wd2_dot_kernel(const float* __restrict__ 
 }
 
 // sums [N][3][C] from the two partial arrays
-__global__ void wd2_finalize_kernel(const float* __restrict__ pS, int nbS, const float* __restrict__ pTI, int nbTI, int C,
-                                    float* __restrict__ sums) {
-  const int n = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) wd2_finalize_kernel(const float* __restrict__ pS, int nbS, const float* __restrict__ pTI, int nbTI,
+                                                           int C, float* __restrict__ sums) {
+  // one warp per output element (a single thread per element walked up to 1184 partial rows serially: 158 us)
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= 3 * C) return;
   const int q = i / C, ch = i - q * C;
   double acc = 0.0;
   if (q == 0) {
     const float* p = pS + (int64_t)n * nbS * C + ch;
-    for (int b = 0; b < nbS; ++b) acc += (double)p[(int64_t)b * C];
+    for (int b = lane; b < nbS; b += 32) acc += (double)p[(int64_t)b * C];
   } else {
     const float* p = pTI + (int64_t)n * nbTI * 2 * C + (q - 1) * C + ch;
-    for (int b = 0; b < nbTI; ++b) acc += (double)p[(int64_t)b * 2 * C];
+    for (int b = lane; b < nbTI; b += 32) acc += (double)p[(int64_t)b * 2 * C];
   }
-  sums[(int64_t)n * 3 * C + i] = (float)acc;
+  acc = warp_sum(acc);
+  if (lane == 0) sums[(int64_t)n * 3 * C + i] = (float)acc;
 }
 
 // Q[q] = sum_c gS_c P[c][q]
@@ -366,7 +371,7 @@ DA_API int da_warp_dice_sums_fwd(const float* prob, const float* field, int add_
 #undef CALL
     rc = da_check_launch("da_warp_dice_sums_fwd/dot");
     if (rc) return rc;
-    wd2_finalize_kernel<<<dim3((3 * C + 127) / 128, N), 128, 0, stream>>>(pS, nbd, pTI, nb, C, sums);
+    wd2_finalize_kernel<<<dim3((3 * C + 7) / 8, N), 256, 0, stream>>>(pS, nbd, pTI, nb, C, sums);
     return da_check_launch("da_warp_dice_sums_fwd/finalize");
   }
 #define CALL(CP)                                                                                                          \
@@ -378,8 +383,8 @@ DA_API int da_warp_dice_sums_fwd(const float* prob, const float* field, int add_
 #undef CALL
   int rc = da_check_launch("da_warp_dice_sums_fwd");
   if (rc) return rc;
-  dim3 g2((3 * C + 127) / 128, N);
-  warp_dice_finalize_kernel<<<g2, 128, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
+  dim3 g2((3 * C + 7) / 8, N);
+  warp_dice_finalize_kernel<<<g2, 256, 0, stream>>>((const float*)workspace, nb, 3 * C, sums);
   return da_check_launch("da_warp_dice_sums_fwd/finalize");
 }
 

@@ -339,6 +339,12 @@ def test_softmax_dice_with_probs_equals_the_two_pass_form(cuda, C, dtype):
     (3.0 * lb + (pb * cot).sum()).backward()
     assert torch.equal(la, lb) and torch.equal(pa, pb)
     assert rel_err(xa.grad, xb.grad) < 1e-5
+    # ... and against the CPU oracle (softmax + DiceLossMultiClass of the reference), values and the combined gradient
+    from oracle import ref_port as P
+    xo = x.clone().requires_grad_(True)
+    lo, po = P.dice_multiclass(xo, t.cpu().long(), C, "Uniform", False, True, 1e-6), torch.softmax(xo, 1)
+    (3.0 * lo + (po * cot.cpu()).sum()).backward()
+    assert rel_err(la, lo) < TOL and rel_err(pa, po) < TOL and rel_err(xa.grad, xo.grad) < TOL
     # only one of the two outputs used downstream
     xc = x.to(cuda).requires_grad_(True)
     lc, _ = crit.forward_with_probs(xc, t)
@@ -404,3 +410,41 @@ def test_head_softmax_dice_vs_oracle(cuda, C, dtype, size):
     fg3 = feat.to(cuda).requires_grad_(True)
     loss3 = crit(head(fg3), t.to(dtype).to(cuda))
     assert rel_err(loss3, loss2) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["convT3_res", "k2s2", "conv_res"])
+def test_vm_blocks_residual_and_deconv_vs_reference_semantics(cuda, kind):
+    """modules.convBlock(residual=True) (``x += x``, modules.py:59-60) and modules.deconvBlock (ConvTranspose3d k3 s1 p1 with
+    ``x += input``, k2 s2; modules.py:65-86) on the GPU against their restatement on torch's CPU ops: values, input and
+    parameter gradients."""
+    import torch.nn.functional as F
+
+    from deepatlas_b200 import networks as M
+    g = _g()
+    C, size = 8, (6, 8, 10)
+    x = torch.randn((2, C) + size, generator=g)
+    if kind == "conv_res":
+        blk = M.convBlockVM(C, C, stride=1, bias=True, residual=True).to(cuda)
+        w, b = blk.conv.weight, blk.conv.bias
+        ref = lambda xx, ww, bb: 2.0 * torch.relu(F.conv3d(xx, ww, bb, padding=1))  # noqa: E731
+    elif kind == "convT3_res":
+        blk = M.deconvBlockVM(C, C, 3, stride=1, padding=1, bias=True, residual=True).to(cuda)
+        w, b = blk.deconv.weight, blk.deconv.bias
+        ref = lambda xx, ww, bb: torch.relu(F.conv_transpose3d(xx, ww, bb, stride=1, padding=1)) + xx  # noqa: E731
+    else:
+        blk = M.deconvBlockVM(C, 12, 2, stride=2, bias=True).to(cuda)
+        w, b = blk.deconv.weight, blk.deconv.bias
+        ref = lambda xx, ww, bb: torch.relu(F.conv_transpose3d(xx, ww, bb, stride=2))  # noqa: E731
+    with torch.no_grad():
+        w.copy_((torch.randn(w.shape, generator=g) * 0.2).to(cuda))
+        b.copy_((torch.randn(b.shape, generator=g) * 0.1).to(cuda))
+    xg = x.to(cuda).requires_grad_(True)
+    y = blk(xg)
+    xc, wc, bc = x.clone().requires_grad_(True), w.detach().cpu().clone().requires_grad_(True), b.detach().cpu().clone().requires_grad_(True)
+    yc = ref(xc, wc, bc)
+    cot = torch.randn(yc.shape, generator=g)
+    (y * cot.to(cuda)).sum().backward()
+    (yc * cot).sum().backward()
+    assert rel_err(y, yc) < TOL
+    for name, a, r in (("dx", xg.grad, xc.grad), ("dw", w.grad, wc.grad), ("db", b.grad, bc.grad)):
+        assert rel_err(a, r) < 2 * TOL, (kind, name)
