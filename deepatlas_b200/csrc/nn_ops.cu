@@ -15,6 +15,13 @@ constexpr int BN_THREADS = 256;
 #define DA_BN_SPLITS 32
 #endif
 constexpr int BN_SPLITS = DA_BN_SPLITS;  // blocks per channel for the statistics passes
+// -DDA_BN_REVERSE=1 makes the statistics passes walk their tensor from its END (the producing kernel's last ~100 MB
+// should still be in the 126 MB L2, and blocks are dispatched in blockIdx order).  Measured on one box against the
+// forward order (tools/ab_bench.py, three rounds): 44.87 vs 44.75 ms per step, i.e. nothing -- left off.
+#ifndef DA_BN_REVERSE
+#define DA_BN_REVERSE 0
+#endif
+constexpr bool BN_REVERSE = DA_BN_REVERSE != 0;
 
 __device__ __forceinline__ float act_fwd(float z, int act, float slope) { return (act && z <= 0.f) ? z * slope : z; }
 __device__ __forceinline__ float act_grad(float z, int act, float slope) { return (act && z <= 0.f) ? slope : 1.f; }
@@ -41,7 +48,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const float* __res
                                                               double* __restrict__ partials, float* __restrict__ amax_slot) {
   __shared__ double red[BN_THREADS / 32];
   __shared__ float redm[2][BN_THREADS / 32];
-  const int c = blockIdx.x, s = blockIdx.y;
+  const int c = blockIdx.x, s = BN_REVERSE ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
   if (amax_slot && c == 0 && s == 0 && threadIdx.x == 0) *amax_slot = 0.f;   // the finalize kernel folds into it with atomicMax
   double a1 = 0, a2 = 0;
   float vmin = INFINITY, vmax = -INFINITY;   // value range of the channel: bounds the layer's output (bn_finalize_kernel)
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const float* _
                                                                   int N, int C, int64_t V, int act, float slope, int vec,
                                                                   double* __restrict__ partials, float* __restrict__ amax_slot) {
   __shared__ double red[BN_THREADS / 32];
-  const int c = blockIdx.x, s = blockIdx.y;
+  const int c = blockIdx.x, s = BN_REVERSE ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
   if (amax_slot && c == 0 && s == 0 && threadIdx.x == 0) *amax_slot = 0.f;   // the finalize kernel folds into it with atomicMax
   const float mu = mean[c], is = invstd[c], ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
   double a1 = 0, a2 = 0;

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def run(env_extra, steps, warmup):
     env = dict(os.environ)
     env.update(env_extra)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(steps), "--warmup", str(warmup), "--no-cpu-baseline"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(steps), "--warmup", str(warmup), "--no-cpu-baseline", "--no-torch-cuda", "--no-parity"],
                          env=env, capture_output=True, text=True, cwd=ROOT)
     for line in reversed(out.stdout.strip().splitlines()):
         if line.startswith("{"):
