@@ -467,13 +467,16 @@ def run_ours(args, wl):
         roofline = tensor_roofline(
             "conv3d_umma_kernel (decBlock2.0 forward cat(32,16) -> 16 @160x192x160; tcgen05 kind::f16, 3xFP16 split): "
             "absmax + weight image + one 32-channel and one 16-channel launch", fw_ms, f_bytes,
-            {"traffic": None, "traffic_source": "see profiles/ (r02 ncu capture of this layer); the second launch re-reads and re-writes Y",
+            {"traffic": 1.513e9, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of the two tcgen05 launches of this layer "
+                                                  "(profiles/r02_ncu_a_conv_umma_tma_in_32ch.csv: 642 + 287 MB; r02_ncu_r02_umma_16ch.csv: 316 + 267 MB) "
+                                                  "against 1.258 GB algorithmic: the 16-channel launch re-reads and re-writes Y",
              "step": {"algorithmic_bytes": wl["algo_bytes"], "achieved": wl["algo_bytes"] / (ms * 1e-3) / 1e9,
                       "frac": wl["algo_bytes"] / (ms * 1e-3) / 1e9 / hbm_peak}})
         roofline_wgrad = tensor_roofline(
             "conv3d_wgrad_umma16_kernel<32> (decBlock2.0 weight gradient, cat(32,16) x dY16 @160x192x160; tcgen05 3xFP16, one launch) "
             "+ absmax + region reduce + bias sum", wg_ms, k_bytes,
-            {"traffic": None, "note": "128-row MMAs carry 96 useful rows (kx = 0..2 x 32 ci) in the 32-channel block and 48 in the padded 16-channel one"})
+            {"traffic": 1.323e9, "traffic_source": "ncu --set full (profiles/r02_ncu_r02_wgrad16.csv): 1.319 GB read + 4.4 MB written against 1.258 GB algorithmic",
+             "note": "128-row MMAs carry 96 useful rows (kx = 0..2 x 32 ci) in the 32-channel block and 48 in the padded 16-channel one"})
         cpu = parity = tcuda = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
