@@ -283,7 +283,7 @@ def run_ours(args, wl):
 
     torch.manual_seed(230)
     if wl["kind"] == "joint":
-        model = JointModel(n_classes=CLASSES).to(dev)
+        model = JointModel(n_classes=CLASSES, overlap_reg=not (args.no_overlap or os.environ.get("DA_BENCH_NO_OVERLAP") == "1")).to(dev)
     elif wl["kind"] == "reg":
         model = RegOnlyModel().to(dev)
     else:
@@ -304,6 +304,8 @@ def run_ours(args, wl):
         bucket.zero()
         loss, _ = model.joint_loss(*batch)
         loss.backward()
+        if hasattr(model, "join_streams"):
+            model.join_streams()   # the registration branch's backward ran on its side stream
         return loss.detach()
 
     def update():
@@ -531,6 +533,7 @@ def main():
     ap.add_argument("--no-torch-cuda", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of the captured CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="joint step: registration net on the main stream (no side-stream overlap)")
     ap.add_argument("--precision", default=None, choices=["fp32", "f16x1"],
                     help="k3 convolutions: fp32-grade 3xFP16 (default, all configs but c2) or the single-pass reduced-precision mode (c2)")
     args = ap.parse_args()

@@ -27,8 +27,16 @@ DEFAULT_LAMBDAS = dict(sim=1.0, reg=1000.0, ana=1.0, sup=1.0)
 
 
 class JointModel(nn.Module):
-    def __init__(self, n_classes=32, in_channel=1, seg_name="UNet_light", lambdas=None):
+    def __init__(self, n_classes=32, in_channel=1, seg_name="UNet_light", lambdas=None, overlap_reg=False):
+        """``overlap_reg``: run the registration network on a side stream next to the two segmentation passes (they
+        share no state: the registration net has no BatchNorm, parameters are read-only in the forward, its gradients
+        land in its own bucket slots).  Small low-resolution kernels of one branch then fill SMs the other leaves idle;
+        inside a captured CUDA graph the two branches become parallel paths.  The backward of each branch runs on the
+        stream of its forward (autograd's rule); call ``join_streams()`` after ``backward()`` and before anything on the
+        current stream reads the registration net's gradients (an optimizer step, an all-reduce)."""
         super().__init__()
+        self.overlap_reg = bool(overlap_reg)
+        self._side = None
         self.n_classes = n_classes
         self.seg = get_network(seg_name)(in_channel, n_classes, bias=True, BN=True)
         self.reg = get_network("voxel_morph_cvpr")()
@@ -45,6 +53,44 @@ class JointModel(nn.Module):
     def trainable_parameters(self):
         return list(self.seg.parameters()) + list(self.reg.parameters())
 
+    def _side_stream(self, device):
+        if self._side is None or self._side.device != device:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
+    def join_streams(self):
+        """Make the current stream wait for the side stream (after ``backward()`` with ``overlap_reg``)."""
+        if self.overlap_reg and self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+
+    def _run_reg(self, I_m, I_t):
+        """Registration branch: network, warp, and the two losses that depend on nothing else (similarity, bending
+        energy).  Returns (disp, I_w, phi, sim, reg)."""
+        def branch():
+            disp, I_w, phi = self.reg(I_m, I_t)
+            return disp, I_w, phi, self.sim_loss(I_w, I_t), self.reg_loss(disp)
+        if not (self.overlap_reg and I_m.is_cuda):
+            return branch()
+        # the side stream waits for the fork event recorded at the START of joint_loss, not for the segmentation passes
+        # that the host has enqueued in between (the host-side call order stays seg, seg, reg)
+        side = self._side_stream(I_m.device)
+        side.wait_event(self._fork)
+        with torch.cuda.stream(side):
+            out = branch()
+        return out
+
+    def _fork_here(self, ref):
+        if self.overlap_reg and ref.is_cuda:
+            self._fork = torch.cuda.Event()
+            self._fork.record(torch.cuda.current_stream(ref.device))
+
+    def _join_reg(self, outs):
+        if self.overlap_reg and self._side is not None and outs[0].is_cuda:
+            main = torch.cuda.current_stream(outs[0].device)
+            main.wait_stream(self._side)
+            for t in outs:
+                t.record_stream(main)
+
     def joint_loss(self, I_m, S_m, I_t, S_t):
         """I_*: (1,1,D,H,W) fp32 images; S_*: (1,D,H,W) integer label maps (uint8 is read directly)."""
         lam = self.lambdas
@@ -54,15 +100,19 @@ class JointModel(nn.Module):
             # the class head, softmax and the Dice sums as one kernel each way: the 32-class logits (629 MB per volume at
             # 160x192x160) and their gradient never reach HBM; for the moving image the same pass writes the
             # probabilities that the anatomy term warps, and the backward takes both of their gradients
+            self._fork_here(I_m)
             F_m = self.seg.forward_features(I_m)
             F_t = self.seg.forward_features(I_t)
-            disp, I_w, phi = self.reg(I_m, I_t)
+            disp, I_w, phi, sim, reg = self._run_reg(I_m, I_t)     # (side stream with overlap_reg)
             sup_m, prob_m = self.sup_dice.forward_head(F_m, self.seg.head, S_m, want_probs=True)
             sup_t, _ = self.sup_dice.forward_head(F_t, self.seg.head, S_t)
+            self._join_reg((disp, I_w, phi, sim, reg))
         else:
+            self._fork_here(I_m)
             P_m = self.seg(I_m)
             P_t = self.seg(I_t)
-            disp, I_w, phi = self.reg(I_m, I_t)
+            disp, I_w, phi, sim, reg = self._run_reg(I_m, I_t)
+            self._join_reg((disp, I_w, phi, sim, reg))
             # softmax(P_m) has two consumers (supervised Dice, anatomy term): one pass yields the Dice sums AND the
             # probabilities, and one backward pass takes both gradients (no separate softmax, no sum of two gradients)
             if mode == "1":
@@ -71,8 +121,8 @@ class JointModel(nn.Module):
                 sup_m, prob_m = self.sup_dice.forward_with_probs(P_m, S_m)
             sup_t = self.sup_dice(P_t, S_t)
         parts = {
-            "sim": self.sim_loss(I_w, I_t),
-            "reg": self.reg_loss(disp),
+            "sim": sim,
+            "reg": reg,
             # dice(grid_sample(softmax(P_m), phi), onehot(S_t)): warp and Dice sums fused, labels stand for the one-hot
             "ana": self.ana_dice.forward_warped(prob_m, phi, S_t),
             "sup": sup_m + sup_t,

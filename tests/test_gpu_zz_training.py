@@ -143,3 +143,40 @@ def test_graphed_step_equals_eager(cuda):
         assert rel_err(g_g, g_e) < 1e-4, mode
         # (parameters are not compared: Adam's first updates are lr * sign(g), so every element whose gradient is round-off
         # -- the anatomy term's scatter kernels add with atomics -- moves by +-lr at random in any two runs)
+
+
+def test_overlapped_registration_branch_equals_serial(cuda):
+    """JointModel(overlap_reg=True) runs the registration network on a side stream next to the segmentation passes
+    (forward and, by autograd's stream rule, backward): same loss and gradients as the serial order, eagerly and inside a
+    captured graph (where the two branches become parallel paths)."""
+    from deepatlas_b200.dist import FlatGradBucket
+    from deepatlas_b200.graph import GraphedStep
+    from deepatlas_b200.joint import JointModel, make_synthetic_pair
+    n_classes, size = 4, (16, 24, 16)
+    batch = make_synthetic_pair(size, n_classes, seed=411, device=cuda)
+    out = {}
+    for mode in ("serial", "overlap", "overlap+graph"):
+        torch.manual_seed(230)
+        model = JointModel(n_classes=n_classes, overlap_reg=mode != "serial").to(cuda)
+        model.weights_init()
+        bucket = FlatGradBucket(model.trainable_parameters())
+
+        def compute(*b):
+            bucket.zero()
+            loss, _ = model.joint_loss(*b)
+            loss.backward()
+            model.join_streams()
+            return loss.detach()
+
+        if mode == "overlap+graph":
+            state = {k: v.clone() for k, v in model.state_dict().items()}
+            run = GraphedStep(compute, batch, warmup=2)
+            model.load_state_dict(state)     # (the warm-up runs moved the BatchNorm running statistics only)
+        else:
+            run = compute
+        loss = float(run(*batch))
+        torch.cuda.synchronize()
+        out[mode] = (loss, bucket.flat.clone())
+    for mode in ("overlap", "overlap+graph"):
+        assert abs(out[mode][0] - out["serial"][0]) <= 1e-6 * abs(out["serial"][0]), mode
+        assert rel_err(out[mode][1], out["serial"][1]) < 1e-5, mode
