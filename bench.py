@@ -277,6 +277,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     _lib.load()
     SIZE, CLASSES = wl["size"], wl["classes"]
+    ops.set_wgrad_overlap(not (args.no_overlap or os.environ.get("DA_BENCH_NO_WGRAD_OVERLAP") == "1"))
     precision = args.precision or wl.get("precision", "fp32")
     if precision == "f16x1":
         _lib.call("da_set_conv_split", 2)
@@ -306,6 +307,7 @@ def run_ours(args, wl):
         loss.backward()
         if hasattr(model, "join_streams"):
             model.join_streams()   # the registration branch's backward ran on its side stream
+        ops.join_wgrad_stream()    # weight gradients run on theirs
         return loss.detach()
 
     def update():

@@ -59,9 +59,11 @@ class JointModel(nn.Module):
         return self._side
 
     def join_streams(self):
-        """Make the current stream wait for the side stream (after ``backward()`` with ``overlap_reg``)."""
+        """Make the current stream wait for the side streams (after ``backward()``): the registration branch's and the
+        weight-gradient stream of ``ops.set_wgrad_overlap``."""
         if self.overlap_reg and self._side is not None:
             torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+        ops.join_wgrad_stream()
 
     def _run_reg(self, I_m, I_t):
         """Registration branch: network, warp, and the two losses that depend on nothing else (similarity, bending

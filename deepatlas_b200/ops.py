@@ -71,6 +71,35 @@ def _grad_dst(p, wanted: bool):
     return g
 
 
+# Weight gradients on a side stream.  A convolution's weight gradient has no consumer before the optimizer step, so (when
+# it is accumulated in place, i.e. nothing is handed back to autograd) it can leave the backward chain: it is launched on a
+# per-device side stream as soon as dy exists, and the chain (data gradient -> batch-norm backward -> next data gradient)
+# continues on the calling stream.  The tcgen05 kernels own a whole SM each, so two of them never share one, but the
+# HBM-bound elementwise kernels of the chain run next to the shared-memory-bound weight-gradient kernels.
+# ``join_wgrad_stream()`` must be called after backward() and before the gradients are read.
+_WGRAD_OVERLAP = False
+_WGRAD_SIDE = {}
+
+
+def set_wgrad_overlap(on: bool):
+    global _WGRAD_OVERLAP
+    _WGRAD_OVERLAP = bool(on)
+
+
+def _wgrad_side(device):
+    st = _WGRAD_SIDE.get(device.index)
+    if st is None:
+        st = _WGRAD_SIDE[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def join_wgrad_stream():
+    """The current stream waits for every weight gradient launched on the side stream of the current device."""
+    st = _WGRAD_SIDE.get(torch.cuda.current_device()) if torch.cuda.is_available() else None
+    if st is not None:
+        torch.cuda.current_stream().wait_stream(st)
+
+
 def _check_device(t: torch.Tensor, name: str):
     """Kernels launch on the CURRENT device's current stream (``_stream()``): a tensor living on another GPU would be
     dereferenced in the wrong context.  Fail loudly instead; ``with torch.cuda.device(t.device):`` is the fix."""
@@ -543,6 +572,39 @@ class Conv3dFunction(torch.autograd.Function):
         dy_valid = 1
         if amax_dy is None:
             amax_dy, dy_valid = torch.empty((1,), dtype=torch.float32, device=dy.device), 0
+        want_w = ctx.needs_input_grad[2] or (has_bias and ctx.needs_input_grad[3])
+        gw_dst = gb_dst = None
+        inplace = False
+        if want_w:
+            bias = ctx.bias_ref
+            gw_dst = _grad_dst(weight, ctx.needs_input_grad[2])
+            gb_dst = _grad_dst(bias, has_bias and ctx.needs_input_grad[3]) if has_bias else None
+            inplace = gw_dst is not None and (not has_bias or gb_dst is not None)
+
+        def wgrad(stream, valid):
+            dw_ = gw_dst if inplace else torch.empty_like(weight)
+            db_ = (gb_dst if inplace else torch.empty((Cout,), dtype=torch.float32, device=dy.device)) if has_bias else None
+            nbw = _lib.size("da_conv3d_wgrad_workspace_bytes", Cin, Cout, ks)
+            wsw = _ws(nbw, dy.device)
+            _lib.call("da_conv3d_wgrad_ex", _p(x1), C1, _p(x2), C2, _p(dy), int(transposed), _p(dw_), _p(db_), N, Di, Hi,
+                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, stream, _p(ctx.amax_x), 1, _p(amax_dy), valid, int(inplace))
+            return (None, None) if inplace else (dw_, db_)   # in place: already added to weight.grad / bias.grad
+
+        side_wgrad = want_w and inplace and _WGRAD_OVERLAP
+        if side_wgrad:
+            # off the chain: the weight gradient starts as soon as dy (and its max-abs bound) exist
+            if not dy_valid:
+                _lib.call("da_absmax", _p(dy), dy.numel(), None, 0, _p(amax_dy), st)
+                dy_valid = 1
+            cur, side = torch.cuda.current_stream(dy.device), _wgrad_side(dy.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                wgrad(_stream(), 1)
+            for t in (x1, x2, dy, ctx.amax_x, amax_dy):
+                if t is not None:
+                    t.record_stream(side)
         if ctx.needs_input_grad[0]:
             dx1 = torch.empty_like(x1)
             _lib.call("da_conv3d_dgrad_ex", _p(dy), _p(weight), int(transposed), _p(dx1), N, Cin, 0, C1, Cout, Di, Hi,
@@ -553,19 +615,8 @@ class Conv3dFunction(torch.autograd.Function):
             _lib.call("da_conv3d_dgrad_ex", _p(dy), _p(weight), int(transposed), _p(dx2), N, Cin, C1, C2, Cout, Di, Hi,
                       Wi, ks, stride, pad, _p(ws), nb, st, _p(amax_dy), dy_valid)
             dy_valid = 1
-        if ctx.needs_input_grad[2] or (has_bias and ctx.needs_input_grad[3]):
-            bias = ctx.bias_ref
-            gw_dst = _grad_dst(weight, ctx.needs_input_grad[2])
-            gb_dst = _grad_dst(bias, has_bias and ctx.needs_input_grad[3]) if has_bias else None
-            inplace = gw_dst is not None and (not has_bias or gb_dst is not None)
-            dw = gw_dst if inplace else torch.empty_like(weight)
-            db = (gb_dst if inplace else torch.empty((Cout,), dtype=torch.float32, device=dy.device)) if has_bias else None
-            nbw = _lib.size("da_conv3d_wgrad_workspace_bytes", Cin, Cout, ks)
-            wsw = _ws(nbw, dy.device)
-            _lib.call("da_conv3d_wgrad_ex", _p(x1), C1, _p(x2), C2, _p(dy), int(transposed), _p(dw), _p(db), N, Di, Hi,
-                      Wi, Cout, ks, stride, pad, _p(wsw), nbw, st, _p(ctx.amax_x), 1, _p(amax_dy), dy_valid, int(inplace))
-            if inplace:
-                dw = db = None   # already added to weight.grad / bias.grad
+        if want_w and not side_wgrad:
+            dw, db = wgrad(st, dy_valid)
         return dx1, dx2, dw, db, None, None, None, None
 
 

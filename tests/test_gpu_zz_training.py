@@ -155,7 +155,9 @@ def test_overlapped_registration_branch_equals_serial(cuda):
     n_classes, size = 4, (16, 24, 16)
     batch = make_synthetic_pair(size, n_classes, seed=411, device=cuda)
     out = {}
-    for mode in ("serial", "overlap", "overlap+graph"):
+    from deepatlas_b200 import ops
+    for mode in ("serial", "overlap", "overlap+graph", "overlap+wgrad", "overlap+wgrad+graph"):
+        ops.set_wgrad_overlap("wgrad" in mode)   # weight gradients on their own side stream
         torch.manual_seed(230)
         model = JointModel(n_classes=n_classes, overlap_reg=mode != "serial").to(cuda)
         model.weights_init()
@@ -168,7 +170,7 @@ def test_overlapped_registration_branch_equals_serial(cuda):
             model.join_streams()
             return loss.detach()
 
-        if mode == "overlap+graph":
+        if mode.endswith("graph"):
             state = {k: v.clone() for k, v in model.state_dict().items()}
             run = GraphedStep(compute, batch, warmup=2)
             model.load_state_dict(state)     # (the warm-up runs moved the BatchNorm running statistics only)
@@ -177,6 +179,7 @@ def test_overlapped_registration_branch_equals_serial(cuda):
         loss = float(run(*batch))
         torch.cuda.synchronize()
         out[mode] = (loss, bucket.flat.clone())
-    for mode in ("overlap", "overlap+graph"):
+    ops.set_wgrad_overlap(False)
+    for mode in ("overlap", "overlap+graph", "overlap+wgrad", "overlap+wgrad+graph"):
         assert abs(out[mode][0] - out["serial"][0]) <= 1e-6 * abs(out["serial"][0]), mode
         assert rel_err(out[mode][1], out["serial"][1]) < 1e-5, mode
