@@ -976,17 +976,16 @@ inline bool split_tf32() {
 // mantissa bits at the same MMA rate).  Everything around the k3 convolutions stays fp32.
 inline int single_pass() { return g_conv_split == 2 ? 1 : 0; }
 inline bool fwd_umma_ok(const ConvGeom& g) {
-  // one launch covers a block of 16 output channels: below ~50k voxels a launch no longer amortises its fixed cost and
-  // the tiled FFMA kernel (one launch per layer) wins (measured on UNet's 32^3 levels)
   // structural limits of the kernel: 32-bit element offsets (output tensor, eight input channels), fused activation
   // written as max(r, r * slope)
   const int64_t V = (int64_t)g.Do * g.Ho * g.Wo;
   if ((int64_t)g.N * g.Cout * V >= ((int64_t)1 << 32) || 8 * V >= ((int64_t)1 << 31)) return false;
   if (g.act && !(g.slope >= 0.f && g.slope <= 1.f)) return false;
   if (g_force_direct == 3) return g.stride == 1 && g.pad == 1;  // tests: tensor-core path whatever the size heuristics say
-  // (measured, round 2: with at most four 32-channel launches per layer the tensor path also wins on a 20x24x20 level --
-  // 64 -> 64: 0.060 ms against 0.111 ms for the FFMA kernel)
-  const bool big = V >= 65536 || (V >= 8192 && g.C1 + g.C2 <= 128 && g.Cout <= 64);
+  // (measured, round 2, 32 input channels per launch and all output-channel blocks of a layer in one launch: the tensor
+  // path wins from ~8k voxels up whatever the channel counts -- 64 -> 64 @20x24x20: 0.060 ms against 0.111 ms for the FFMA
+  // kernel; 768 -> 256 @32^3 (24 accumulating launches): 2.04 ms against 7.31 ms)
+  const bool big = V >= 8192;
   return umma_enabled() && !force_direct() && g.stride == 1 && g.pad == 1 && g.C1 + g.C2 >= 8 && g.Wo >= 20 && big;
 }
 inline int64_t umma_workspace_bytes(int Cin, int Cout) {
@@ -1440,7 +1439,8 @@ inline bool wgrad_umma_ok(int N, int D, int H, int W, int Cin, int Cout) {
   const char* e = getenv("DA_WGRAD_UMMA");
   if (e && strcmp(e, "0") == 0) return false;
   const int64_t V = (int64_t)N * D * H * W;
-  const bool big = V >= 65536 || (V >= 8192 && Cin <= 128 && Cout <= 64);   // as fwd_umma_ok
+  (void)Cin; (void)Cout;
+  const bool big = V >= 8192;   // as fwd_umma_ok
   return umma_enabled() && !force_direct() && W >= 16 && big;
 }
 

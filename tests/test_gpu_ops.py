@@ -191,6 +191,7 @@ CONV_CASES = [
     (12, 9, 16, 3, 1, (16, 20, 24), False),     # the concatenation boundary falls inside an 8-channel K chunk of the fp16 tensor path
     (35, 30, 20, 3, 1, (12, 12, 24), False),    # 65 input channels: two 32-channel launches + a 16-channel one holding a single channel
     (96, 0, 32, 3, 1, (8, 12, 40), False),      # three full 32-channel launches accumulate through the output
+    (160, 96, 80, 3, 1, (6, 8, 24), False),     # wide layers of the 32-base UNet: eight accumulating launches, five output blocks
 ]
 
 

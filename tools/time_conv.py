@@ -13,6 +13,8 @@ from deepatlas_b200 import _lib  # noqa: E402
 C1, C2, Cout, D, H, W = (int(v) for v in os.environ.get("DA_SHAPE", "16,0,16,160,192,160").split(","))
 NT = int(os.environ.get("DA_NT", "6"))
 dev = torch.device("cuda:0")
+if os.environ.get("DA_IMPL"):   # 0 auto, 1 direct, 2 tiled FFMA, 3 tensor cores forced
+    _lib.call("da_set_conv_impl", int(os.environ["DA_IMPL"]))
 g = torch.Generator(device=dev).manual_seed(230)
 Cin = C1 + C2
 x1 = torch.rand((1, C1, D, H, W), device=dev, generator=g)
