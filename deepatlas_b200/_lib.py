@@ -53,6 +53,8 @@ SIGNATURES = {
     "da_bending_bwd_workspace_bytes": ("iiii", "size"),
     "da_bending_fwd": ("piiiippls", "rc"),
     "da_bending_bwd": ("ppiiiippls", "rc"),
+    "da_bending_fwd_ex": ("piiiiippls", "rc"),
+    "da_bending_bwd_ex": ("ppiiiiippls", "rc"),
     # conv
     "da_umma_debug_read": ("p", "rc"),
     "da_set_conv_impl": ("i", "rc"),

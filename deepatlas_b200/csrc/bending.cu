@@ -29,8 +29,9 @@ __device__ __forceinline__ void residuals(const float* __restrict__ u, const Geo
 }
 
 // partials [gridDim.x][N*3*6] ; index ((n*3+c)*6+term)
+// l1: sums of |r| (the reference's norm != 'L2' path, lib/loss.py:729 without the squares) instead of r^2
 __global__ void __launch_bounds__(BE_THREADS) bending_fwd_kernel(const float* __restrict__ u, int N, Geo g,
-                                                                 double* __restrict__ partials) {
+                                                                 double* __restrict__ partials, int l1) {
   __shared__ double red[BE_THREADS / 32];
   const int64_t interior = (int64_t)(g.D - 2) * (g.H - 2) * (g.W - 2);
   for (int nc = 0; nc < N * 3; ++nc) {
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(BE_THREADS) bending_fwd_kernel(const float* __
       float r[6];
       residuals(uc, g, (int64_t)z * g.sD + (int64_t)y * g.sH + x, r);
 #pragma unroll
-      for (int k = 0; k < 6; ++k) acc[k] += r[k] * r[k];
+      for (int k = 0; k < 6; ++k) acc[k] += l1 ? fabsf(r[k]) : r[k] * r[k];
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -62,9 +63,9 @@ __global__ void bending_finalize_kernel(const double* __restrict__ partials, int
   sums[i] = (float)acc;
 }
 
-// residual fields rf [N*3][6][V] (zero outside the interior)
+// residual fields rf [N*3][6][V] (zero outside the interior); l1: their signs (d|r|/dr, 0 at 0 as torch.abs)
 __global__ void __launch_bounds__(BE_THREADS) bending_resid_kernel(const float* __restrict__ u, int N, Geo g,
-                                                                   float* __restrict__ rf) {
+                                                                   float* __restrict__ rf, int l1) {
   const int64_t total = (int64_t)N * 3 * g.V;
   for (int64_t i = (int64_t)blockIdx.x * BE_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * BE_THREADS) {
     const int64_t nc = i / g.V, v = i - nc * g.V;
@@ -73,14 +74,14 @@ __global__ void __launch_bounds__(BE_THREADS) bending_resid_kernel(const float* 
     if (x >= 1 && x < g.W - 1 && y >= 1 && y < g.H - 1 && z >= 1 && z < g.D - 1) residuals(u + nc * g.V, g, v, r);
     float* o = rf + nc * 6 * g.V + v;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) o[(int64_t)k * g.V] = r[k];
+    for (int k = 0; k < 6; ++k) o[(int64_t)k * g.V] = l1 ? (float)((r[k] > 0.f) - (r[k] < 0.f)) : r[k];
   }
 }
 
 // grad[q] = sum_term 2*gs[term] * sum_k a_k * r_term[q - o_k]; gsums [N*3*6] upstream grads of the sums
 __global__ void __launch_bounds__(BE_THREADS) bending_gather_kernel(const float* __restrict__ rf,
                                                                     const float* __restrict__ gsums, int N, Geo g,
-                                                                    float* __restrict__ grad) {
+                                                                    float* __restrict__ grad, float outer) {
   const int64_t total = (int64_t)N * 3 * g.V;
   for (int64_t i = (int64_t)blockIdx.x * BE_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * BE_THREADS) {
     const int64_t nc = i / g.V, v = i - nc * g.V;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(BE_THREADS) bending_gather_kernel(const float*
     acc += gs[3] * (at(3, -1, -1, 0) + at(3, 1, 1, 0) - at(3, -1, 1, 0) - at(3, 1, -1, 0));
     acc += gs[4] * (at(4, 0, -1, -1) + at(4, 0, 1, 1) - at(4, 0, -1, 1) - at(4, 0, 1, -1));
     acc += gs[5] * (at(5, -1, 0, -1) + at(5, 1, 0, 1) - at(5, -1, 0, 1) - at(5, 1, 0, -1));
-    grad[i] = 2.f * acc;
+    grad[i] = outer * acc;   // 2 for the squares, 1 for the absolute values
   }
 }
 
@@ -115,27 +116,36 @@ DA_API int64_t da_bending_bwd_workspace_bytes(int N, int D, int H, int W) {
 }
 
 // u [N,3,D,H,W]; sums [N,3,6] (per channel, term order ddD,ddH,ddW,dDdH,dHdW,dDdW) = sum over the interior of r^2
-DA_API int da_bending_fwd(const float* u, int N, int D, int H, int W, float* sums, void* workspace,
-                          int64_t workspace_bytes, cudaStream_t stream) {
+// (norm_l1 = 0) or of |r| (norm_l1 = 1: BendingEnergyLoss with norm != 'L2', lib/loss.py:696-730)
+DA_API int da_bending_fwd_ex(const float* u, int N, int D, int H, int W, int norm_l1, float* sums, void* workspace,
+                             int64_t workspace_bytes, cudaStream_t stream) {
   DA_REQUIRE(u && sums && workspace, "da_bending_fwd: null pointer");
   DA_REQUIRE(D >= 3 && H >= 3 && W >= 3, "da_bending_fwd: extent must be >= 3 per axis");
   if (workspace_bytes < da_bending_fwd_workspace_bytes(N)) { da_set_error("da_bending_fwd: workspace too small"); return DA_ERR_WORKSPACE; }
   Geo g = make_geo(D, H, W);
-  bending_fwd_kernel<<<BE_BLOCKS, BE_THREADS, 0, stream>>>(u, N, g, (double*)workspace);
+  bending_fwd_kernel<<<BE_BLOCKS, BE_THREADS, 0, stream>>>(u, N, g, (double*)workspace, norm_l1 ? 1 : 0);
   bending_finalize_kernel<<<(N * 18 + 63) / 64, 64, 0, stream>>>((const double*)workspace, BE_BLOCKS, N * 18, sums);
   return da_check_launch("da_bending_fwd", 2);
 }
+DA_API int da_bending_fwd(const float* u, int N, int D, int H, int W, float* sums, void* workspace,
+                          int64_t workspace_bytes, cudaStream_t stream) {
+  return da_bending_fwd_ex(u, N, D, H, W, 0, sums, workspace, workspace_bytes, stream);
+}
 
 // grad_sums [N,3,6] upstream; grad_u [N,3,D,H,W]
-DA_API int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, int H, int W, float* grad_u,
-                          void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+DA_API int da_bending_bwd_ex(const float* u, const float* grad_sums, int N, int D, int H, int W, int norm_l1, float* grad_u,
+                             void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
   DA_REQUIRE(u && grad_sums && grad_u && workspace, "da_bending_bwd: null pointer");
   if (workspace_bytes < da_bending_bwd_workspace_bytes(N, D, H, W)) { da_set_error("da_bending_bwd: workspace too small"); return DA_ERR_WORKSPACE; }
   Geo g = make_geo(D, H, W);
   const int64_t total = (int64_t)N * 3 * g.V;
   int64_t b = da_cdiv(total, BE_THREADS);
   const int grid = (int)(b > (int64_t)DA_NUM_SMS * 16 ? (int64_t)DA_NUM_SMS * 16 : b);
-  bending_resid_kernel<<<grid, BE_THREADS, 0, stream>>>(u, N, g, (float*)workspace);
-  bending_gather_kernel<<<grid, BE_THREADS, 0, stream>>>((const float*)workspace, grad_sums, N, g, grad_u);
+  bending_resid_kernel<<<grid, BE_THREADS, 0, stream>>>(u, N, g, (float*)workspace, norm_l1 ? 1 : 0);
+  bending_gather_kernel<<<grid, BE_THREADS, 0, stream>>>((const float*)workspace, grad_sums, N, g, grad_u, norm_l1 ? 1.f : 2.f);
   return da_check_launch("da_bending_bwd", 2);
+}
+DA_API int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, int H, int W, float* grad_u,
+                          void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+  return da_bending_bwd_ex(u, grad_sums, N, D, H, W, 0, grad_u, workspace, workspace_bytes, stream);
 }

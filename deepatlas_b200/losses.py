@@ -157,12 +157,11 @@ class VoxelMorphLNCC(nn.Module):
 
 
 class BendingEnergyLoss(nn.Module):
-    """Bending energy of a 3-D displacement field (L2 form)."""
+    """Bending energy of a 3-D displacement field: norm 'L2' (squared second differences with the reference's per-channel
+    scale factors) or anything else (lib/loss.py:721 falls through: plain means of the absolute second differences)."""
 
     def __init__(self, norm="L2", spacing=(1, 1, 1), normalize=True):
         super().__init__()
-        if norm != "L2":
-            raise NotImplementedError("deepatlas_b200: BendingEnergyLoss is built for norm='L2'")
         self.norm = norm
         self.spacing = torch.tensor(spacing).float()
         self.normalize = normalize
@@ -195,6 +194,12 @@ class BendingEnergyLoss(nn.Module):
         return coef.float()
 
     def forward(self, input):
+        if self.norm != "L2":
+            # lib/loss.py:696-718,729: |second differences|, mean over (B, 3, interior), weights (1,1,1,2,2,2) / 9
+            B, _, D, H, W = input.shape
+            sums = ops.bending_sums(input, l1=True)                  # (B, 3, 6)
+            per_term = sums.sum(dim=(0, 1)) / float(3 * B * (D - 2) * (H - 2) * (W - 2))
+            return (per_term[:3].sum() + 2.0 * per_term[3:].sum()) / 9.0
         sums = ops.bending_sums(input)                               # (B, 3, 6)
         return (sums * self._coef(input.shape, input.device)[None]).sum()
 
@@ -333,8 +338,14 @@ class FocalLoss(nn.Module):
         self.gamma, self.class_num, self.size_average, self.soft_max = gamma, class_num, size_average, soft_max
 
     def forward(self, inputs, targets):
-        if inputs.dim() != 5:
-            raise NotImplementedError("deepatlas_b200: FocalLoss is built for (B,C,X,Y,Z) inputs")
+        if inputs.dim() == 2:
+            # (observations, classes) with one label per row -- the only other shape the reference accepts
+            # (lib/loss.py:167 permutes five axes or nothing): the rows become the voxels of one volume
+            n, c = inputs.shape
+            inputs = inputs.t().reshape(1, c, 1, 1, n)
+            targets = targets.reshape(1, 1, 1, n)
+        elif inputs.dim() != 5:
+            raise NotImplementedError("deepatlas_b200: FocalLoss takes (B,C,X,Y,Z) or (N,C) inputs, as the reference does")
         if inputs.is_cuda and not self.alpha.is_cuda:
             self.alpha = self.alpha.cuda()
         s = ops.xent_sums(inputs, targets, 1, class_weight=self.alpha.float().reshape(-1), gamma=float(self.gamma),

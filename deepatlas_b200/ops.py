@@ -476,10 +476,10 @@ def lncc(I, J, win=9, eps=1e-6):
 # bending energy sums  (lib/loss.py:702-718)
 # ------------------------------------------------------------------------------------------------------
 class BendingSumsFunction(torch.autograd.Function):
-    """sums[N,3,6]: per channel the interior sum of squared (ddD, ddH, ddW, dDdH, dHdW, dDdW)."""
+    """sums[N,3,6]: per channel the interior sum of squared (``l1``: absolute) (ddD, ddH, ddW, dDdH, dHdW, dDdW)."""
 
     @staticmethod
-    def forward(ctx, u):
+    def forward(ctx, u, l1: bool):
         u = _f32(u, "input")
         if u.dim() != 5 or u.shape[1] != 3:
             raise ValueError(f"bending: input must be (N,3,D,H,W), got {tuple(u.shape)}")
@@ -487,8 +487,9 @@ class BendingSumsFunction(torch.autograd.Function):
         sums = torch.empty((N, 3, 6), dtype=torch.float32, device=u.device)
         nb = _lib.size("da_bending_fwd_workspace_bytes", N)
         ws = _ws(nb, u.device)
-        _lib.call("da_bending_fwd", _p(u), N, D, H, W, _p(sums), _p(ws), nb, _stream())
+        _lib.call("da_bending_fwd_ex", _p(u), N, D, H, W, int(l1), _p(sums), _p(ws), nb, _stream())
         ctx.save_for_backward(u)
+        ctx.l1 = bool(l1)
         return sums
 
     @staticmethod
@@ -499,12 +500,12 @@ class BendingSumsFunction(torch.autograd.Function):
         nb = _lib.size("da_bending_bwd_workspace_bytes", N, D, H, W)
         ws = _ws(nb, u.device)
         gu = torch.empty_like(u)
-        _lib.call("da_bending_bwd", _p(u), _p(g), N, D, H, W, _p(gu), _p(ws), nb, _stream())
-        return gu
+        _lib.call("da_bending_bwd_ex", _p(u), _p(g), N, D, H, W, int(ctx.l1), _p(gu), _p(ws), nb, _stream())
+        return gu, None
 
 
-def bending_sums(u):
-    return BendingSumsFunction.apply(u)
+def bending_sums(u, l1=False):
+    return BendingSumsFunction.apply(u, l1)
 
 
 # ------------------------------------------------------------------------------------------------------

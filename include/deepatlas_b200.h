@@ -109,6 +109,11 @@ int da_bending_fwd(const float* u, int N, int D, int H, int W, float* sums, void
                    int64_t workspace_bytes, da_stream_t stream);
 int da_bending_bwd(const float* u, const float* grad_sums, int N, int D, int H, int W, float* grad_u,
                    void* workspace, int64_t workspace_bytes, da_stream_t stream);
+/* norm_l1 = 1: sums of |r| instead of r^2 -- BendingEnergyLoss with norm != 'L2' (lib/loss.py:696-730, no scale factors) */
+int da_bending_fwd_ex(const float* u, int N, int D, int H, int W, int norm_l1, float* sums, void* workspace,
+                      int64_t workspace_bytes, da_stream_t stream);
+int da_bending_bwd_ex(const float* u, const float* grad_sums, int N, int D, int H, int W, int norm_l1, float* grad_u,
+                      void* workspace, int64_t workspace_bytes, da_stream_t stream);
 
 /* ---- 3D convolution --------------------------------------------------------------------------------------
  * nn.Conv3d k3 (stride 1/2, pad 1) and k1: lib/network_factory/unets.py:30,36,98,115,120,250,

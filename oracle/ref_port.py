@@ -239,9 +239,21 @@ def lncc(I, J, filter_size=9, eps=1e-6):
     return 1 - ((cross ** 2) / (Iv * Jv + eps)).mean()
 
 
-def bending_energy(u, spacing=(1.0, 1.0, 1.0), normalize=True):
-    """BendingEnergyLoss.forward, norm='L2' (lib/loss.py:687-730).  Note the per-CHANNEL scale:
-    ``spatial_dims`` (D,H,W)/min multiplies the (B,3) per-channel means (reference quirk, kept)."""
+def bending_energy(u, spacing=(1.0, 1.0, 1.0), normalize=True, norm="L2"):
+    """BendingEnergyLoss.forward (lib/loss.py:687-730).  norm='L2': note the per-CHANNEL scale: ``spatial_dims``
+    (D,H,W)/min multiplies the (B,3) per-channel means (reference quirk, kept).  Any other norm: the `if` at :721 is
+    skipped and :729 takes plain means of the absolute second differences."""
+    if norm != "L2":
+        B, C = u.shape[:2]
+        c = u[:, :, 1:-1, 1:-1, 1:-1]
+        a = lambda t: t.abs().reshape(B, C, -1)  # noqa: E731
+        ddx = a(u[:, :, 2:, 1:-1, 1:-1] + u[:, :, :-2, 1:-1, 1:-1] - 2 * c)
+        ddy = a(u[:, :, 1:-1, 2:, 1:-1] + u[:, :, 1:-1, :-2, 1:-1] - 2 * c)
+        ddz = a(u[:, :, 1:-1, 1:-1, 2:] + u[:, :, 1:-1, 1:-1, :-2] - 2 * c)
+        dxdy = a(u[:, :, 2:, 2:, 1:-1] + u[:, :, :-2, :-2, 1:-1] - u[:, :, 2:, :-2, 1:-1] - u[:, :, :-2, 2:, 1:-1])
+        dydz = a(u[:, :, 1:-1, 2:, 2:] + u[:, :, 1:-1, :-2, :-2] - u[:, :, 1:-1, 2:, :-2] - u[:, :, 1:-1, :-2, 2:])
+        dxdz = a(u[:, :, 2:, 1:-1, 2:] + u[:, :, :-2, 1:-1, :-2] - u[:, :, 2:, 1:-1, :-2] - u[:, :, :-2, 1:-1, 2:])
+        return (ddx.mean() + ddy.mean() + ddz.mean() + 2 * dxdy.mean() + 2 * dydz.mean() + 2 * dxdz.mean()) / 9.0
     sp = torch.tensor(spacing, dtype=torch.float32, device=u.device)
     if normalize:
         sp = sp / sp.min()
@@ -357,7 +369,8 @@ def gradient_loss(u, norm="L2", spacing=(1.0, 1.0, 1.0), normalize=True):
 def focal_loss(inputs, targets, alpha=None, gamma=2, size_average=True, soft_max=True):
     """FocalLoss.forward (lib/loss.py:149-186).  ``F.nll_loss(P, t)`` returns -P[t], hence (1 + P[t])**gamma."""
     C = inputs.shape[1]
-    x = inputs.permute(0, 2, 3, 4, 1).contiguous().view(-1, C)
+    # lib/loss.py:167-169: five axes are permuted to (voxels, classes); (observations, classes) inputs pass as they are
+    x = inputs.permute(0, 2, 3, 4, 1).contiguous().view(-1, C) if (inputs.dim() > 2 and targets.dim() > 1) else inputs
     t = targets.reshape(-1).long()
     P = F.softmax(x, dim=1) if soft_max else x
     a = torch.ones(C, 1, dtype=inputs.dtype) if alpha is None else alpha.to(inputs.dtype)

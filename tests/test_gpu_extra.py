@@ -448,3 +448,21 @@ def test_vm_blocks_residual_and_deconv_vs_reference_semantics(cuda, kind):
     assert rel_err(y, yc) < TOL
     for name, a, r in (("dx", xg.grad, xc.grad), ("dw", w.grad, wc.grad), ("db", b.grad, bc.grad)):
         assert rel_err(a, r) < 2 * TOL, (kind, name)
+
+
+def test_focal_loss_2d_inputs_vs_oracle(cuda):
+    """FocalLoss on (observations, classes) inputs -- the reference's other accepted shape (lib/loss.py:167) -- against the
+    oracle: value and gradient."""
+    import deepatlas_b200 as da
+    from oracle import ref_port as P
+    g = _g()
+    n, C = 301, 5
+    x = torch.randn((n, C), generator=g)
+    t = torch.randint(0, C, (n,), generator=g)
+    xg = x.to(cuda).requires_grad_(True)
+    loss = da.get_loss_function("focal")(C, gamma=2)(xg, t.to(cuda))
+    loss.backward()
+    xc = x.clone().requires_grad_(True)
+    ref = P.focal_loss(xc, t, gamma=2)
+    ref.backward()
+    assert rel_err(loss, ref) < TOL and rel_err(xg.grad, xc.grad) < TOL

@@ -159,6 +159,10 @@ def test_bending(cuda, size, spacing):
     crit = da.get_loss_function("bendingEnergy")(spacing=spacing)
     res = _run_both(lambda a: crit(a), lambda a: P.bending_energy(a, spacing), [u], cuda)
     _check(*res, what="bending")
+    # the reference's non-L2 path (lib/loss.py:721 falls through): means of absolute second differences
+    crit1 = da.get_loss_function("bendingEnergy")(norm="L1", spacing=spacing)
+    res = _run_both(lambda a: crit1(a), lambda a: P.bending_energy(a, spacing, norm="L1"), [u], cuda)
+    _check(*res, what="bending L1")
     # affine field has zero bending energy
     idt = P.identity_transform(size)[None].to(cuda)
     assert float(crit(idt * 0.3 + 0.1)) < 1e-10

@@ -113,6 +113,7 @@ def test_port_lncc_bending(ref):
     u = torch.randn((2, 3, 8, 9, 10), generator=g) * 0.1
     for sp in ((1, 1, 1), (1.0, 1.5, 2.0)):
         assert torch.equal(P.bending_energy(u, sp), ref.get_loss_function("bendingEnergy")(spacing=sp)(u))
+        assert torch.equal(P.bending_energy(u, sp, norm="L1"), ref.get_loss_function("bendingEnergy")(norm="L1", spacing=sp)(u))
     # analytic identities of SURVEY.md section 4
     assert float(P.lncc(I, I)) < 1e-5
     idt = P.identity_transform((8, 9, 10))[None]
@@ -162,6 +163,8 @@ def test_port_remaining_losses(ref):
             assert torch.equal(P.focal_loss(xin, t, None, 2, size_average, soft_max), crit(xin, t))
     alpha = (torch.rand(C, 1, generator=g) + 0.5)
     assert torch.equal(P.focal_loss(x, t, alpha, 1.5), ref.get_loss_function("focal")(C, alpha=alpha, gamma=1.5)(x, t))
+    x2, t2 = torch.randn((37, C), generator=_g(5)), torch.randint(0, C, (37,), generator=_g(6))   # (observations, classes)
+    assert torch.equal(P.focal_loss(x2, t2), ref.get_loss_function("focal")(C)(x2, t2))
     assert torch.equal(P.soft_cross_entropy(x, soft, True), ref.get_loss_function("soft_cross_entropy")(softmax=True)(x, soft))
     p = torch.softmax(x, 1)
     p[0, 0, 0, 0, :3] = 0.0     # exercises the 1e-8 clamp
