@@ -326,6 +326,8 @@ def run_ours(args, wl):
 
     # the whole step as one CUDA graph (deepatlas_b200/graph.py): eager, the host side of a step (about a thousand launches
     # through Python) is as long as its GPU side; --no-graph times the eager loop
+    overlap_on = wl["kind"] == "joint" and not (args.no_overlap or os.environ.get("DA_BENCH_NO_OVERLAP") == "1")
+    overlap_note = "; registration branch and convolution weight gradients on side streams (parallel graph paths)" if overlap_on else ""
     gstep, graph_note = None, "eager"
     run = step
     if use_graph:
@@ -333,10 +335,10 @@ def run_ours(args, wl):
         try:
             if world == 1:
                 gstep = GraphedStep(lambda *b: step(b), dev_batch, warmup=args.warmup)
-                graph_note = "one CUDA graph per step (zero grads, forward, backward, Adam)"
+                graph_note = "one CUDA graph per step (zero grads, forward, backward, Adam)" + overlap_note
             else:   # the NCCL all-reduce and the optimizer stay outside the graph (torch's NCCL watchdog, see graph.py)
                 gstep = GraphedStep(lambda *b: compute(b), dev_batch, warmup=args.warmup, eager_tail=update)
-                graph_note = "one CUDA graph per step (zero grads, forward, backward) + eager NCCL all-reduce and Adam"
+                graph_note = "one CUDA graph per step (zero grads, forward, backward) + eager NCCL all-reduce and Adam" + overlap_note
             run = lambda batch: gstep(*batch)   # noqa: E731
         except Exception as e:   # noqa: BLE001  (keep the bench alive: the eager step is the same arithmetic)
             torch.cuda.synchronize()
