@@ -284,7 +284,8 @@ def run_ours(args, wl):
 
     torch.manual_seed(230)
     if wl["kind"] == "joint":
-        model = JointModel(n_classes=CLASSES, overlap_reg=not (args.no_overlap or os.environ.get("DA_BENCH_NO_OVERLAP") == "1")).to(dev)
+        ov = not (args.no_overlap or os.environ.get("DA_BENCH_NO_OVERLAP") == "1")
+        model = JointModel(n_classes=CLASSES, overlap_reg=ov, overlap_seg=ov and os.environ.get("DA_BENCH_NO_SEG_OVERLAP") != "1").to(dev)
     elif wl["kind"] == "reg":
         model = RegOnlyModel().to(dev)
     else:
@@ -292,6 +293,8 @@ def run_ours(args, wl):
     model.weights_init()
     broadcast_parameters(model)
     bucket = FlatGradBucket(model.trainable_parameters())
+    if getattr(model, "overlap_seg", False):
+        bucket.enable_alt()
     use_graph = not args.no_graph
     opt = torch.optim.Adam(bucket.params, lr=1e-3, fused=True, capturable=use_graph)
 

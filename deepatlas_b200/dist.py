@@ -63,6 +63,25 @@ class FlatGradBucket:
             p.grad = v
             off += n
         self.rebound = 0   # gradients found outside the bucket so far (diagnostic)
+        self.flat_alt = None
+
+    def enable_alt(self):
+        """A second flat buffer with the same layout, reachable as ``p.grad._da_alt``: ops created under
+        ``ops.grad_slot(1)`` add their parameter gradients there (a second pass of the same network on another stream);
+        ``fold_alt()`` -- called by ``allreduce()`` -- adds it into the primary buffer."""
+        if self.flat_alt is None:
+            self.flat_alt = torch.zeros_like(self.flat)
+            off = 0
+            for p, v in zip(self.params, self._views):
+                n = p.numel()
+                v._da_alt = self.flat_alt[off:off + n].view_as(p)
+                off += n
+        return self
+
+    def fold_alt(self):
+        if self.flat_alt is not None:
+            self.flat.add_(self.flat_alt)
+            self.flat_alt.zero_()
 
     @property
     def nbytes(self) -> int:
@@ -70,6 +89,8 @@ class FlatGradBucket:
 
     def zero(self):
         self.flat.zero_()
+        if self.flat_alt is not None:
+            self.flat_alt.zero_()
         self.rebind(copy=False)
 
     zero_grad = zero
@@ -94,7 +115,12 @@ class FlatGradBucket:
         return fixed
 
     def allreduce(self, world: int | None = None):
-        """One collective per step.  No collective for a single process (the views are still re-checked)."""
+        """One collective per step.  No collective for a single process (the views are still re-checked).  Weight
+        gradients that ``ops.set_wgrad_overlap`` put on the side stream are joined first."""
+        if self.flat.is_cuda:
+            from . import ops
+            ops.join_wgrad_stream()
+        self.fold_alt()
         if not dist.is_available() or not dist.is_initialized():
             self.rebind(copy=True)
             return

@@ -27,16 +27,24 @@ DEFAULT_LAMBDAS = dict(sim=1.0, reg=1000.0, ana=1.0, sup=1.0)
 
 
 class JointModel(nn.Module):
-    def __init__(self, n_classes=32, in_channel=1, seg_name="UNet_light", lambdas=None, overlap_reg=False):
+    def __init__(self, n_classes=32, in_channel=1, seg_name="UNet_light", lambdas=None, overlap_reg=False, overlap_seg=False):
         """``overlap_reg``: run the registration network on a side stream next to the two segmentation passes (they
         share no state: the registration net has no BatchNorm, parameters are read-only in the forward, its gradients
         land in its own bucket slots).  Small low-resolution kernels of one branch then fill SMs the other leaves idle;
         inside a captured CUDA graph the two branches become parallel paths.  The backward of each branch runs on the
         stream of its forward (autograd's rule); call ``join_streams()`` after ``backward()`` and before anything on the
-        current stream reads the registration net's gradients (an optimizer step, an all-reduce)."""
+        current stream reads the registration net's gradients (an optimizer step, an all-reduce).
+
+        ``overlap_seg``: additionally run the TARGET image's segmentation pass (and its supervised Dice) on a second side
+        stream next to the moving image's.  The two passes share one network, so the side pass (a) defers its BatchNorm
+        running-statistics updates (``networks.deferred_bn_updates``: applied after the join, i.e. in the reference's
+        order: moving, then target) and (b) adds its parameter gradients into the gradient bucket's alternate slots
+        (``ops.grad_slot(1)``, ``FlatGradBucket.enable_alt()``; folded in by ``allreduce()``).  Needs the fused head path."""
         super().__init__()
         self.overlap_reg = bool(overlap_reg)
+        self.overlap_seg = bool(overlap_seg)
         self._side = None
+        self._side2 = None
         self.n_classes = n_classes
         self.seg = get_network(seg_name)(in_channel, n_classes, bias=True, BN=True)
         self.reg = get_network("voxel_morph_cvpr")()
@@ -63,6 +71,8 @@ class JointModel(nn.Module):
         weight-gradient stream of ``ops.set_wgrad_overlap``."""
         if self.overlap_reg and self._side is not None:
             torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+        if self.overlap_seg and self._side2 is not None:
+            torch.cuda.current_stream(self._side2.device).wait_stream(self._side2)
         ops.join_wgrad_stream()
 
     def _run_reg(self, I_m, I_t):
@@ -82,7 +92,7 @@ class JointModel(nn.Module):
         return out
 
     def _fork_here(self, ref):
-        if self.overlap_reg and ref.is_cuda:
+        if (self.overlap_reg or self.overlap_seg) and ref.is_cuda:
             self._fork = torch.cuda.Event()
             self._fork.record(torch.cuda.current_stream(ref.device))
 
@@ -103,11 +113,28 @@ class JointModel(nn.Module):
             # 160x192x160) and their gradient never reach HBM; for the moving image the same pass writes the
             # probabilities that the anatomy term warps, and the backward takes both of their gradients
             self._fork_here(I_m)
-            F_m = self.seg.forward_features(I_m)
-            F_t = self.seg.forward_features(I_t)
-            disp, I_w, phi, sim, reg = self._run_reg(I_m, I_t)     # (side stream with overlap_reg)
-            sup_m, prob_m = self.sup_dice.forward_head(F_m, self.seg.head, S_m, want_probs=True)
-            sup_t, _ = self.sup_dice.forward_head(F_t, self.seg.head, S_t)
+            if self.overlap_seg and I_m.is_cuda:
+                # the target image's pass on its own stream: BatchNorm buffer updates deferred, gradients into slot 1
+                from .networks import deferred_bn_updates
+                main = torch.cuda.current_stream(I_m.device)
+                if self._side2 is None or self._side2.device != I_m.device:
+                    self._side2 = torch.cuda.Stream(device=I_m.device)
+                self._side2.wait_event(self._fork)
+                with torch.cuda.stream(self._side2), deferred_bn_updates() as pending, ops.grad_slot(1):
+                    F_t = self.seg.forward_features(I_t)
+                    sup_t, _ = self.sup_dice.forward_head(F_t, self.seg.head, S_t)
+                F_m = self.seg.forward_features(I_m)
+                disp, I_w, phi, sim, reg = self._run_reg(I_m, I_t)
+                sup_m, prob_m = self.sup_dice.forward_head(F_m, self.seg.head, S_m, want_probs=True)
+                main.wait_stream(self._side2)
+                sup_t.record_stream(main)
+                pending.apply()      # after the moving pass's own updates (stream order) and the side pass's statistics (join)
+            else:
+                F_m = self.seg.forward_features(I_m)
+                F_t = self.seg.forward_features(I_t)
+                disp, I_w, phi, sim, reg = self._run_reg(I_m, I_t)     # (side stream with overlap_reg)
+                sup_m, prob_m = self.sup_dice.forward_head(F_m, self.seg.head, S_m, want_probs=True)
+                sup_t, _ = self.sup_dice.forward_head(F_t, self.seg.head, S_t)
             self._join_reg((disp, I_w, phi, sim, reg))
         else:
             self._fork_here(I_m)

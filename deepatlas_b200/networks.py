@@ -24,8 +24,65 @@ from . import ops
 _ACT = {"ReLU": (nn.ReLU, 0.0), "LeakyReLU": (nn.LeakyReLU, 0.01)}
 
 
+_BN_DEFER = None   # list of pending running-statistics updates while a deferred_bn_updates context is open
+
+
+class deferred_bn_updates:
+    """Inside this context the BatchNorm layers of this module normalise with batch statistics as usual but leave
+    ``running_mean`` / ``running_var`` / ``num_batches_tracked`` alone; ``apply()`` performs those updates afterwards, in
+    call order, with a handful of multi-tensor launches.  For a pass that runs on a side stream next to another pass of
+    the SAME network (the joint step's two segmentation passes): the buffers then see the two updates in sequence, as
+    in the reference's two sequential calls, instead of racing."""
+
+    def __init__(self):
+        self.items = []
+
+    def __enter__(self):
+        global _BN_DEFER
+        if _BN_DEFER is not None:
+            raise RuntimeError("deferred_bn_updates does not nest")
+        _BN_DEFER = self.items
+        return self
+
+    def __exit__(self, *exc):
+        global _BN_DEFER
+        _BN_DEFER = None
+
+    def apply(self):
+        items, self.items = self.items, []
+        if not items:
+            return
+        mom = items[0][0].momentum if items[0][0].momentum is not None else 0.1
+        eps = items[0][0].eps
+        uniform = all((bn.momentum if bn.momentum is not None else 0.1) == mom and bn.eps == eps for bn, *_ in items)
+        with torch.no_grad():
+            if uniform:
+                var = torch._foreach_pow([i for _, _, i, _ in items], -2.0)          # var + eps
+                torch._foreach_sub_(var, eps)
+                torch._foreach_mul_(var, [float(M) / float(M - 1) if M > 1 else 1.0 for *_, M in items])   # unbiased
+                torch._foreach_lerp_([bn.running_mean for bn, *_ in items], [m for _, m, _, _ in items], mom)
+                torch._foreach_lerp_([bn.running_var for bn, *_ in items], var, mom)
+                nbt = [bn.num_batches_tracked for bn, *_ in items if bn.num_batches_tracked is not None]
+                if nbt:
+                    torch._foreach_add_(nbt, 1)
+            else:
+                for bn, mean, invstd, M in items:
+                    m_ = bn.momentum if bn.momentum is not None else 0.1
+                    var = (invstd.pow(-2) - bn.eps) * (float(M) / float(M - 1) if M > 1 else 1.0)
+                    bn.running_mean.lerp_(mean, m_)
+                    bn.running_var.lerp_(var, m_)
+                    if bn.num_batches_tracked is not None:
+                        bn.num_batches_tracked.add_(1)
+
+
 def _bn_apply(bn: nn.BatchNorm3d, y, slope):
     training = bn.training or bn.running_mean is None
+    if _BN_DEFER is not None and bn.training and bn.running_mean is not None:
+        out, mean, invstd = ops.bn_act(y, bn.weight, bn.bias, None, None, training=True,
+                                       momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps, slope=slope,
+                                       return_stats=True)
+        _BN_DEFER.append((bn, mean, invstd, y.numel() // y.shape[1]))
+        return out
     if bn.training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return ops.bn_act(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, training=training,

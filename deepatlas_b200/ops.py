@@ -59,13 +59,39 @@ def _set_amax(t, a):
 # the producing backward's own fixed-order reduce kernel (``accumulate = 1``), and autograd is handed ``None`` -- instead of
 # a fresh tensor that autograd then adds to ``p.grad`` with one more kernel per parameter and use (187 launches per joint
 # step).  Opt-in per parameter, because ``torch.autograd.grad`` and parameter hooks expect the tensors.
-def _grad_dst(p, wanted: bool):
-    """``p.grad`` if the gradient of parameter ``p`` is to be accumulated in place, else None."""
+# A second set of gradient slots: two passes of ONE network that run on different streams (the joint step's two
+# segmentation passes) must not add into the same memory concurrently.  Ops created under ``grad_slot(1)`` remember the
+# slot and their backward adds into the bucket's alternate views (``FlatGradBucket.enable_alt``), which the bucket folds
+# into the primary ones before the all-reduce.
+_GRAD_SLOT = 0
+
+
+class grad_slot:
+    def __init__(self, slot: int):
+        self.slot, self.prev = int(slot), 0
+
+    def __enter__(self):
+        global _GRAD_SLOT
+        self.prev, _GRAD_SLOT = _GRAD_SLOT, self.slot
+        return self
+
+    def __exit__(self, *exc):
+        global _GRAD_SLOT
+        _GRAD_SLOT = self.prev
+
+
+def _grad_dst(p, wanted: bool, slot: int = 0):
+    """``p.grad`` (or its alternate view for ``slot`` 1) if the gradient of parameter ``p`` is to be accumulated in
+    place, else None."""
     if not wanted or p is None or not p.is_leaf:
         return None
     g = p.grad
     if g is None or not getattr(g, "_da_inplace", False):
         return None
+    if slot:
+        g = getattr(g, "_da_alt", None)
+        if g is None:
+            return None
     if g.dtype != torch.float32 or g.device != p.device or not g.is_contiguous() or g.shape != p.shape:
         return None
     return g
@@ -315,6 +341,7 @@ class HeadSoftmaxDiceFunction(torch.autograd.Function):
                   nb, _stream())
         ctx.save_for_backward(feat, weight, bias, target)
         ctx.kind = kind
+        ctx.grad_slot = _GRAD_SLOT
         if probs is None:
             ctx.mark_non_differentiable()
             return sums, None
@@ -330,8 +357,8 @@ class HeadSoftmaxDiceFunction(torch.autograd.Function):
         gS, gI = g[:, 0].contiguous(), g[:, 2].contiguous()
         gp = _f32(gp, "grad_probs") if gp is not None else None
         gfeat = torch.empty_like(feat)
-        gw_dst = _grad_dst(weight, ctx.needs_input_grad[1])
-        gb_dst = _grad_dst(bias, ctx.needs_input_grad[2]) if bias is not None else None
+        gw_dst = _grad_dst(weight, ctx.needs_input_grad[1], ctx.grad_slot)
+        gb_dst = _grad_dst(bias, ctx.needs_input_grad[2], ctx.grad_slot) if bias is not None else None
         inplace = gw_dst is not None and (bias is None or gb_dst is not None)
         gw = gw_dst if inplace else torch.empty_like(weight)
         gb = (gb_dst if inplace else torch.empty_like(bias)) if bias is not None else None
@@ -550,6 +577,7 @@ class Conv3dFunction(torch.autograd.Function):
         ctx.amax_x = amax_x
         ctx.save_for_backward(x1, x2, weight, out if slope is not None else None)
         ctx.bias_ref = bias   # (only its .grad is looked at in backward)
+        ctx.grad_slot = _GRAD_SLOT
         ctx.cfg = (bool(transposed), ks, stride, pad, slope, bias is not None, Cout)
         return out
 
@@ -578,8 +606,8 @@ class Conv3dFunction(torch.autograd.Function):
         inplace = False
         if want_w:
             bias = ctx.bias_ref
-            gw_dst = _grad_dst(weight, ctx.needs_input_grad[2])
-            gb_dst = _grad_dst(bias, has_bias and ctx.needs_input_grad[3]) if has_bias else None
+            gw_dst = _grad_dst(weight, ctx.needs_input_grad[2], ctx.grad_slot)
+            gb_dst = _grad_dst(bias, has_bias and ctx.needs_input_grad[3], ctx.grad_slot) if has_bias else None
             inplace = gw_dst is not None and (not has_bias or gb_dst is not None)
 
         def wgrad(stream, valid):
@@ -658,20 +686,23 @@ class BnActFunction(torch.autograd.Function):
                   0 if slope is None else 1, 0.0 if slope is None else float(slope), _p(y), st)
         ctx.save_for_backward(x, mean, invstd, gamma, beta)
         ctx.cfg = (bool(training), slope)
-        if amax_y is not None:
-            ctx.mark_non_differentiable(amax_y)
-        return y, amax_y   # (the bound is attached to y by bn_act(): attributes set here do not reach the tensor apply() returns)
+        ctx.grad_slot = _GRAD_SLOT
+        # the bound is attached to y by bn_act() (attributes set here do not reach the tensor apply() returns); the batch
+        # statistics go out too, for callers that apply the running-statistics update themselves (deferred_bn_updates)
+        stats_out = (mean, invstd) if training else (None, None)
+        ctx.mark_non_differentiable(*[t for t in (amax_y,) + stats_out if t is not None])
+        return (y, amax_y) + stats_out
 
     @staticmethod
-    def backward(ctx, dy, _g_amax=None):
+    def backward(ctx, dy, _g_amax=None, _g_mean=None, _g_invstd=None):
         x, mean, invstd, gamma, beta = ctx.saved_tensors
         training, slope = ctx.cfg
         dy = _f32(dy, "grad_out")
         N, C = x.shape[:2]
         V = x[0, 0].numel()
         dx = torch.empty_like(x)
-        g_dst = _grad_dst(gamma, gamma is not None and ctx.needs_input_grad[1])
-        b_dst = _grad_dst(beta, beta is not None and ctx.needs_input_grad[2])
+        g_dst = _grad_dst(gamma, gamma is not None and ctx.needs_input_grad[1], ctx.grad_slot)
+        b_dst = _grad_dst(beta, beta is not None and ctx.needs_input_grad[2], ctx.grad_slot)
         inplace = g_dst is not None and b_dst is not None
         dg = g_dst if inplace else torch.empty_like(mean)
         db = b_dst if inplace else torch.empty_like(mean)
@@ -687,9 +718,12 @@ class BnActFunction(torch.autograd.Function):
         return dx, (dg if gamma is not None else None), (db if beta is not None else None), None, None, None, None, None, None
 
 
-def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, slope=None):
-    y, amax = BnActFunction.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, slope)
-    return _set_amax(y, amax)
+def bn_act(x, gamma, beta, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, slope=None, return_stats=False):
+    """``return_stats``: also return the batch mean and 1/sqrt(var + eps) (training mode), for a caller that passed
+    ``running_mean = running_var = None`` and applies the running-statistics update itself."""
+    y, amax, mean, invstd = BnActFunction.apply(x, gamma, beta, running_mean, running_var, training, momentum, eps, slope)
+    y = _set_amax(y, amax)
+    return (y, mean, invstd) if return_stats else y
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -759,6 +793,7 @@ class DeconvK2S2Function(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.bias_ref = bias
+        ctx.grad_slot = _GRAD_SLOT
         return out
 
     @staticmethod
@@ -773,8 +808,8 @@ class DeconvK2S2Function(torch.autograd.Function):
             dx = torch.empty_like(x)
             _lib.call("da_deconv_k2s2_dgrad", _p(dy), _p(weight), _p(dx), N, Cin, Cout, D, H, W, st)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gw_dst = _grad_dst(weight, ctx.needs_input_grad[1])
-            gb_dst = _grad_dst(ctx.bias_ref, ctx.has_bias and ctx.needs_input_grad[2]) if ctx.has_bias else None
+            gw_dst = _grad_dst(weight, ctx.needs_input_grad[1], ctx.grad_slot)
+            gb_dst = _grad_dst(ctx.bias_ref, ctx.has_bias and ctx.needs_input_grad[2], ctx.grad_slot) if ctx.has_bias else None
             inplace = gw_dst is not None and (not ctx.has_bias or gb_dst is not None)
             dw = gw_dst if inplace else torch.empty_like(weight)
             db = (gb_dst if inplace else torch.empty((Cout,), dtype=torch.float32, device=dy.device)) if ctx.has_bias else None

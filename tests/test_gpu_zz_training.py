@@ -145,41 +145,53 @@ def test_graphed_step_equals_eager(cuda):
         # -- the anatomy term's scatter kernels add with atomics -- moves by +-lr at random in any two runs)
 
 
-def test_overlapped_registration_branch_equals_serial(cuda):
+def test_overlapped_branches_equal_serial(cuda):
     """JointModel(overlap_reg=True) runs the registration network on a side stream next to the segmentation passes
-    (forward and, by autograd's stream rule, backward): same loss and gradients as the serial order, eagerly and inside a
-    captured graph (where the two branches become parallel paths)."""
+    (forward and, by autograd's stream rule, backward); overlap_seg=True also the target image's segmentation pass
+    (BatchNorm buffer updates deferred, gradients into the bucket's alternate slots); ops.set_wgrad_overlap puts the
+    convolutions' weight gradients on their own stream.  Same loss, gradients and BatchNorm running statistics as the
+    serial order, eagerly and inside a captured graph (where the branches become parallel paths)."""
+    from deepatlas_b200 import ops
     from deepatlas_b200.dist import FlatGradBucket
     from deepatlas_b200.graph import GraphedStep
     from deepatlas_b200.joint import JointModel, make_synthetic_pair
     n_classes, size = 4, (16, 24, 16)
     batch = make_synthetic_pair(size, n_classes, seed=411, device=cuda)
     out = {}
-    from deepatlas_b200 import ops
-    for mode in ("serial", "overlap", "overlap+graph", "overlap+wgrad", "overlap+wgrad+graph"):
+    modes = ("serial", "reg", "reg+graph", "reg+wgrad", "reg+wgrad+graph", "reg+seg+wgrad", "reg+seg+wgrad+graph")
+    for mode in modes:
         ops.set_wgrad_overlap("wgrad" in mode)   # weight gradients on their own side stream
         torch.manual_seed(230)
-        model = JointModel(n_classes=n_classes, overlap_reg=mode != "serial").to(cuda)
+        model = JointModel(n_classes=n_classes, overlap_reg="reg" in mode, overlap_seg="seg" in mode).to(cuda)
         model.weights_init()
         bucket = FlatGradBucket(model.trainable_parameters())
+        if "seg" in mode:
+            bucket.enable_alt()
 
         def compute(*b):
             bucket.zero()
             loss, _ = model.joint_loss(*b)
             loss.backward()
             model.join_streams()
+            bucket.allreduce(1)          # (single process: joins the weight-gradient stream, folds the alternate slots)
             return loss.detach()
 
+        state = {k: v.clone() for k, v in model.state_dict().items()}
         if mode.endswith("graph"):
-            state = {k: v.clone() for k, v in model.state_dict().items()}
             run = GraphedStep(compute, batch, warmup=2)
             model.load_state_dict(state)     # (the warm-up runs moved the BatchNorm running statistics only)
         else:
             run = compute
         loss = float(run(*batch))
         torch.cuda.synchronize()
-        out[mode] = (loss, bucket.flat.clone())
+        bn = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+        out[mode] = (loss, bucket.flat.clone(), bn)
     ops.set_wgrad_overlap(False)
-    for mode in ("overlap", "overlap+graph", "overlap+wgrad", "overlap+wgrad+graph"):
+    for mode in modes[1:]:
         assert abs(out[mode][0] - out["serial"][0]) <= 1e-6 * abs(out["serial"][0]), mode
         assert rel_err(out[mode][1], out["serial"][1]) < 1e-5, mode
+        for k, v in out["serial"][2].items():
+            if "num_batches" in k:
+                assert int(out[mode][2][k]) == int(v) == 2, (mode, k)     # two passes of the network per step
+            else:
+                assert rel_err(out[mode][2][k], v) < 1e-5, (mode, k)
