@@ -330,7 +330,7 @@ def run_ours(args, wl):
     # the whole step as one CUDA graph (deepatlas_b200/graph.py): eager, the host side of a step (about a thousand launches
     # through Python) is as long as its GPU side; --no-graph times the eager loop
     overlap_on = wl["kind"] == "joint" and not (args.no_overlap or os.environ.get("DA_BENCH_NO_OVERLAP") == "1")
-    overlap_note = "; registration branch and convolution weight gradients on side streams (parallel graph paths)" if overlap_on else ""
+    overlap_note = "; registration branch, the target image's segmentation pass and the convolution weight gradients on side streams (parallel graph paths)" if overlap_on else ""
     gstep, graph_note = None, "eager"
     run = step
     if use_graph:
