@@ -11,6 +11,7 @@ GraphedStep per input shape.  The optimizer must be capturable (``torch.optim.Ad
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Sequence
 
 import torch
@@ -36,7 +37,10 @@ class GraphedStep:
             raise RuntimeError("deepatlas_b200: GraphedStep needs CUDA example inputs (no CPU path exists)")
         self.device = example_inputs[0].device
         self.static_inputs = [t.clone() for t in example_inputs]
-        side = torch.cuda.Stream(device=self.device)
+        # DA_GRAPH_PRIORITY=1 captures the step on a HIGH-priority stream (the priority is recorded in the graph's kernel
+        # nodes, so the chain the step was written on would get free SMs before the branches forked onto side streams).
+        prio = os.environ.get("DA_GRAPH_PRIORITY", "0") == "1"   # measured: 41.84 vs 41.46 ms without -- off
+        side = torch.cuda.Stream(device=self.device, priority=-1 if prio else 0)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(max(int(warmup), 1)):
@@ -48,7 +52,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         l0 = _lib.size("da_launch_count")
         # thread_local: the NCCL watchdog thread polls events while the collective of the step is being captured
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
             self.static_loss = step_fn(*self.static_inputs)
         self.launches_per_step = _lib.size("da_launch_count") - l0   # library kernels inside one replay
         self.eager_tail = eager_tail
