@@ -29,7 +29,8 @@ def timeit(fn):
 
 tot = [0.0, 0.0, 0.0]
 for name, Cin, Cout, (D, H, W) in (("up2 32->32 @80x96x80", 32, 32, (80, 96, 80)), ("up1 64->64 @40x48x40", 64, 64, (40, 48, 40)),
-                                     ("up0 64->64 @20x24x20", 64, 64, (20, 24, 20))):
+                                     ("up0 64->64 @20x24x20", 64, 64, (20, 24, 20))) if not os.environ.get("DA_C2") else (
+        ("dc3 128->128 @64^3", 128, 128, (64, 64, 64)), ("dc6 256->256 @32^3", 256, 256, (32, 32, 32)), ("dc9 512->512 @16^3", 512, 512, (16, 16, 16))):
     x = torch.rand((1, Cin, D, H, W), device=dev)
     w = torch.randn((Cin, Cout, 2, 2, 2), device=dev) * 0.1
     b = torch.zeros(Cout, device=dev)
