@@ -45,6 +45,7 @@ class JointModel(nn.Module):
         self.overlap_seg = bool(overlap_seg)
         self._side = None
         self._side2 = None
+        self._pending = []      # side streams whose backward has not been joined yet
         self.n_classes = n_classes
         self.seg = get_network(seg_name)(in_channel, n_classes, bias=True, BN=True)
         self.reg = get_network("voxel_morph_cvpr")()
@@ -69,10 +70,10 @@ class JointModel(nn.Module):
     def join_streams(self):
         """Make the current stream wait for the side streams (after ``backward()``): the registration branch's and the
         weight-gradient stream of ``ops.set_wgrad_overlap``."""
-        if self.overlap_reg and self._side is not None:
-            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
-        if self.overlap_seg and self._side2 is not None:
-            torch.cuda.current_stream(self._side2.device).wait_stream(self._side2)
+        # (only streams that ran a branch since the last join: see ops.join_wgrad_stream)
+        for st in self._pending:
+            torch.cuda.current_stream(st.device).wait_stream(st)
+        self._pending = []
         ops.join_wgrad_stream()
 
     def _run_reg(self, I_m, I_t):
@@ -89,6 +90,7 @@ class JointModel(nn.Module):
         side.wait_event(self._fork)
         with torch.cuda.stream(side):
             out = branch()
+        self._pending.append(side)
         return out
 
     def _fork_here(self, ref):
@@ -127,6 +129,7 @@ class JointModel(nn.Module):
                 disp, I_w, phi, sim, reg = self._run_reg(I_m, I_t)
                 sup_m, prob_m = self.sup_dice.forward_head(F_m, self.seg.head, S_m, want_probs=True)
                 main.wait_stream(self._side2)
+                self._pending.append(self._side2)
                 sup_t.record_stream(main)
                 pending.apply()      # after the moving pass's own updates (stream order) and the side pass's statistics (join)
             else:

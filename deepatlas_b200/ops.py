@@ -105,6 +105,7 @@ def _grad_dst(p, wanted: bool, slot: int = 0):
 # ``join_wgrad_stream()`` must be called after backward() and before the gradients are read.
 _WGRAD_OVERLAP = False
 _WGRAD_SIDE = {}
+_WGRAD_PENDING = set()   # devices whose side stream holds weight gradients that have not been joined yet
 
 
 def set_wgrad_overlap(on: bool):
@@ -120,10 +121,15 @@ def _wgrad_side(device):
 
 
 def join_wgrad_stream():
-    """The current stream waits for every weight gradient launched on the side stream of the current device."""
-    st = _WGRAD_SIDE.get(torch.cuda.current_device()) if torch.cuda.is_available() else None
-    if st is not None:
-        torch.cuda.current_stream().wait_stream(st)
+    """The current stream waits for every weight gradient launched on the side stream of the current device since the
+    last join.  (Only then: waiting for a side stream that took no part in an ongoing graph capture would tie the capture
+    to uncaptured work -- cudaErrorStreamCaptureIsolation.)"""
+    if not torch.cuda.is_available():
+        return
+    dev = torch.cuda.current_device()
+    if dev in _WGRAD_PENDING:
+        _WGRAD_PENDING.discard(dev)
+        torch.cuda.current_stream().wait_stream(_WGRAD_SIDE[dev])
 
 
 def _check_device(t: torch.Tensor, name: str):
@@ -631,6 +637,7 @@ class Conv3dFunction(torch.autograd.Function):
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 wgrad(_stream(), 1)
+            _WGRAD_PENDING.add(dy.device.index)
             for t in (x1, x2, dy, ctx.amax_x, amax_dy):
                 if t is not None:
                     t.record_stream(side)
