@@ -384,21 +384,29 @@ def run_ours(args, wl):
     # next 1000-node graph); every step's loss is read inside the timed region, the last one after the loop.
     loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_steps(nsteps):
+        last_ = None
+        submit_all()
+        for k in range(nsteps):
+            batch = [t for _ in samples for t in stage.get()]
+            loss_k = run(batch)           # asynchronous: one graph launch (or the eager launches)
+            loss_host[k % 2].copy_(loss_k, non_blocking=True)
+            loss_ready[k % 2].record()
+            if k + 1 < nsteps:
+                submit_all()              # the next step's staging + copies run while this step computes
+            if k > 0:
+                loss_ready[(k - 1) % 2].synchronize()
+                last_ = float(loss_host[(k - 1) % 2])
+        loss_ready[(nsteps - 1) % 2].synchronize()
+        return float(loss_host[(nsteps - 1) % 2])
+
+    # untimed warm-up of this path too (first use of the input stage: lazy loading of its crop kernel, its side stream and
+    # device buffers; on a fresh box this stalled one timed step by 130 ms), then EXACTLY args.steps timed steps
+    e2e_steps(min(args.warmup, 2))
+    barrier()
     f0.record()
-    last = None
-    submit_all()
-    for k in range(args.steps):
-        batch = [t for _ in samples for t in stage.get()]
-        loss_k = run(batch)           # asynchronous: one graph launch (or the eager launches)
-        loss_host[k % 2].copy_(loss_k, non_blocking=True)
-        loss_ready[k % 2].record()
-        if k + 1 < args.steps:
-            submit_all()              # the next step's staging + copies run while this step computes
-        if k > 0:
-            loss_ready[(k - 1) % 2].synchronize()
-            last = float(loss_host[(k - 1) % 2])
-    loss_ready[(args.steps - 1) % 2].synchronize()
-    last = float(loss_host[(args.steps - 1) % 2])
+    last = e2e_steps(args.steps)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps
